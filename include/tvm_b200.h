@@ -1,0 +1,206 @@
+/*
+ * tvm_b200.h -- C ABI of the B200-native PagedKVCache attention kernel set.
+ *
+ * Every entry point replaces one callback that the reference's C++ cache object
+ * (PagedAttentionKVCacheObj, /root/reference/src/runtime/vm/paged_kv_cache.cc) receives
+ * through `vm.builtin.paged_attention_kv_cache_create` (paged_kv_cache.cc:2535-2639).
+ * The reference implements the callbacks as TIR PrimFuncs
+ * (python/tvm/relax/frontend/nn/llm/_{page,decode,prefill}_kernels.py, tree_attn.py,
+ * position_embedding.py); here they are hand-written sm_100a CUDA.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all tensor pointers are DEVICE pointers that already
+ *    include the DLTensor byte_offset; tensors are compact row-major.
+ *  - `dtype` is the element type of q/k/v/o/pages: TVMB200_F16 or TVMB200_BF16.
+ *  - every call is asynchronous on `stream` (a cudaStream_t), never synchronises the device.
+ *  - return value: 0 on success, non-zero on error; the message is in tvmb200_last_error()
+ *    (thread local).  Nothing is launched when an error is returned.
+ *  - there is NO CPU fallback: without a CUDA device every call fails.
+ *
+ * The same library also exports the tvm-ffi packed-function symbols (`__tvm_ffi_<name>`,
+ * TVMFFISafeCallType) with the reference's positional signatures; see INTEGRATION.md.
+ */
+#ifndef TVM_B200_H_
+#define TVM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVMB200_F16 0
+#define TVMB200_BF16 1
+
+/* mask kinds of tvmb200_attention_prefill* (host side picks them from the reference's arguments) */
+#define TVMB200_MASK_NONE 0   /* col < kv_len                                             */
+#define TVMB200_MASK_CAUSAL 1 /* col < kv_len - qo_len + row + 1  (_kernel_common.py:130) */
+
+typedef void* tvmb200_stream_t;
+
+#if defined(__GNUC__)
+#define TVMB200_API __attribute__((visibility("default")))
+#else
+#define TVMB200_API
+#endif
+
+/*! \brief last error message of the calling thread ("" if none). */
+TVMB200_API const char* tvmb200_last_error(void);
+/*! \brief library version string. */
+TVMB200_API const char* tvmb200_version(void);
+/*! \brief number of kernels launched by this library in this process (all threads). */
+TVMB200_API int64_t tvmb200_launch_count(void);
+
+/*!
+ * \brief Pre-size the per-device split-KV workspace (partial O / LSE).  Optional: the workspace grows
+ *        on demand, but growing calls cudaMalloc, which must not happen inside CUDA-graph capture.
+ */
+TVMB200_API int tvmb200_reserve_workspace(int device_id, int64_t bytes);
+
+/*!
+ * \brief Per-layer sliding window size compiled into the reference's `*_sliding_window` prefill
+ *        flavour (kv_cache.py:494,703 `layer_sliding_window_size`, default 1024).  Only used by the
+ *        tvm-ffi symbol `batch_prefill_paged_kv_sliding_window`; the C entry point takes it explicitly.
+ */
+TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
+
+/*!
+ * \brief f_transpose_append  (ctor arg 13; _page_kernels.py:40-74; called paged_kv_cache.cc:1371,1399)
+ *  pages[pos/page_size, 0|1, h, pos%page_size, :] = k|v[t, h, :]  for pos = position_map[t] != -1.
+ *  pages: [num_pages, 2, num_kv_heads, page_size, head_dim]; k, v: [ntoken, num_kv_heads, head_dim].
+ */
+TVMB200_API int tvmb200_transpose_append(void* pages, const void* k, const void* v, const int32_t* position_map,
+                             int64_t ntoken, int64_t num_pages, int32_t num_kv_heads,
+                             int32_t page_size, int32_t head_dim, int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_debug_get_kv  (ctor arg 26; _page_kernels.py:106-136; called paged_kv_cache.cc:1718)
+ *  k_out|v_out[layer_id, p, h, :] = pages[pos/page_size, 0|1, h, pos%page_size, :], pos = position_map[p].
+ *  k_out, v_out: [num_layers, seqlen, num_kv_heads, head_dim].
+ */
+TVMB200_API int tvmb200_debug_get_kv(const void* pages, const int32_t* position_map, void* k_out, void* v_out,
+                         int64_t layer_id, int64_t num_layers, int64_t seqlen, int64_t num_pages,
+                         int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int dtype,
+                         tvmb200_stream_t stream);
+
+/*!
+ * \brief f_copy_single_page  (ctor arg 25; _page_kernels.py:169-189; called paged_kv_cache.cc:728)
+ *  pages[tgt, :, :, 0:copy_length, :] = pages[src, :, :, 0:copy_length, :].
+ */
+TVMB200_API int tvmb200_copy_single_page(void* pages, int64_t src_page_id, int64_t tgt_page_id,
+                             int64_t copy_length, int64_t num_pages, int32_t num_kv_heads,
+                             int32_t page_size, int32_t head_dim, int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_compact_copy  (ctor arg 27; _page_kernels.py:235-263; called paged_kv_cache.cc:759)
+ *  for each sequence b, for i in [indptr[b], indptr[b+1]) IN ORDER: slot dst[i] <- slot src[i]
+ *  (slot = page_id*page_size + offset).  src_dst_pos: [2, total_copy_length].
+ */
+TVMB200_API int tvmb200_compact_kv_copy(void* pages, const int32_t* copy_length_indptr,
+                            const int32_t* copy_src_dst_pos, int32_t batch_size,
+                            int32_t total_copy_length, int64_t num_pages, int32_t num_kv_heads,
+                            int32_t page_size, int32_t head_dim, int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_split_rotary  (ctor arg 24; position_embedding.py:444-565; called paged_kv_cache.cc:1360)
+ *  Split fused qkv [n, Hq+2Hkv, D] into q [n,Hq,D], k,v [n,Hkv,D]; when apply_rope > 0 rotate q and k
+ *  (neox half-split) at position_map[t]: freq = pos*rope_scale / rope_theta^((2d mod rd)/rd).
+ *  rotary_dim <= 0 means head_dim.
+ */
+TVMB200_API int tvmb200_split_rotary(const void* qkv, const int32_t* position_map, void* q, void* k, void* v,
+                         int64_t ntoken, int32_t num_qo_heads, int32_t num_kv_heads,
+                         int32_t head_dim, int32_t rotary_dim, int64_t apply_rope, float rope_scale,
+                         float rope_theta, int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_merge_inplace  (ctor arg 23; _decode_kernels.py:414-526; called paged_kv_cache.cc:2292,2329,1557)
+ *  (V,S) <- merge((V,S),(V',S')) with base-2 LSE.  v, v_other: [N,H,D]; s, s_other: [N,H] float32.
+ */
+TVMB200_API int tvmb200_merge_state_inplace(void* v, float* s, const void* v_other, const float* s_other,
+                                int64_t n, int32_t num_heads, int32_t head_dim, int dtype,
+                                tvmb200_stream_t stream);
+
+/*!
+ * \brief f_attention_decode (+ sliding-window flavour)  (ctor args 17, 19; _decode_kernels.py:49-411;
+ *        adapter attn_backend.h:507-515)
+ *  One query token per sequence against that sequence's paged KV.  Split-KV over CTAs with an
+ *  in-kernel LSE merge pass.  length_info is [B] (sliding_window == 0) or [3,B] (sliding_window != 0).
+ *  lse is base-2; empty KV gives O = 0, lse = -5e4.
+ */
+TVMB200_API int tvmb200_attention_decode(const void* q, const void* pages, const int32_t* page_indptr,
+                             const int32_t* page_values, const int32_t* length_info,
+                             const int32_t* k_rope_pos_offset, const int32_t* q_rope_position,
+                             void* output, float* lse, int32_t batch_size, int32_t nnz_pages,
+                             int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                             int32_t page_size, int32_t head_dim, int sliding_window,
+                             int rotary_mode, float rope_scale, float rope_theta, float sm_scale,
+                             int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_attention_prefill (+ sliding-window flavour)  (ctor args 16, 18; _prefill_kernels.py:54-391;
+ *        adapter attn_backend.h:234-243).  Ragged Q vs paged KV.
+ *  layer_sliding_window_size is the reference's compile-time constant; it only matters when
+ *  sliding_window != 0 and causal > 0 (_kernel_common.py:138-144).
+ */
+TVMB200_API int tvmb200_attention_prefill_paged(const void* q, const int32_t* q_indptr, const void* pages,
+                                    const int32_t* page_indptr, const int32_t* page_values,
+                                    const int32_t* length_info, const int32_t* k_rope_pos_offset,
+                                    const int32_t* q_rope_position, void* output, float* lse,
+                                    int32_t batch_size, int32_t total_q_len, int32_t nnz_pages,
+                                    int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                    int32_t page_size, int32_t head_dim, int sliding_window,
+                                    int32_t layer_sliding_window_size, int causal, int rotary_mode,
+                                    float rope_scale, float rope_theta, float sm_scale, int dtype,
+                                    tvmb200_stream_t stream);
+
+/*!
+ * \brief f_attention_prefill_ragged  (ctor arg 15; _prefill_kernels.py:677-923; adapter
+ *        attn_backend.h:388-396; called paged_kv_cache.cc:2187).  Ragged Q vs ragged K,V.
+ */
+TVMB200_API int tvmb200_attention_prefill_ragged(const void* q, const int32_t* q_indptr, const void* k,
+                                     const void* v, const int32_t* kv_indptr,
+                                     const int32_t* q_rope_position,
+                                     const int32_t* k_rope_pos_offset, void* output, float* lse,
+                                     int32_t batch_size, int32_t total_q_len, int32_t total_kv_len,
+                                     int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_dim,
+                                     int causal, int rotary_mode, float rope_scale,
+                                     float rope_theta, float sm_scale, int dtype,
+                                     tvmb200_stream_t stream);
+
+/*!
+ * \brief f_attention_prefill_with_tree_mask  (ctor arg 21; tree_attn.py:68-603; adapter
+ *        attn_backend.h:665-673).  Ragged self-attention under a token-tree mask.
+ *  mask: [tree_size, 2] int32 rows (dfs_order, subtree_end); mn_indptr: [B+1].
+ */
+TVMB200_API int tvmb200_attention_prefill_tree_ragged(const void* q, const int32_t* q_indptr, const void* k,
+                                          const void* v, const int32_t* kv_indptr,
+                                          const int32_t* q_rope_position, const int32_t* mn_indptr,
+                                          const int32_t* mask, void* output, float* lse,
+                                          int32_t batch_size, int32_t total_q_len,
+                                          int32_t total_kv_len, int32_t num_qo_heads,
+                                          int32_t num_kv_heads, int32_t head_dim, int rotary_mode,
+                                          float rope_scale, float rope_theta, float sm_scale,
+                                          int dtype, tvmb200_stream_t stream);
+
+/*!
+ * \brief f_attention_prefill_with_tree_mask_paged_kv  (ctor arg 20; tree_attn.py:606-1259; adapter
+ *        attn_backend.h:618-627).  Ragged Q vs paged KV, tree mask on the trailing tree_len columns.
+ *  rotary_mode must be 0 (the reference asserts it, tree_attn.py:699,930).
+ */
+TVMB200_API int tvmb200_attention_prefill_tree_paged(const void* q, const int32_t* q_indptr, const void* pages,
+                                         const int32_t* page_indptr, const int32_t* page_values,
+                                         const int32_t* length_info,
+                                         const int32_t* k_rope_pos_offset,
+                                         const int32_t* q_rope_position, void* output, float* lse,
+                                         int32_t batch_size, int32_t total_q_len, int32_t nnz_pages,
+                                         int64_t num_pages, int32_t num_qo_heads,
+                                         int32_t num_kv_heads, int32_t page_size, int32_t head_dim,
+                                         int rotary_mode, float rope_scale, float rope_theta,
+                                         float sm_scale, const int32_t* tree_order_indptr,
+                                         const int32_t* tree_order, int dtype,
+                                         tvmb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVM_B200_H_ */

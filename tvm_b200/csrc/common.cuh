@@ -1,0 +1,271 @@
+// Shared device/host helpers for the B200 (sm_100a) PagedKVCache kernel set.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/tvm_b200.h"
+
+namespace tvmb200 {
+
+// ---------------------------------------------------------------------------------------------
+// host side: error reporting + launch accounting
+// ---------------------------------------------------------------------------------------------
+std::string& last_error_ref();
+int set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+#define TVMB200_CHECK(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) return ::tvmb200::set_error(__VA_ARGS__); \
+  } while (0)
+
+#define TVMB200_CUDA(expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::tvmb200::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__),   \
+                                  __FILE__, __LINE__, #expr);                               \
+  } while (0)
+
+// checks the launch, bumps the launch counter
+#define TVMB200_LAUNCH_OK()                      \
+  do {                                           \
+    TVMB200_CUDA(cudaGetLastError());            \
+    ::tvmb200::g_launch_count.fetch_add(1);      \
+  } while (0)
+
+int num_sms();  // SM count of the current device (cached)
+
+// per-device scratch used by split-KV decode (partial O / LSE / chunk offsets)
+int get_workspace(int64_t bytes, void** out);
+int32_t layer_sliding_window_size();
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kNegInit = -5e4f;  // the reference's running-max sentinel (_decode_kernels.py:134)
+
+template <typename T>
+struct DT;
+template <>
+struct DT<__half> {
+  using T2 = __half2;
+  static __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+  static __device__ __forceinline__ __half from_f(float x) { return __float2half_rn(x); }
+  static __device__ __forceinline__ float2 to_f2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ __half neg(__half x) { return __hneg(x); }
+};
+template <>
+struct DT<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+  static __device__ __forceinline__ float2 to_f2(uint32_t u) {
+    // bf16 -> f32 is a 16-bit shift
+    float2 r;
+    r.x = __uint_as_float(u << 16);
+    r.y = __uint_as_float(u & 0xffff0000u);
+    return r;
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ __nv_bfloat16 neg(__nv_bfloat16 x) { return __hneg(x); }
+};
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_na_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- mbarrier / TMA (cp.async.bulk.tensor) ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0,
+                                            int c1, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- legacy tensor path (mma.sync), used by the HBM-bound decode kernel and the generic prefill ----
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                            uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                                  uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                          uint32_t a3, uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&c)[4], uint32_t a0, uint32_t a1,
+                                                  uint32_t a2, uint32_t a3, uint32_t b0,
+                                                  uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1,
+                                                         uint32_t a2, uint32_t a3, uint32_t b0,
+                                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, bool pred) {
+  int sz = pred ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// RoPE inverse-frequency denominator of the reference: theta^((2d mod rd)/rd)
+// (position_embedding.py:63 rope_freq_default)
+__device__ __forceinline__ float rope_denominator(int d, int rotary_dim, float theta) {
+  return powf(theta, static_cast<float>((d * 2) % rotary_dim) / static_cast<float>(rotary_dim));
+}
+
+// block-wide exclusive scan helper for the device-side work schedulers.  vals in smem [n+1]:
+// on entry s[i] (i<n) holds the count of item i; on exit s[i] = sum_{j<i}, s[n] = total.
+// All threads of the block must call it.  tmp: smem scratch of >= 33 ints.
+__device__ __forceinline__ void block_exclusive_scan(int* s, int n, int* tmp) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (n + nt - 1) / nt;
+  const int beg = min(tid * per, n), end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += s[i];
+  // scan of per-thread sums
+  const int lane = tid & 31, warp = tid >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) tmp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = (nt + 31) >> 5;
+    int w = lane < nw ? tmp[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    tmp[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) tmp[32] = wi;
+  }
+  __syncthreads();
+  int run = tmp[warp] + incl - sum;
+  for (int i = beg; i < end; ++i) {
+    int c = s[i];
+    s[i] = run;
+    run += c;
+  }
+  if (tid == 0) s[n] = tmp[32];
+  __syncthreads();
+}
+
+}  // namespace tvmb200

@@ -1,0 +1,90 @@
+// Library-wide host state: thread-local error string, launch counter, SM count, split-KV workspace.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace tvmb200 {
+
+std::atomic<int64_t> g_launch_count{0};
+static std::atomic<int32_t> g_layer_sliding_window_size{1024};
+
+std::string& last_error_ref() {
+  static thread_local std::string err;
+  return err;
+}
+
+int set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return 1;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+struct Workspace {
+  void* ptr = nullptr;
+  int64_t bytes = 0;
+};
+static Workspace g_ws[64];
+static std::mutex g_ws_mu;
+
+static int ensure_workspace(int dev, int64_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  Workspace& w = g_ws[dev];
+  if (w.bytes < bytes) {
+    // growing is synchronous (cudaFree/cudaMalloc); callers that capture CUDA graphs pre-size the
+    // workspace with tvmb200_reserve_workspace.
+    int64_t want = bytes < (int64_t(8) << 20) ? (int64_t(8) << 20) : bytes + bytes / 4;
+    if (w.ptr) {
+      TVMB200_CUDA(cudaDeviceSynchronize());
+      TVMB200_CUDA(cudaFree(w.ptr));
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    TVMB200_CUDA(cudaMalloc(&w.ptr, static_cast<size_t>(want)));
+    w.bytes = want;
+  }
+  if (out) *out = w.ptr;
+  return 0;
+}
+
+int get_workspace(int64_t bytes, void** out) {
+  int dev = 0;
+  TVMB200_CUDA(cudaGetDevice(&dev));
+  TVMB200_CHECK(dev >= 0 && dev < 64, "device id %d out of range", dev);
+  return ensure_workspace(dev, bytes, out);
+}
+
+int32_t layer_sliding_window_size() { return g_layer_sliding_window_size.load(); }
+
+}  // namespace tvmb200
+
+extern "C" const char* tvmb200_last_error(void) { return tvmb200::last_error_ref().c_str(); }
+extern "C" const char* tvmb200_version(void) { return "tvm_b200 0.1 (sm_100a)"; }
+extern "C" int64_t tvmb200_launch_count(void) { return tvmb200::g_launch_count.load(); }
+extern "C" void tvmb200_set_layer_sliding_window_size(int32_t size) {
+  tvmb200::g_layer_sliding_window_size.store(size);
+}
+extern "C" int tvmb200_reserve_workspace(int device_id, int64_t bytes) {
+  TVMB200_CHECK(device_id >= 0 && device_id < 64, "device id %d out of range", device_id);
+  int prev = 0;
+  TVMB200_CUDA(cudaGetDevice(&prev));
+  TVMB200_CUDA(cudaSetDevice(device_id));
+  int rc = tvmb200::ensure_workspace(device_id, bytes, nullptr);
+  cudaSetDevice(prev);
+  return rc;
+}

@@ -1,0 +1,569 @@
+// Batch decode attention over the paged KV cache (f_attention_decode).
+//
+// Reference: python/tvm/relax/frontend/nn/llm/_decode_kernels.py:49-178 (CPU semantics),
+//            :181-411 (reference GPU schedule: one 512-thread CTA per (seq, kv-head), 8-byte loads,
+//            no split-KV).
+//
+// B200 design (HBM-bound; every KV byte is read from DRAM exactly once):
+//  * a work item is (sequence b, kv head h, chunk of `chunk_pages` pages).  Items are enumerated on
+//    the DEVICE from page_indptr (the callback only gets device arrays), by every CTA redundantly
+//    (block scan in shared memory); a persistent grid of CTAs strides over them (split-KV).
+//  * inside an item each WARP owns an independent TMA pipeline: lane 0 issues
+//    cp.async.bulk.tensor (128B-swizzled boxes of 16 slots x 64 elements; one page/head K block is
+//    4 KiB contiguous in HBM) into the warp's private ring of NSTAGE stages and waits on the warp's
+//    own mbarriers -- there is no CTA-wide barrier in the main loop.
+//  * math runs on the legacy tensor path with the KV tokens as the MMA M dimension:
+//    S^T[16 tok x 8 q] = K[16 x D] . Q^T, online softmax over the token axis with warp shuffles,
+//    O^T[D x 8 q] += V^T[D x 16] . P^T, so the whole GQA group (<= 8 query heads) shares every K/V
+//    byte and the FMA/cvt pressure of a SIMT kernel (which would make this kernel issue-bound on
+//    B200) disappears.  For bf16, P is split into hi+lo bf16 parts so the PV product
+//    keeps ~16 bits of P (the reference keeps P in fp32).
+//  * the warps of an item merge (m, d, O) through shared memory; items that cover a whole sequence
+//    write O/LSE directly, the others write fp32 partials that decode_merge_kernel reduces
+//    (base-2 LSE merge, same arithmetic as f_merge_inplace).
+#include "common.cuh"
+
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+
+namespace tvmb200 {
+
+constexpr int kMaxBatchSmem = 8192;  // page_indptr scan lives in shared memory (sized per launch)
+
+struct DecodeParams {
+  const void* q;               // [B, Hq, D]
+  const int32_t* page_indptr;  // [B+1]
+  const int32_t* page_values;  // [nnz]
+  const int32_t* length_info;  // [B] or [3,B]
+  const int32_t* k_rope_pos_offset;
+  const int32_t* q_rope_position;
+  void* output;        // [B, Hq, D]
+  float* lse;          // [B, Hq]
+  float* part_o;       // [n_chunks_total, Hq, D] fp32 (normalised partial outputs)
+  float* part_lse;     // [n_chunks_total, Hq]
+  int32_t* chunk_off;  // [B+1] exclusive scan of chunks per sequence (written by CTA 0)
+  int batch;
+  int num_qo_heads;
+  int num_kv_heads;
+  int group;  // Hq / Hkv
+  int chunk_pages;
+  int sliding;  // length_info is [3,B]
+  int rotary_mode;
+  float rope_scale;
+  float rope_theta;
+  float scale_log2;  // sm_scale * log2(e)
+};
+
+// shared-memory plan per CTA (dynamic):
+//   [0, NW*NSTAGE*STAGE_BYTES)   K/V stages, 1024-aligned, per warp
+//   then: mbarriers (NW*NSTAGE * 8 B), chunk_off scan (batch+1 ints), scan scratch (40 ints)
+template <int D>
+struct DecodeCfg {
+  static constexpr int kPage = 16;
+  static constexpr int kBlockBytes = kPage * D * 2;        // one K (or V) block of a page/head
+  static constexpr int kStageBytes = 2 * kBlockBytes;      // K + V
+  static constexpr int kHalves = D / 64;                   // 128-byte column groups per row
+  static constexpr int kHalfBytes = kPage * 128;           // 2 KiB per TMA box
+};
+
+template <typename T, int D, int NW, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32)
+decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
+  using Cfg = DecodeCfg<D>;
+  constexpr int KS = D / 16;  // k-steps of QK^T == m-tiles of O^T
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-byte aligned: align by hand
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t stages_base = smem_base + warp * NSTAGE * Cfg::kStageBytes;
+  const uint32_t bars_base = smem_base + NW * NSTAGE * Cfg::kStageBytes;
+  int* s_chunk_off = reinterpret_cast<int*>(smem_gen + NW * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8);
+  int* s_scan_tmp = s_chunk_off + (p.batch + 1);
+  auto bar_addr = [&](int w, int s) -> uint32_t { return bars_base + (w * NSTAGE + s) * 8; };
+
+  // ---- setup: barriers, work enumeration -----------------------------------------------------
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < NW * NSTAGE; ++i) mbar_init(bars_base + i * 8, 1);
+    mbar_fence_init();
+  }
+  const int B = p.batch;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int np = p.page_indptr[b + 1] - p.page_indptr[b];
+    s_chunk_off[b] = max(1, (np + p.chunk_pages - 1) / p.chunk_pages);
+  }
+  __syncthreads();
+  block_exclusive_scan(s_chunk_off, B, s_scan_tmp);
+  const int total_chunks = s_chunk_off[B];
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b <= B; b += blockDim.x) p.chunk_off[b] = s_chunk_off[b];
+  }
+  const int n_items = total_chunks * p.num_kv_heads;
+
+  // per-warp pipeline bookkeeping: number of loads issued / consumed so far (monotonic across items,
+  // so mbarrier phase parity is (count / NSTAGE) & 1)
+  uint32_t n_consumed = 0, n_issued = 0;
+
+  const int g = p.group;
+  const int qrow = lane >> 2;           // query head within the group held by this lane (B-frag n)
+  const int qc0 = (lane & 3) * 2;       // S^T / O^T column pair (query heads qc0, qc0+1)
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int cg = item / p.num_kv_heads;
+    const int h = item - cg * p.num_kv_heads;
+    // binary search: largest b with chunk_off[b] <= cg
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_chunk_off[mid] <= cg) lo = mid; else hi = mid;
+    }
+    const int b = lo;
+    const int chunk = cg - s_chunk_off[b];
+    const int n_chunks_b = s_chunk_off[b + 1] - s_chunk_off[b];
+    const int pg_beg_seq = p.page_indptr[b];
+    const int n_pages_seq = p.page_indptr[b + 1] - pg_beg_seq;
+    const int pg0 = chunk * p.chunk_pages;
+    const int pg1 = min(n_pages_seq, pg0 + p.chunk_pages);
+
+    // sequence length bookkeeping (_kernel_common.py:155-170)
+    int last_page_len, sw_off = 0, sink = 0;
+    if (p.sliding) {
+      last_page_len = p.length_info[b];
+      sw_off = p.length_info[B + b];
+      sink = p.length_info[2 * B + b];
+    } else {
+      last_page_len = p.length_info[b];
+    }
+    const int total_slots = n_pages_seq > 0 ? (n_pages_seq - 1) * Cfg::kPage + last_page_len : 0;
+    // valid slot s (slot = index into the sequence's page list * 16 + offset):
+    //   s < sink   or   sw_off <= s < total_slots          (non-sliding: sink = sw_off = 0)
+    // (kv_len = total_slots - sw_off + sink; position -> slot is pos<sink ? pos : pos-sink+sw_off)
+
+    // ---- Q^T fragments (B operand, [k = d][n = q head]) -----------------------------------------
+    uint32_t qf[KS][2];
+    {
+      const T* qp = static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g + qrow) * D;
+      const bool qv = qrow < g;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int d0 = ks * 16 + (lane & 3) * 2;
+        qf[ks][0] = qv ? *reinterpret_cast<const uint32_t*>(qp + d0) : 0u;
+        qf[ks][1] = qv ? *reinterpret_cast<const uint32_t*>(qp + d0 + 8) : 0u;
+      }
+    }
+
+    float o[KS][4];
+#pragma unroll
+    for (int i = 0; i < KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = kNegInit, m1 = kNegInit;  // running max of columns qc0, qc0+1 (warp-uniform per column)
+    float d0s = 0.f, d1s = 0.f;          // per-lane partial denominators
+
+    // pages of this warp: pg0 + warp, pg0 + warp + NW, ...
+    const int my_n = (pg1 - pg0 - warp + NW - 1) / NW > 0 ? (pg1 - pg0 - warp + NW - 1) / NW : 0;
+    const int32_t* my_pages = p.page_values + pg_beg_seq + pg0 + warp;
+
+    int ids_cache = 0;  // page ids of this warp's pages [32*batch_k, 32*batch_k+32), one per lane
+    int ids_batch = -1;
+    auto page_id_of = [&](int j) -> int {  // warp-uniform j
+      const int bk = j >> 5;
+      if (bk != ids_batch) {
+        const int jj = bk * 32 + lane;
+        ids_cache = jj < my_n ? __ldg(my_pages + static_cast<int64_t>(jj) * NW) : 0;
+        ids_batch = bk;
+      }
+      return __shfl_sync(0xffffffffu, ids_cache, j & 31);
+    };
+    auto issue = [&](int j) {  // all lanes call (shuffle inside); lane 0 issues the TMA
+      const int pid = page_id_of(j);
+      const uint32_t st = n_issued % NSTAGE;
+      if (lane == 0) {
+        const uint32_t bar = bar_addr(warp, st);
+        const uint32_t dst = stages_base + st * Cfg::kStageBytes;
+        mbar_expect_tx(bar, Cfg::kStageBytes);
+        const int row_k = ((pid * 2 + 0) * p.num_kv_heads + h) * Cfg::kPage;
+        const int row_v = ((pid * 2 + 1) * p.num_kv_heads + h) * Cfg::kPage;
+#pragma unroll
+        for (int hf = 0; hf < Cfg::kHalves; ++hf) {
+          tma_load_2d(dst + hf * Cfg::kHalfBytes, &tmap, hf * 64, row_k, bar, kEvictFirst);
+          tma_load_2d(dst + Cfg::kBlockBytes + hf * Cfg::kHalfBytes, &tmap, hf * 64, row_v, bar, kEvictFirst);
+        }
+      }
+      ++n_issued;
+    };
+
+    int issued_here = 0;
+    for (; issued_here < my_n && issued_here < NSTAGE; ++issued_here) issue(issued_here);
+
+    for (int j = 0; j < my_n; ++j) {
+      const uint32_t st = n_consumed % NSTAGE;
+      mbar_wait(bar_addr(warp, st), (n_consumed / NSTAGE) & 1);
+      const uint32_t kb = stages_base + st * Cfg::kStageBytes;
+      const uint32_t vb = kb + Cfg::kBlockBytes;
+
+      // slot validity of this page
+      const int slot0 = (pg0 + warp + j * NW) * Cfg::kPage;
+      uint32_t vmask;  // bit t = slot0 + t is a live KV entry
+      {
+        const int hi_end = min(max(total_slots - slot0, 0), 16);
+        const int lo_beg = min(max(sw_off - slot0, 0), 16);
+        const int sink_end = min(max(sink - slot0, 0), 16);
+        const uint32_t window = ((1u << hi_end) - 1u) & ~((1u << lo_beg) - 1u);
+        const uint32_t sinkm = ((1u << min(sink_end, hi_end)) - 1u);
+        vmask = window | sinkm;
+      }
+      if (vmask != 0xffffu) {
+        // zero the dead V rows so that 0 * garbage cannot produce NaN (rows are 128-byte swizzle
+        // units, so zeroing a whole row is layout independent)
+        for (int r = 0; r < 16; ++r) {
+          if (!((vmask >> r) & 1u)) {
+#pragma unroll
+            for (int hf = 0; hf < Cfg::kHalves; ++hf) {
+              uint32_t a = vb + hf * Cfg::kHalfBytes + r * 128 + lane * 4;
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
+            }
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes before the next TMA refill of this stage
+        __syncwarp();
+      }
+
+      // ---- S^T = K . Q^T ------------------------------------------------------------------------
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int c = ks * 2 + (lane >> 4);
+          const uint32_t addr = kb + (c >> 3) * Cfg::kHalfBytes + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(addr, a0, a1, a2, a3);
+          mma_16816<T>(s, a0, a1, a2, a3, qf[ks][0], qf[ks][1]);
+        }
+      }
+      // s[0],s[1]: token (lane>>2), heads qc0,qc0+1; s[2],s[3]: token (lane>>2)+8
+      {
+        const int t0 = lane >> 2;
+        const bool v0 = (vmask >> t0) & 1u, v1 = (vmask >> (t0 + 8)) & 1u;
+        s[0] = v0 ? s[0] * p.scale_log2 : -INFINITY;
+        s[1] = v0 ? s[1] * p.scale_log2 : -INFINITY;
+        s[2] = v1 ? s[2] * p.scale_log2 : -INFINITY;
+        s[3] = v1 ? s[3] * p.scale_log2 : -INFINITY;
+      }
+      float mx0 = fmaxf(s[0], s[2]), mx1 = fmaxf(s[1], s[3]);
+#pragma unroll
+      for (int o_ = 4; o_ < 32; o_ <<= 1) {
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o_));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o_));
+      }
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      if (__any_sync(0xffffffffu, (mn0 > m0) || (mn1 > m1))) {
+        const float f0 = fast_exp2(m0 - mn0), f1 = fast_exp2(m1 - mn1);
+        d0s *= f0;
+        d1s *= f1;
+#pragma unroll
+        for (int i = 0; i < KS; ++i) {
+          o[i][0] *= f0; o[i][1] *= f1; o[i][2] *= f0; o[i][3] *= f1;
+        }
+        m0 = mn0;
+        m1 = mn1;
+      }
+      const float p0 = fast_exp2(s[0] - m0), p1 = fast_exp2(s[1] - m1);
+      const float p2 = fast_exp2(s[2] - m0), p3 = fast_exp2(s[3] - m1);
+      d0s += p0 + p2;
+      d1s += p1 + p3;
+
+      // ---- P^T as B operand ([k = token][n = head]) via 8x8 transposes --------------------------
+      uint32_t pb0 = movmatrix_trans(DT<T>::pack(p0, p1));
+      uint32_t pb1 = movmatrix_trans(DT<T>::pack(p2, p3));
+      uint32_t pl0 = 0, pl1 = 0;
+      constexpr bool kSplitP = std::is_same<T, __nv_bfloat16>::value;
+      if (kSplitP) {
+        // residuals of the bf16 rounding of P
+        const float2 h01 = DT<T>::to_f2(DT<T>::pack(p0, p1));
+        const float2 h23 = DT<T>::to_f2(DT<T>::pack(p2, p3));
+        pl0 = movmatrix_trans(DT<T>::pack(p0 - h01.x, p1 - h01.y));
+        pl1 = movmatrix_trans(DT<T>::pack(p2 - h23.x, p3 - h23.y));
+      }
+
+      // ---- O^T += V^T . P^T ---------------------------------------------------------------------
+      {
+        const int trow = (lane & 7) + (lane >> 4) * 8;
+#pragma unroll
+        for (int mt = 0; mt < KS; ++mt) {
+          const int c = mt * 2 + ((lane >> 3) & 1);
+          const uint32_t addr = vb + (c >> 3) * Cfg::kHalfBytes + trow * 128 + (((c & 7) ^ (trow & 7)) << 4);
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4_trans(addr, a0, a1, a2, a3);
+          mma_16816<T>(o[mt], a0, a1, a2, a3, pb0, pb1);
+          if (kSplitP) mma_16816<T>(o[mt], a0, a1, a2, a3, pl0, pl1);
+        }
+      }
+      ++n_consumed;
+      __syncwarp();
+      if (issued_here < my_n) {
+        issue(issued_here);
+        ++issued_here;
+      }
+    }
+
+    // ---- merge the NW warps of this item through shared memory --------------------------------
+    // every warp writes into its OWN stage region (its pipeline is drained), layout:
+    //   float O[8 heads][132] (pad 132 -> conflict free), float m[8], float d[8]
+    constexpr int OS = D + 4;
+    static_assert((8 * OS + 16) * 4 <= NSTAGE * Cfg::kStageBytes, "merge scratch must fit in the warp's stages");
+    // reduce per-lane partial denominators over the 8 lanes that share a column
+#pragma unroll
+    for (int o_ = 4; o_ < 32; o_ <<= 1) {
+      d0s += __shfl_xor_sync(0xffffffffu, d0s, o_);
+      d1s += __shfl_xor_sync(0xffffffffu, d1s, o_);
+    }
+    float* my_scr = reinterpret_cast<float*>(smem_gen + warp * NSTAGE * Cfg::kStageBytes);
+#pragma unroll
+    for (int mt = 0; mt < KS; ++mt) {
+      const int dd = mt * 16 + (lane >> 2);
+      my_scr[qc0 * OS + dd] = o[mt][0];
+      my_scr[(qc0 + 1) * OS + dd] = o[mt][1];
+      my_scr[qc0 * OS + dd + 8] = o[mt][2];
+      my_scr[(qc0 + 1) * OS + dd + 8] = o[mt][3];
+    }
+    if (lane < 4) {
+      my_scr[8 * OS + qc0] = m0;
+      my_scr[8 * OS + qc0 + 1] = m1;
+      my_scr[8 * OS + 8 + qc0] = d0s;
+      my_scr[8 * OS + 8 + qc0 + 1] = d1s;
+    }
+    // generic-proxy writes to stage memory must be ordered before the async-proxy (TMA) refill
+    fence_proxy_async();
+    __syncthreads();
+    {
+      // thread -> (head qh, dims): NW*32 threads cover g*D outputs
+      for (int idx = threadIdx.x; idx < g * D; idx += NW * 32) {
+        const int qh = idx / D, dd = idx - qh * D;
+        float mm = kNegInit;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const float* scr = reinterpret_cast<const float*>(smem_gen + w * NSTAGE * Cfg::kStageBytes);
+          mm = fmaxf(mm, scr[8 * OS + qh]);
+        }
+        float acc = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const float* scr = reinterpret_cast<const float*>(smem_gen + w * NSTAGE * Cfg::kStageBytes);
+          const float f = fast_exp2(scr[8 * OS + qh] - mm);
+          acc += scr[qh * OS + dd] * f;
+          den += scr[8 * OS + 8 + qh] * f;
+        }
+        const int hq = h * g + qh;
+        const bool empty = den == 0.f;
+        const float outv = empty ? 0.f : acc / den;
+        const float lsev = empty ? kNegInit : mm + log2f(den);
+        if (n_chunks_b == 1) {
+          static_cast<T*>(p.output)[(static_cast<int64_t>(b) * p.num_qo_heads + hq) * D + dd] = DT<T>::from_f(outv);
+          if (dd == 0) p.lse[static_cast<int64_t>(b) * p.num_qo_heads + hq] = lsev;
+        } else {
+          p.part_o[(static_cast<int64_t>(cg) * p.num_qo_heads + hq) * D + dd] = outv;
+          if (dd == 0) p.part_lse[static_cast<int64_t>(cg) * p.num_qo_heads + hq] = lsev;
+        }
+      }
+    }
+    __syncthreads();  // scratch (= stage memory) is reused by the next item's TMA
+  }
+}
+
+// reduce the partial (O, LSE) of sequences that were split into > 1 chunks.  grid = (B, Hq), D threads.
+template <typename T, int D>
+__global__ void __launch_bounds__(D)
+decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                    const int32_t* __restrict__ chunk_off, T* __restrict__ output,
+                    float* __restrict__ lse, int num_qo_heads) {
+  const int b = blockIdx.x, hq = blockIdx.y, dd = threadIdx.x;
+  const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
+  if (c1 - c0 <= 1) return;
+  float mm = kNegInit;
+  for (int c = c0; c < c1; ++c) mm = fmaxf(mm, part_lse[static_cast<int64_t>(c) * num_qo_heads + hq]);
+  float acc = 0.f, den = 0.f;
+  for (int c = c0; c < c1; ++c) {
+    const float w = exp2f(part_lse[static_cast<int64_t>(c) * num_qo_heads + hq] - mm);
+    acc += w * part_o[(static_cast<int64_t>(c) * num_qo_heads + hq) * D + dd];
+    den += w;
+  }
+  output[(static_cast<int64_t>(b) * num_qo_heads + hq) * D + dd] = DT<T>::from_f(acc / den);
+  if (dd == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = mm + log2f(den);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  });
+  return fn;
+}
+
+// 2-D view of a 16-bit row-major matrix [rows, cols], box = [box_rows, 64 elements], 128B swizzle
+int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                 uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  TVMB200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TVMB200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA needs a 16-byte aligned base pointer");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dtype == TVMB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TVMB200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols;
+  uint32_t box_rows;
+  int dtype;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && dtype == o.dtype;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    return std::hash<const void*>()(k.base) ^ (k.rows * 1315423911u) ^ (k.cols << 7) ^ (k.box_rows << 3) ^ k.dtype;
+  }
+};
+
+int get_tmap_2d_cached(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{base, rows, cols, box_rows, dtype};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  int rc = make_tmap_2d(out, base, dtype, rows, cols, box_rows, 64);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+template <typename T, int D, int NW, int NSTAGE>
+static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
+                         cudaStream_t st) {
+  using Cfg = DecodeCfg<D>;
+  const size_t smem = 1024 + static_cast<size_t>(NW) * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8 +
+                      (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
+  auto kern = decode_kernel<T, D, NW, NSTAGE>;
+  TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<grid, NW * 32, smem, st>>>(tmap, p);
+  TVMB200_LAUNCH_OK();
+  if (need_merge) {
+    decode_merge_kernel<T, D><<<dim3(p.batch, p.num_qo_heads), D, 0, st>>>(
+        p.part_o, p.part_lse, p.chunk_off, static_cast<T*>(p.output), p.lse, p.num_qo_heads);
+    TVMB200_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace tvmb200
+
+using namespace tvmb200;
+
+extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const int32_t* page_indptr,
+                                        const int32_t* page_values, const int32_t* length_info,
+                                        const int32_t* k_rope_pos_offset,
+                                        const int32_t* q_rope_position, void* output, float* lse,
+                                        int32_t batch_size, int32_t nnz_pages, int64_t num_pages,
+                                        int32_t num_qo_heads, int32_t num_kv_heads,
+                                        int32_t page_size, int32_t head_dim, int sliding_window,
+                                        int rotary_mode, float rope_scale, float rope_theta,
+                                        float sm_scale, int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "attention_decode: unsupported dtype %d", dtype);
+  TVMB200_CHECK(page_size == 16, "attention_decode: page_size %d unsupported (the B200 path is built for 16-slot pages)", page_size);
+  TVMB200_CHECK(head_dim == 128 || head_dim == 64, "attention_decode: head_dim %d unsupported (64 or 128)", head_dim);
+  TVMB200_CHECK(num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0, "attention_decode: num_qo_heads %d not a multiple of num_kv_heads %d", num_qo_heads, num_kv_heads);
+  const int group = num_qo_heads / num_kv_heads;
+  TVMB200_CHECK(group <= 8, "attention_decode: GQA group size %d > 8 unsupported", group);
+  TVMB200_CHECK(batch_size <= kMaxBatchSmem, "attention_decode: batch %d exceeds %d", batch_size, kMaxBatchSmem);
+  TVMB200_CHECK(rotary_mode == 0, "attention_decode: inline RoPE (rotary_mode=1) is not implemented in the sm_100a path yet");
+  if (batch_size <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // split-KV plan from host-known sizes only (nnz_pages, batch, heads, SM count)
+  constexpr int NW = 4;
+  const int sms = num_sms();
+  const int ctas_per_sm = 2;
+  const int grid_max = sms * ctas_per_sm;
+  int64_t work = static_cast<int64_t>(nnz_pages) * num_kv_heads;  // (page, head) units
+  int chunk_pages = static_cast<int>((work + static_cast<int64_t>(grid_max) * 8 - 1) / (static_cast<int64_t>(grid_max) * 8));
+  chunk_pages = ((chunk_pages + NW - 1) / NW) * NW;
+  if (chunk_pages < 8) chunk_pages = 8;
+  const bool need_merge = chunk_pages < nnz_pages;  // otherwise every sequence is a single chunk
+  const int64_t max_chunks = static_cast<int64_t>(nnz_pages) / chunk_pages + batch_size;
+  const int64_t n_items_max = max_chunks * num_kv_heads;
+  const int grid = static_cast<int>(n_items_max < grid_max ? n_items_max : grid_max);
+
+  // workspace: chunk_off [B+1] | part_lse [max_chunks, Hq] | part_o [max_chunks, Hq, D]
+  const int64_t off_bytes = ((static_cast<int64_t>(batch_size) + 1) * 4 + 255) / 256 * 256;
+  const int64_t lse_bytes = (max_chunks * num_qo_heads * 4 + 255) / 256 * 256;
+  const int64_t o_bytes = max_chunks * num_qo_heads * head_dim * 4;
+  void* ws = nullptr;
+  if (int rc = get_workspace(off_bytes + lse_bytes + o_bytes, &ws)) return rc;
+
+  DecodeParams p;
+  p.q = q;
+  p.page_indptr = page_indptr;
+  p.page_values = page_values;
+  p.length_info = length_info;
+  p.k_rope_pos_offset = k_rope_pos_offset;
+  p.q_rope_position = q_rope_position;
+  p.output = output;
+  p.lse = lse;
+  p.chunk_off = static_cast<int32_t*>(ws);
+  p.part_lse = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + off_bytes);
+  p.part_o = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + off_bytes + lse_bytes);
+  p.batch = batch_size;
+  p.num_qo_heads = num_qo_heads;
+  p.num_kv_heads = num_kv_heads;
+  p.group = group;
+  p.chunk_pages = chunk_pages;
+  p.sliding = sliding_window ? 1 : 0;
+  p.rotary_mode = rotary_mode;
+  p.rope_scale = rope_scale;
+  p.rope_theta = rope_theta;
+  p.scale_log2 = sm_scale * kLog2e;
+
+  CUtensorMap tmap;
+  const uint64_t rows = static_cast<uint64_t>(num_pages) * 2 * num_kv_heads * page_size;
+  if (int rc = get_tmap_2d_cached(&tmap, pages, dtype, rows, head_dim, 16)) return rc;
+
+  if (dtype == TVMB200_F16) {
+    if (head_dim == 128) return launch_decode<__half, 128, NW, 3>(tmap, p, grid, need_merge, st);
+    return launch_decode<__half, 64, NW, 6>(tmap, p, grid, need_merge, st);
+  } else {
+    if (head_dim == 128) return launch_decode<__nv_bfloat16, 128, NW, 3>(tmap, p, grid, need_merge, st);
+    return launch_decode<__nv_bfloat16, 64, NW, 6>(tmap, p, grid, need_merge, st);
+  }
+}

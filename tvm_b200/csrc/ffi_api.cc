@@ -1,0 +1,641 @@
+// tvm-ffi packed-function layer: every callback of the reference's PagedKVCache is exported as a
+// `__tvm_ffi_<name>` symbol with the TVMFFISafeCallType ABI and the reference's positional argument
+// order (src/runtime/vm/attn_backend.h:234-243, 388-396, 507-515, 618-627, 665-673 and
+// paged_kv_cache.cc:1360-1373, 728, 759, 1718, 2292), then forwarded to the plain C ABI of
+// include/tvm_b200.h.  Only the tvm-ffi *C* API is used (no tvm::ffi C++ templates), so the same
+// .so loads under pip tvm_ffi 0.1.9 and the reference's vendored 0.1.14 (call-ABI type indices
+// are identical).  libtvm_ffi symbols are resolved lazily with dlsym so the library also loads
+// in a process that only uses the plain C ABI.
+//
+// Stream: kernels launch on TVMFFIEnvGetStream(kDLCUDA, device_id), the stream the reference cache
+// switches with DeviceAPI::SetStream (paged_kv_cache.cc:724,755,2352).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <dlpack/dlpack.h>
+#include <tvm/ffi/c_api.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/tvm_b200.h"
+
+namespace tvmb200 {
+int32_t layer_sliding_window_size();
+}
+
+namespace {
+
+typedef void* (*PFN_GetStream)(int32_t, int32_t);
+typedef void (*PFN_SetRaised)(const char*, const char*);
+
+void* ffi_sym(const char* name) {
+  void* s = dlsym(RTLD_DEFAULT, name);
+  if (s) return s;
+  void* h = dlopen("libtvm_ffi.so", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libtvm_ffi.so", RTLD_NOW | RTLD_GLOBAL);
+  return h ? dlsym(h, name) : nullptr;
+}
+
+void* env_stream(int device_id) {
+  static PFN_GetStream fn = reinterpret_cast<PFN_GetStream>(ffi_sym("TVMFFIEnvGetStream"));
+  return fn ? fn(kDLCUDA, device_id) : nullptr;
+}
+
+int raise(const char* kind, const std::string& msg) {
+  static PFN_SetRaised fn = reinterpret_cast<PFN_SetRaised>(ffi_sym("TVMFFIErrorSetRaisedFromCStr"));
+  if (fn) fn(kind, msg.c_str());
+  return -1;
+}
+
+std::string fmt(const char* f, ...) {
+  char buf[768];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+struct Err {
+  std::string kind, msg;
+};
+
+struct Tensor {
+  void* data = nullptr;
+  const DLTensor* t = nullptr;
+  int ndim() const { return t->ndim; }
+  int64_t shape(int i) const { return t->shape[i]; }
+};
+
+// ---- argument decoding (throws Err) -----------------------------------------------------------------
+Tensor arg_tensor(const TVMFFIAny* args, int i, const char* fn, const char* name) {
+  const TVMFFIAny& a = args[i];
+  const DLTensor* t = nullptr;
+  if (a.type_index == kTVMFFIDLTensorPtr) {
+    t = static_cast<const DLTensor*>(a.v_ptr);
+  } else if (a.type_index == kTVMFFITensor) {
+    t = TVMFFITensorGetDLTensorPtr(a.v_obj);
+  } else {
+    throw Err{"TypeError", fmt("%s: argument %d (%s) must be a Tensor, got type index %d", fn, i, name, a.type_index)};
+  }
+  if (t->strides != nullptr) {
+    int64_t expect = 1;
+    for (int d = t->ndim - 1; d >= 0; --d) {
+      if (t->shape[d] != 1 && t->strides[d] != expect)
+        throw Err{"ValueError", fmt("%s: argument %d (%s) must be compact row-major", fn, i, name)};
+      expect *= t->shape[d];
+    }
+  }
+  Tensor r;
+  r.t = t;
+  r.data = static_cast<char*>(t->data) + t->byte_offset;
+  return r;
+}
+
+int64_t arg_int(const TVMFFIAny* args, int i, const char* fn, const char* name) {
+  const TVMFFIAny& a = args[i];
+  if (a.type_index == kTVMFFIInt || a.type_index == kTVMFFIBool) return a.v_int64;
+  throw Err{"TypeError", fmt("%s: argument %d (%s) must be an int, got type index %d", fn, i, name, a.type_index)};
+}
+
+// the TIR binder also accepts an int for a float parameter (tvm_ffi_binder.cc:488-534)
+double arg_float(const TVMFFIAny* args, int i, const char* fn, const char* name) {
+  const TVMFFIAny& a = args[i];
+  if (a.type_index == kTVMFFIFloat) return a.v_float64;
+  if (a.type_index == kTVMFFIInt || a.type_index == kTVMFFIBool) return static_cast<double>(a.v_int64);
+  throw Err{"TypeError", fmt("%s: argument %d (%s) must be a float, got type index %d", fn, i, name, a.type_index)};
+}
+
+void expect_nargs(int got, int want, const char* fn) {
+  if (got != want) throw Err{"TypeError", fmt("%s expects %d arguments, got %d", fn, want, got)};
+}
+
+int kv_dtype(const Tensor& x, const char* fn, const char* name) {
+  const DLDataType d = x.t->dtype;
+  if (d.lanes == 1 && d.bits == 16 && d.code == kDLFloat) return TVMB200_F16;
+  if (d.lanes == 1 && d.bits == 16 && d.code == kDLBfloat) return TVMB200_BF16;
+  throw Err{"ValueError", fmt("%s: %s has dtype (code %d, bits %d); the sm_100a kernels support float16 and bfloat16", fn, name, d.code, d.bits)};
+}
+void expect_dtype(const Tensor& x, int code, int bits, const char* fn, const char* name, const char* what) {
+  const DLDataType d = x.t->dtype;
+  if (!(d.lanes == 1 && d.bits == bits && d.code == code))
+    throw Err{"ValueError", fmt("%s: %s must be %s", fn, name, what)};
+}
+void expect_i32(const Tensor& x, const char* fn, const char* name) { expect_dtype(x, kDLInt, 32, fn, name, "int32"); }
+void expect_f32(const Tensor& x, const char* fn, const char* name) { expect_dtype(x, kDLFloat, 32, fn, name, "float32"); }
+void expect_ndim(const Tensor& x, int nd, const char* fn, const char* name) {
+  if (x.ndim() != nd) throw Err{"ValueError", fmt("%s: %s.ndim is expected to equal %d, got %d", fn, name, nd, x.ndim())};
+}
+void expect_shape(bool ok, const char* fn, const char* what) {
+  if (!ok) throw Err{"ValueError", fmt("%s: shape mismatch: %s", fn, what)};
+}
+void expect_same_dtype(const Tensor& a, const Tensor& b, const char* fn, const char* what) {
+  if (a.t->dtype.code != b.t->dtype.code || a.t->dtype.bits != b.t->dtype.bits)
+    throw Err{"ValueError", fmt("%s: dtype mismatch: %s", fn, what)};
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int dev;
+  explicit DeviceGuard(const Tensor& x, const char* fn) {
+    const DLDevice d = x.t->device;
+    if (d.device_type != kDLCUDA && d.device_type != kDLCUDAManaged)
+      throw Err{"ValueError", fmt("%s: tensors must live on a CUDA device (device_type %d); there is no CPU fallback", fn, d.device_type)};
+    dev = d.device_id;
+    if (cudaGetDevice(&prev) != cudaSuccess)
+      throw Err{"RuntimeError", fmt("%s: no usable CUDA device: %s", fn, cudaGetErrorString(cudaGetLastError()))};
+    if (prev != dev) {
+      cudaSetDevice(dev);
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+void expect_same_device(const Tensor& a, const Tensor& b, const char* fn, const char* name) {
+  if (a.t->device.device_type != b.t->device.device_type || a.t->device.device_id != b.t->device.device_id)
+    throw Err{"ValueError", fmt("%s: %s is on a different device", fn, name)};
+}
+
+void check_rc(int rc) {
+  if (rc != 0) throw Err{"RuntimeError", tvmb200_last_error()};
+}
+
+struct PagesInfo {
+  int64_t num_pages;
+  int hkv, page_size, d, dtype;
+};
+PagesInfo pages_info(const Tensor& pages, const char* fn) {
+  expect_ndim(pages, 5, fn, "pages");
+  expect_shape(pages.shape(1) == 2, fn, "pages.shape[1] must be 2");
+  PagesInfo pi;
+  pi.num_pages = pages.shape(0);
+  pi.hkv = static_cast<int>(pages.shape(2));
+  pi.page_size = static_cast<int>(pages.shape(3));
+  pi.d = static_cast<int>(pages.shape(4));
+  pi.dtype = kv_dtype(pages, fn, "pages");
+  return pi;
+}
+
+#define TVMB200_FFI_BEGIN() try {
+#define TVMB200_FFI_END()                                   \
+    if (result) { result->type_index = kTVMFFINone; result->zero_padding = 0; result->v_int64 = 0; } \
+    return 0;                                               \
+  } catch (const Err& e) {                                  \
+    return raise(e.kind.c_str(), e.msg);                    \
+  } catch (const std::exception& e) {                       \
+    return raise("RuntimeError", e.what());                 \
+  }
+
+// ---- the callbacks --------------------------------------------------------------------------------
+
+// (pages, k_data, v_data, position_map)
+int impl_transpose_append(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "tir_kv_cache_transpose_append";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 4, fn);
+  Tensor pages = arg_tensor(args, 0, fn, "pages"), k = arg_tensor(args, 1, fn, "k_data"),
+         v = arg_tensor(args, 2, fn, "v_data"), pm = arg_tensor(args, 3, fn, "position_map");
+  PagesInfo pi = pages_info(pages, fn);
+  expect_ndim(k, 3, fn, "k_data");
+  expect_ndim(v, 3, fn, "v_data");
+  expect_ndim(pm, 1, fn, "position_map");
+  expect_i32(pm, fn, "position_map");
+  expect_same_dtype(pages, k, fn, "k_data vs pages");
+  expect_same_dtype(pages, v, fn, "v_data vs pages");
+  const int64_t nt = k.shape(0);
+  expect_shape(k.shape(1) == pi.hkv && k.shape(2) == pi.d, fn, "k_data must be [ntoken, num_kv_heads, head_dim]");
+  expect_shape(v.shape(0) == nt && v.shape(1) == pi.hkv && v.shape(2) == pi.d, fn, "v_data must match k_data");
+  expect_shape(pm.shape(0) == nt, fn, "position_map must be [ntoken]");
+  DeviceGuard g(pages, fn);
+  expect_same_device(pages, k, fn, "k_data");
+  expect_same_device(pages, v, fn, "v_data");
+  expect_same_device(pages, pm, fn, "position_map");
+  check_rc(tvmb200_transpose_append(pages.data, k.data, v.data, static_cast<const int32_t*>(pm.data), nt,
+                                    pi.num_pages, pi.hkv, pi.page_size, pi.d, pi.dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (pages, position_map, k_data, v_data, layer_id)
+int impl_debug_get_kv(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "tir_kv_cache_debug_get_kv";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 5, fn);
+  Tensor pages = arg_tensor(args, 0, fn, "pages"), pm = arg_tensor(args, 1, fn, "position_map"),
+         k = arg_tensor(args, 2, fn, "k_data"), v = arg_tensor(args, 3, fn, "v_data");
+  const int64_t layer_id = arg_int(args, 4, fn, "layer_id");
+  PagesInfo pi = pages_info(pages, fn);
+  expect_ndim(k, 4, fn, "k_data");
+  expect_ndim(v, 4, fn, "v_data");
+  expect_ndim(pm, 1, fn, "position_map");
+  expect_i32(pm, fn, "position_map");
+  expect_same_dtype(pages, k, fn, "k_data vs pages");
+  expect_same_dtype(pages, v, fn, "v_data vs pages");
+  const int64_t layers = k.shape(0), seqlen = k.shape(1);
+  expect_shape(k.shape(2) == pi.hkv && k.shape(3) == pi.d, fn, "k_data must be [layers, seqlen, num_kv_heads, head_dim]");
+  expect_shape(v.shape(0) == layers && v.shape(1) == seqlen && v.shape(2) == pi.hkv && v.shape(3) == pi.d, fn, "v_data must match k_data");
+  expect_shape(pm.shape(0) == seqlen, fn, "position_map must be [seqlen]");
+  DeviceGuard g(pages, fn);
+  check_rc(tvmb200_debug_get_kv(pages.data, static_cast<const int32_t*>(pm.data), k.data, v.data, layer_id, layers,
+                                seqlen, pi.num_pages, pi.hkv, pi.page_size, pi.d, pi.dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (pages, src_page_id, tgt_page_id, copy_length)
+int impl_copy_single_page(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "copy_single_page";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 4, fn);
+  Tensor pages = arg_tensor(args, 0, fn, "pages");
+  const int64_t src = arg_int(args, 1, fn, "src_page_id"), tgt = arg_int(args, 2, fn, "tgt_page_id"),
+                len = arg_int(args, 3, fn, "copy_length");
+  PagesInfo pi = pages_info(pages, fn);
+  DeviceGuard g(pages, fn);
+  check_rc(tvmb200_copy_single_page(pages.data, src, tgt, len, pi.num_pages, pi.hkv, pi.page_size, pi.d, pi.dtype,
+                                    env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (pages, copy_length_indptr, copy_src_dst_pos, batch_size)
+int impl_compact_kv_copy(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "compact_kv_copy";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 4, fn);
+  Tensor pages = arg_tensor(args, 0, fn, "pages"), ip = arg_tensor(args, 1, fn, "copy_length_indptr"),
+         sd = arg_tensor(args, 2, fn, "copy_src_dst_pos");
+  const int64_t batch = arg_int(args, 3, fn, "batch_size");
+  PagesInfo pi = pages_info(pages, fn);
+  expect_ndim(ip, 1, fn, "copy_length_indptr");
+  expect_ndim(sd, 2, fn, "copy_src_dst_pos");
+  expect_i32(ip, fn, "copy_length_indptr");
+  expect_i32(sd, fn, "copy_src_dst_pos");
+  expect_shape(ip.shape(0) == batch + 1, fn, "copy_length_indptr must be [batch_size + 1]");
+  expect_shape(sd.shape(0) == 2, fn, "copy_src_dst_pos must be [2, total_copy_length]");
+  DeviceGuard g(pages, fn);
+  check_rc(tvmb200_compact_kv_copy(pages.data, static_cast<const int32_t*>(ip.data),
+                                   static_cast<const int32_t*>(sd.data), static_cast<int32_t>(batch),
+                                   static_cast<int32_t>(sd.shape(1)), pi.num_pages, pi.hkv, pi.page_size, pi.d,
+                                   pi.dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (qkv, position_map, q, k, v, apply_rope)     rope theta/scale are module state (see set_rope_params)
+float g_rope_theta = 10000.0f, g_rope_scale = 1.0f;
+int g_rotary_dim = 0;
+int impl_fused_rope(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "fused_rope";
+  TVMB200_FFI_BEGIN();
+  // 6 arguments = the reference signature (theta/scale/rotary_dim from module state);
+  // 9 arguments = explicit (..., apply_rope, rope_theta, rope_scale, rotary_dim) used by our own host
+  if (n != 6 && n != 9) throw Err{"TypeError", fmt("%s expects 6 (or 9) arguments, got %d", fn, n)};
+  float theta = g_rope_theta, scale = g_rope_scale;
+  int rotary_dim = g_rotary_dim;
+  if (n == 9) {
+    theta = static_cast<float>(arg_float(args, 6, fn, "rope_theta"));
+    scale = static_cast<float>(arg_float(args, 7, fn, "rope_scale"));
+    rotary_dim = static_cast<int>(arg_int(args, 8, fn, "rotary_dim"));
+  }
+  Tensor qkv = arg_tensor(args, 0, fn, "qkv"), pm = arg_tensor(args, 1, fn, "position_map"),
+         q = arg_tensor(args, 2, fn, "q"), k = arg_tensor(args, 3, fn, "k"), v = arg_tensor(args, 4, fn, "v");
+  const int64_t apply_rope = arg_int(args, 5, fn, "apply_rope");
+  expect_ndim(qkv, 3, fn, "qkv");
+  expect_ndim(q, 3, fn, "q");
+  expect_ndim(k, 3, fn, "k");
+  expect_ndim(v, 3, fn, "v");
+  expect_ndim(pm, 1, fn, "position_map");
+  expect_i32(pm, fn, "position_map");
+  const int dtype = kv_dtype(qkv, fn, "qkv");
+  expect_same_dtype(qkv, q, fn, "q vs qkv");
+  expect_same_dtype(qkv, k, fn, "k vs qkv");
+  expect_same_dtype(qkv, v, fn, "v vs qkv");
+  const int64_t nt = qkv.shape(0);
+  const int hq = static_cast<int>(q.shape(1)), hkv = static_cast<int>(k.shape(1)), d = static_cast<int>(qkv.shape(2));
+  expect_shape(qkv.shape(1) == hq + 2 * hkv, fn, "qkv.shape[1] must equal num_q_heads + 2*num_kv_heads");
+  expect_shape(q.shape(0) == nt && q.shape(2) == d, fn, "q must be [seq_len, num_q_heads, head_dim]");
+  expect_shape(k.shape(0) == nt && k.shape(2) == d, fn, "k must be [seq_len, num_kv_heads, head_dim]");
+  expect_shape(v.shape(0) == nt && v.shape(1) == hkv && v.shape(2) == d, fn, "v must be [seq_len, num_kv_heads, head_dim]");
+  expect_shape(pm.shape(0) == nt, fn, "position_map must be [seq_len]");
+  DeviceGuard g(qkv, fn);
+  check_rc(tvmb200_split_rotary(qkv.data, static_cast<const int32_t*>(pm.data), q.data, k.data, v.data, nt, hq, hkv,
+                                d, rotary_dim, apply_rope, scale, theta, dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (theta, scale[, rotary_dim]) -- the reference bakes these into the fused_rope PrimFunc when it is
+// built (position_embedding.py:444-452); a loaded .so needs them as state.
+int impl_set_rope_params(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "set_rope_params";
+  TVMB200_FFI_BEGIN();
+  if (n != 2 && n != 3) throw Err{"TypeError", "set_rope_params expects (theta, scale[, rotary_dim])"};
+  g_rope_theta = static_cast<float>(arg_float(args, 0, fn, "theta"));
+  g_rope_scale = static_cast<float>(arg_float(args, 1, fn, "scale"));
+  g_rotary_dim = n == 3 ? static_cast<int>(arg_int(args, 2, fn, "rotary_dim")) : 0;
+  TVMB200_FFI_END();
+}
+
+// (layer_sliding_window_size)
+int impl_set_layer_sliding_window_size(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "set_layer_sliding_window_size";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 1, fn);
+  tvmb200_set_layer_sliding_window_size(static_cast<int32_t>(arg_int(args, 0, fn, "size")));
+  TVMB200_FFI_END();
+}
+
+// (v, s, v_other, s_other)
+int impl_merge_state_inplace(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "merge_state_inplace";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 4, fn);
+  Tensor v = arg_tensor(args, 0, fn, "v"), s = arg_tensor(args, 1, fn, "s"), vo = arg_tensor(args, 2, fn, "v_other"),
+         so = arg_tensor(args, 3, fn, "s_other");
+  expect_ndim(v, 3, fn, "v");
+  expect_ndim(s, 2, fn, "s");
+  expect_ndim(vo, 3, fn, "v_other");
+  expect_ndim(so, 2, fn, "s_other");
+  const int dtype = kv_dtype(v, fn, "v");
+  expect_same_dtype(v, vo, fn, "v_other vs v");
+  expect_f32(s, fn, "s");
+  expect_f32(so, fn, "s_other");
+  const int64_t N = v.shape(0);
+  const int H = static_cast<int>(v.shape(1)), D = static_cast<int>(v.shape(2));
+  expect_shape(vo.shape(0) == N && vo.shape(1) == H && vo.shape(2) == D, fn, "v_other must match v");
+  expect_shape(s.shape(0) == N && s.shape(1) == H && so.shape(0) == N && so.shape(1) == H, fn, "s, s_other must be [N, H]");
+  DeviceGuard g(v, fn);
+  check_rc(tvmb200_merge_state_inplace(v.data, static_cast<float*>(s.data), vo.data, static_cast<const float*>(so.data),
+                                       N, H, D, dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+struct PagedArgs {
+  Tensor pages, page_indptr, page_values, length_info, k_rope_pos_offset;
+  PagesInfo pi;
+  int batch, nnz, sliding;
+};
+PagedArgs paged_args(const TVMFFIAny* args, int i0, const char* fn) {
+  PagedArgs a;
+  a.pages = arg_tensor(args, i0, fn, "pages");
+  a.page_indptr = arg_tensor(args, i0 + 1, fn, "page_indptr");
+  a.page_values = arg_tensor(args, i0 + 2, fn, "page_values");
+  a.length_info = arg_tensor(args, i0 + 3, fn, "length_info");
+  a.k_rope_pos_offset = arg_tensor(args, i0 + 4, fn, "k_rope_pos_offset");
+  a.pi = pages_info(a.pages, fn);
+  expect_ndim(a.page_indptr, 1, fn, "page_indptr");
+  expect_ndim(a.page_values, 1, fn, "page_values");
+  expect_ndim(a.k_rope_pos_offset, 1, fn, "k_rope_pos_offset");
+  expect_i32(a.page_indptr, fn, "page_indptr");
+  expect_i32(a.page_values, fn, "page_values");
+  expect_i32(a.length_info, fn, "length_info");
+  expect_i32(a.k_rope_pos_offset, fn, "k_rope_pos_offset");
+  a.batch = static_cast<int>(a.page_indptr.shape(0)) - 1;
+  a.nnz = static_cast<int>(a.page_values.shape(0));
+  // [B] for a cache built without sliding-window support, [3,B] otherwise (paged_kv_cache.cc:2443-2452)
+  if (a.length_info.ndim() == 1) {
+    a.sliding = 0;
+    expect_shape(a.length_info.shape(0) == a.batch, fn, "length_info must be [batch_size]");
+  } else if (a.length_info.ndim() == 2) {
+    a.sliding = 1;
+    expect_shape(a.length_info.shape(0) == 3 && a.length_info.shape(1) == a.batch, fn, "length_info must be [3, batch_size]");
+  } else {
+    throw Err{"ValueError", fmt("%s: length_info.ndim is expected to equal 1 or 2", fn)};
+  }
+  expect_shape(a.k_rope_pos_offset.shape(0) == a.batch, fn, "k_rope_pos_offset must be [batch_size]");
+  return a;
+}
+
+// (q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
+//  rotary_mode, rope_scale, rope_theta, sm_scale)
+int impl_decode(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "batch_decode_paged_kv";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 13, fn);
+  Tensor q = arg_tensor(args, 0, fn, "Q");
+  PagedArgs pa = paged_args(args, 1, fn);
+  Tensor qpos = arg_tensor(args, 6, fn, "q_rope_position"), out = arg_tensor(args, 7, fn, "output"),
+         lse = arg_tensor(args, 8, fn, "lse");
+  const int rotary_mode = static_cast<int>(arg_int(args, 9, fn, "rotary_mode"));
+  const float rope_scale = static_cast<float>(arg_float(args, 10, fn, "rope_scale"));
+  const float rope_theta = static_cast<float>(arg_float(args, 11, fn, "rope_theta"));
+  const float sm_scale = static_cast<float>(arg_float(args, 12, fn, "sm_scale"));
+  expect_ndim(q, 3, fn, "Q");
+  expect_ndim(out, 3, fn, "output");
+  expect_ndim(lse, 2, fn, "lse");
+  expect_ndim(qpos, 1, fn, "q_rope_position");
+  expect_i32(qpos, fn, "q_rope_position");
+  expect_f32(lse, fn, "lse");
+  expect_same_dtype(pa.pages, q, fn, "Q vs pages");
+  expect_same_dtype(pa.pages, out, fn, "output vs pages");
+  const int B = static_cast<int>(q.shape(0)), hq = static_cast<int>(q.shape(1));
+  expect_shape(B == pa.batch, fn, "page_indptr must be [batch_size + 1]");
+  expect_shape(q.shape(2) == pa.pi.d, fn, "Q.shape[2] must equal head_dim of pages");
+  expect_shape(out.shape(0) == B && out.shape(1) == hq && out.shape(2) == pa.pi.d, fn, "output must match Q");
+  expect_shape(lse.shape(0) == B && lse.shape(1) == hq, fn, "lse must be [batch_size, num_qo_heads]");
+  expect_shape(qpos.shape(0) == B, fn, "q_rope_position must be [batch_size]");
+  DeviceGuard g(q, fn);
+  expect_same_device(q, pa.pages, fn, "pages");
+  expect_same_device(q, out, fn, "output");
+  check_rc(tvmb200_attention_decode(
+      q.data, pa.pages.data, static_cast<const int32_t*>(pa.page_indptr.data),
+      static_cast<const int32_t*>(pa.page_values.data), static_cast<const int32_t*>(pa.length_info.data),
+      static_cast<const int32_t*>(pa.k_rope_pos_offset.data), static_cast<const int32_t*>(qpos.data), out.data,
+      static_cast<float*>(lse.data), B, pa.nnz, pa.pi.num_pages, hq, pa.pi.hkv, pa.pi.page_size, pa.pi.d,
+      pa.sliding, rotary_mode, rope_scale, rope_theta, sm_scale, pa.pi.dtype, env_stream(g.dev)));
+  TVMB200_FFI_END();
+}
+
+// (q, q_indptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position,
+//  output, lse, causal, rotary_mode, rope_scale, rope_theta, sm_scale)
+// tree flavour: (..., output, lse, rotary_mode, rope_scale, rope_theta, sm_scale, tree_indptr, tree_order)
+int prefill_paged_common(const TVMFFIAny* args, int32_t n, TVMFFIAny* result, bool tree, const char* fn) {
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, tree ? 16 : 15, fn);
+  Tensor q = arg_tensor(args, 0, fn, "q"), qi = arg_tensor(args, 1, fn, "q_indptr");
+  PagedArgs pa = paged_args(args, 2, fn);
+  Tensor qpos = arg_tensor(args, 7, fn, "q_rope_position"), out = arg_tensor(args, 8, fn, "output"),
+         lse = arg_tensor(args, 9, fn, "lse");
+  int causal = 0, i = 10;
+  if (!tree) causal = static_cast<int>(arg_int(args, i++, fn, "causal"));
+  const int rotary_mode = static_cast<int>(arg_int(args, i++, fn, "rotary_mode"));
+  const float rope_scale = static_cast<float>(arg_float(args, i++, fn, "rope_scale"));
+  const float rope_theta = static_cast<float>(arg_float(args, i++, fn, "rope_theta"));
+  const float sm_scale = static_cast<float>(arg_float(args, i++, fn, "sm_scale"));
+  expect_ndim(q, 3, fn, "q");
+  expect_ndim(qi, 1, fn, "q_indptr");
+  expect_ndim(out, 3, fn, "output");
+  expect_ndim(lse, 2, fn, "lse");
+  expect_ndim(qpos, 1, fn, "q_rope_position");
+  expect_i32(qi, fn, "q_indptr");
+  expect_i32(qpos, fn, "q_rope_position");
+  expect_f32(lse, fn, "lse");
+  expect_same_dtype(pa.pages, q, fn, "q vs pages");
+  expect_same_dtype(pa.pages, out, fn, "output vs pages");
+  const int total = static_cast<int>(q.shape(0)), hq = static_cast<int>(q.shape(1));
+  expect_shape(qi.shape(0) == pa.batch + 1, fn, "q_indptr and page_indptr must both be [batch_size + 1]");
+  expect_shape(q.shape(2) == pa.pi.d, fn, "q.shape[2] must equal head_dim of pages");
+  expect_shape(out.shape(0) == total && out.shape(1) == hq && out.shape(2) == pa.pi.d, fn, "output must match q");
+  expect_shape(lse.shape(0) == total && lse.shape(1) == hq, fn, "lse must be [total_len, num_qo_heads]");
+  expect_shape(qpos.shape(0) == total, fn, "q_rope_position must be [total_len]");
+  DeviceGuard g(q, fn);
+  expect_same_device(q, pa.pages, fn, "pages");
+  if (tree) {
+    Tensor ti = arg_tensor(args, i++, fn, "tree_order_indptr"), to = arg_tensor(args, i++, fn, "tree_order");
+    expect_i32(ti, fn, "tree_order_indptr");
+    expect_i32(to, fn, "tree_order");
+    expect_ndim(ti, 1, fn, "tree_order_indptr");
+    expect_ndim(to, 2, fn, "tree_order");
+    expect_shape(ti.shape(0) == pa.batch + 1 && to.shape(1) == 2, fn, "tree_order_indptr [batch_size+1], tree_order [tree_size, 2]");
+    check_rc(tvmb200_attention_prefill_tree_paged(
+        q.data, static_cast<const int32_t*>(qi.data), pa.pages.data, static_cast<const int32_t*>(pa.page_indptr.data),
+        static_cast<const int32_t*>(pa.page_values.data), static_cast<const int32_t*>(pa.length_info.data),
+        static_cast<const int32_t*>(pa.k_rope_pos_offset.data), static_cast<const int32_t*>(qpos.data), out.data,
+        static_cast<float*>(lse.data), pa.batch, total, pa.nnz, pa.pi.num_pages, hq, pa.pi.hkv, pa.pi.page_size,
+        pa.pi.d, rotary_mode, rope_scale, rope_theta, sm_scale, static_cast<const int32_t*>(ti.data),
+        static_cast<const int32_t*>(to.data), pa.pi.dtype, env_stream(g.dev)));
+  } else {
+    check_rc(tvmb200_attention_prefill_paged(
+        q.data, static_cast<const int32_t*>(qi.data), pa.pages.data, static_cast<const int32_t*>(pa.page_indptr.data),
+        static_cast<const int32_t*>(pa.page_values.data), static_cast<const int32_t*>(pa.length_info.data),
+        static_cast<const int32_t*>(pa.k_rope_pos_offset.data), static_cast<const int32_t*>(qpos.data), out.data,
+        static_cast<float*>(lse.data), pa.batch, total, pa.nnz, pa.pi.num_pages, hq, pa.pi.hkv, pa.pi.page_size,
+        pa.pi.d, pa.sliding, tvmb200::layer_sliding_window_size(), causal, rotary_mode, rope_scale, rope_theta,
+        sm_scale, pa.pi.dtype, env_stream(g.dev)));
+  }
+  TVMB200_FFI_END();
+}
+int impl_prefill_paged(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  return prefill_paged_common(args, n, result, false, "batch_prefill_paged_kv");
+}
+int impl_tree_paged(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  return prefill_paged_common(args, n, result, true, "tree_attn_paged_kv");
+}
+
+// ragged: (q, q_indptr, k, v, kv_indptr, q_rope_position, k_rope_pos_offset, output, lse,
+//          causal, rotary_mode, rope_scale, rope_theta, sm_scale)
+// tree:   (q, q_indptr, k, v, kv_indptr, q_rope_position, mn_indptr, mask, output, lse,
+//          rotary_mode, rope_scale, rope_theta, sm_scale)
+int prefill_ragged_common(const TVMFFIAny* args, int32_t n, TVMFFIAny* result, bool tree, const char* fn) {
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 14, fn);
+  Tensor q = arg_tensor(args, 0, fn, "q"), qi = arg_tensor(args, 1, fn, "q_indptr"), k = arg_tensor(args, 2, fn, "k"),
+         v = arg_tensor(args, 3, fn, "v"), ki = arg_tensor(args, 4, fn, "kv_indptr"),
+         qpos = arg_tensor(args, 5, fn, "q_rope_position");
+  int i = 6;
+  Tensor a6 = arg_tensor(args, i++, fn, tree ? "mn_indptr" : "k_rope_pos_offset");
+  Tensor mask;
+  if (tree) mask = arg_tensor(args, i++, fn, "mask");
+  Tensor out = arg_tensor(args, i++, fn, "output"), lse = arg_tensor(args, i++, fn, "lse");
+  int causal = 0;
+  if (!tree) causal = static_cast<int>(arg_int(args, i++, fn, "causal"));
+  const int rotary_mode = static_cast<int>(arg_int(args, i++, fn, "rotary_mode"));
+  const float rope_scale = static_cast<float>(arg_float(args, i++, fn, "rope_scale"));
+  const float rope_theta = static_cast<float>(arg_float(args, i++, fn, "rope_theta"));
+  const float sm_scale = static_cast<float>(arg_float(args, i++, fn, "sm_scale"));
+  expect_ndim(q, 3, fn, "q");
+  expect_ndim(k, 3, fn, "k");
+  expect_ndim(v, 3, fn, "v");
+  expect_ndim(qi, 1, fn, "q_indptr");
+  expect_ndim(ki, 1, fn, "kv_indptr");
+  expect_ndim(qpos, 1, fn, "q_rope_position");
+  expect_ndim(out, 3, fn, "output");
+  expect_ndim(lse, 2, fn, "lse");
+  expect_i32(qi, fn, "q_indptr");
+  expect_i32(ki, fn, "kv_indptr");
+  expect_i32(qpos, fn, "q_rope_position");
+  expect_i32(a6, fn, tree ? "mn_indptr" : "k_rope_pos_offset");
+  expect_f32(lse, fn, "lse");
+  const int dtype = kv_dtype(q, fn, "q");
+  expect_same_dtype(q, k, fn, "k vs q");
+  expect_same_dtype(q, v, fn, "v vs q");
+  expect_same_dtype(q, out, fn, "output vs q");
+  const int total = static_cast<int>(q.shape(0)), hq = static_cast<int>(q.shape(1)), d = static_cast<int>(q.shape(2));
+  const int total_kv = static_cast<int>(k.shape(0)), hkv = static_cast<int>(k.shape(1));
+  const int batch = static_cast<int>(qi.shape(0)) - 1;
+  expect_shape(ki.shape(0) == batch + 1, fn, "q_indptr and kv_indptr must both be [batch_size + 1]");
+  expect_shape(k.shape(2) == d, fn, "k.shape[2] must equal q.shape[2]");
+  expect_shape(v.shape(0) == total_kv && v.shape(1) == hkv && v.shape(2) == d, fn,
+               "v must match k (the sm_100a path needs d_v == d_qk)");
+  expect_shape(out.shape(0) == total && out.shape(1) == hq && out.shape(2) == d, fn, "output must match q");
+  expect_shape(lse.shape(0) == total && lse.shape(1) == hq, fn, "lse must be [total_len, num_qo_heads]");
+  expect_shape(qpos.shape(0) == total, fn, "q_rope_position must be [total_len]");
+  DeviceGuard g(q, fn);
+  expect_same_device(q, k, fn, "k");
+  expect_same_device(q, v, fn, "v");
+  if (tree) {
+    expect_i32(mask, fn, "mask");
+    expect_ndim(a6, 1, fn, "mn_indptr");
+    expect_shape(a6.shape(0) == batch + 1, fn, "mn_indptr must be [batch_size + 1]");
+    check_rc(tvmb200_attention_prefill_tree_ragged(
+        q.data, static_cast<const int32_t*>(qi.data), k.data, v.data, static_cast<const int32_t*>(ki.data),
+        static_cast<const int32_t*>(qpos.data), static_cast<const int32_t*>(a6.data),
+        static_cast<const int32_t*>(mask.data), out.data, static_cast<float*>(lse.data), batch, total, total_kv, hq,
+        hkv, d, rotary_mode, rope_scale, rope_theta, sm_scale, dtype, env_stream(g.dev)));
+  } else {
+    expect_ndim(a6, 1, fn, "k_rope_pos_offset");
+    expect_shape(a6.shape(0) == batch, fn, "k_rope_pos_offset must be [batch_size]");
+    check_rc(tvmb200_attention_prefill_ragged(
+        q.data, static_cast<const int32_t*>(qi.data), k.data, v.data, static_cast<const int32_t*>(ki.data),
+        static_cast<const int32_t*>(qpos.data), static_cast<const int32_t*>(a6.data), out.data,
+        static_cast<float*>(lse.data), batch, total, total_kv, hq, hkv, d, causal, rotary_mode, rope_scale,
+        rope_theta, sm_scale, dtype, env_stream(g.dev)));
+  }
+  TVMB200_FFI_END();
+}
+int impl_prefill_ragged(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  return prefill_ragged_common(args, n, result, false, "batch_prefill_ragged_kv");
+}
+int impl_tree_ragged(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  return prefill_ragged_common(args, n, result, true, "batch_tree_attn");
+}
+
+int impl_launch_count(const TVMFFIAny*, int32_t, TVMFFIAny* result) {
+  result->type_index = kTVMFFIInt;
+  result->zero_padding = 0;
+  result->v_int64 = tvmb200_launch_count();
+  return 0;
+}
+
+}  // namespace
+
+#define TVMB200_EXPORT(name, impl)                                                                      \
+  extern "C" __attribute__((visibility("default"))) int __tvm_ffi_##name(void* self, const TVMFFIAny* args, \
+                                                                         int32_t num_args, TVMFFIAny* result) { \
+    (void)self;                                                                                         \
+    return impl(args, num_args, result);                                                                \
+  }
+
+// role names used by the reference cache constructor (paged_kv_cache.cc:2573-2603) ...
+TVMB200_EXPORT(f_transpose_append, impl_transpose_append)
+TVMB200_EXPORT(f_attention_decode, impl_decode)
+TVMB200_EXPORT(f_attention_decode_sliding_window, impl_decode)
+TVMB200_EXPORT(f_attention_prefill, impl_prefill_paged)
+TVMB200_EXPORT(f_attention_prefill_sliding_window, impl_prefill_paged)
+TVMB200_EXPORT(f_attention_prefill_ragged, impl_prefill_ragged)
+TVMB200_EXPORT(f_attention_prefill_with_tree_mask, impl_tree_ragged)
+TVMB200_EXPORT(f_attention_prefill_with_tree_mask_paged_kv, impl_tree_paged)
+TVMB200_EXPORT(f_merge_inplace, impl_merge_state_inplace)
+TVMB200_EXPORT(f_split_rotary, impl_fused_rope)
+TVMB200_EXPORT(f_copy_single_page, impl_copy_single_page)
+TVMB200_EXPORT(f_debug_get_kv, impl_debug_get_kv)
+TVMB200_EXPORT(f_compact_copy, impl_compact_kv_copy)
+// ... and the global_symbols of the reference PrimFuncs they replace
+TVMB200_EXPORT(tir_kv_cache_transpose_append, impl_transpose_append)
+TVMB200_EXPORT(batch_decode_paged_kv, impl_decode)
+TVMB200_EXPORT(batch_decode_paged_kv_sliding_window, impl_decode)
+TVMB200_EXPORT(batch_prefill_paged_kv, impl_prefill_paged)
+TVMB200_EXPORT(batch_prefill_paged_kv_sliding_window, impl_prefill_paged)
+TVMB200_EXPORT(batch_prefill_ragged_kv, impl_prefill_ragged)
+TVMB200_EXPORT(batch_tree_attn, impl_tree_ragged)
+TVMB200_EXPORT(tree_attn_paged_kv, impl_tree_paged)
+TVMB200_EXPORT(merge_state_inplace, impl_merge_state_inplace)
+TVMB200_EXPORT(fused_rope, impl_fused_rope)
+TVMB200_EXPORT(copy_single_page, impl_copy_single_page)
+TVMB200_EXPORT(tir_kv_cache_debug_get_kv, impl_debug_get_kv)
+TVMB200_EXPORT(compact_kv_copy, impl_compact_kv_copy)
+// module state the reference bakes in at TIR build time
+TVMB200_EXPORT(set_rope_params, impl_set_rope_params)
+TVMB200_EXPORT(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)
+TVMB200_EXPORT(launch_count, impl_launch_count)

@@ -1,0 +1,328 @@
+// Page-cache data movement kernels: append, debug-get, page fork copy, tree-commit compaction,
+// fused QKV split + RoPE, and the in-place LSE merge.  All HBM-bound: 128-bit accesses, streaming
+// cache hints, bit-exact copies.
+//
+// Reference (TIR) counterparts:
+//   transpose_append   python/tvm/relax/frontend/nn/llm/_page_kernels.py:40-74
+//   debug_get_kv       _page_kernels.py:106-136
+//   copy_single_page   _page_kernels.py:169-189
+//   compact_kv_copy    _page_kernels.py:235-263
+//   split_rotary       python/tvm/relax/frontend/nn/llm/position_embedding.py:444-565
+//   merge_state_inplace python/tvm/relax/frontend/nn/llm/_decode_kernels.py:414-526
+#include "common.cuh"
+
+namespace tvmb200 {
+
+// one thread = one 16-byte vector of K and the matching vector of V
+__global__ void __launch_bounds__(256)
+transpose_append_kernel(uint4* __restrict__ pages, const uint4* __restrict__ k,
+                        const uint4* __restrict__ v, const int32_t* __restrict__ position_map,
+                        int64_t total_vecs, int num_kv_heads, int page_size, int row_vecs) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total_vecs) return;
+  const int per_token = num_kv_heads * row_vecs;
+  const int64_t t = idx / per_token;
+  const int r = static_cast<int>(idx - t * per_token);
+  const int h = r / row_vecs;
+  const int c = r - h * row_vecs;
+  const int pos = __ldg(position_map + t);
+  if (pos < 0) return;  // -1 = "do not append" (reference: position_map != -1)
+  const int64_t page = pos / page_size;
+  const int slot = pos - static_cast<int>(page) * page_size;
+  const int64_t dst_k = (((page * 2 + 0) * num_kv_heads + h) * page_size + slot) * row_vecs + c;
+  const int64_t dst_v = dst_k + static_cast<int64_t>(num_kv_heads) * page_size * row_vecs;
+  const uint4 kv = ldg_nc_v4(k + idx);
+  const uint4 vv = ldg_nc_v4(v + idx);
+  pages[dst_k] = kv;
+  pages[dst_v] = vv;
+}
+
+__global__ void __launch_bounds__(256)
+debug_get_kv_kernel(const uint4* __restrict__ pages, const int32_t* __restrict__ position_map,
+                    uint4* __restrict__ k_out, uint4* __restrict__ v_out, int64_t total_vecs,
+                    int num_kv_heads, int page_size, int row_vecs) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total_vecs) return;
+  const int per_token = num_kv_heads * row_vecs;
+  const int64_t t = idx / per_token;
+  const int r = static_cast<int>(idx - t * per_token);
+  const int h = r / row_vecs;
+  const int c = r - h * row_vecs;
+  const int pos = __ldg(position_map + t);
+  const int64_t page = pos / page_size;
+  const int slot = pos - static_cast<int>(page) * page_size;
+  const int64_t src_k = (((page * 2 + 0) * num_kv_heads + h) * page_size + slot) * row_vecs + c;
+  const int64_t src_v = src_k + static_cast<int64_t>(num_kv_heads) * page_size * row_vecs;
+  k_out[idx] = pages[src_k];
+  v_out[idx] = pages[src_v];
+}
+
+// pages[tgt, kv, h, 0:copy_length, :] = pages[src, kv, h, 0:copy_length, :]
+__global__ void __launch_bounds__(256)
+copy_single_page_kernel(uint4* __restrict__ pages, int64_t src_page, int64_t tgt_page,
+                        int copy_length, int num_kv_heads, int page_size, int row_vecs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_head = copy_length * row_vecs;
+  const int total = 2 * num_kv_heads * per_head;
+  if (idx >= total) return;
+  const int kvh = idx / per_head;  // (kv, head) flattened
+  const int r = idx - kvh * per_head;
+  const int64_t in_page = static_cast<int64_t>(kvh) * page_size * row_vecs + r;
+  const int64_t page_vecs = static_cast<int64_t>(2) * num_kv_heads * page_size * row_vecs;
+  pages[tgt_page * page_vecs + in_page] = pages[src_page * page_vecs + in_page];
+}
+
+// thread = (sequence b, kv head h, 16-byte column c); walks that sequence's copy list IN ORDER
+// (a destination may be a later source: the serial order of the reference must be kept).
+__global__ void __launch_bounds__(256)
+compact_kv_copy_kernel(uint4* __restrict__ pages, const int32_t* __restrict__ indptr,
+                       const int32_t* __restrict__ src_dst, int batch_size, int total_copy_length,
+                       int num_kv_heads, int page_size, int row_vecs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_seq = num_kv_heads * row_vecs;
+  if (idx >= batch_size * per_seq) return;
+  const int b = idx / per_seq;
+  const int r = idx - b * per_seq;
+  const int h = r / row_vecs;
+  const int c = r - h * row_vecs;
+  const int beg = indptr[b], end = indptr[b + 1];
+  const int64_t v_off = static_cast<int64_t>(num_kv_heads) * page_size * row_vecs;
+  for (int i = beg; i < end; ++i) {
+    const int sp = src_dst[i];
+    const int dp = src_dst[total_copy_length + i];
+    const int64_t spage = sp / page_size, dpage = dp / page_size;
+    const int sslot = sp - static_cast<int>(spage) * page_size;
+    const int dslot = dp - static_cast<int>(dpage) * page_size;
+    const int64_t s = (((spage * 2) * num_kv_heads + h) * page_size + sslot) * row_vecs + c;
+    const int64_t d = (((dpage * 2) * num_kv_heads + h) * page_size + dslot) * row_vecs + c;
+    const uint4 kk = pages[s];
+    const uint4 vv = pages[s + v_off];
+    pages[d] = kk;
+    pages[d + v_off] = vv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused QKV split + RoPE.  One CTA per token: the D/2 (cos, sin) pairs of the token's position are
+// computed ONCE into shared memory (the reference recomputes powf/cosf/sinf per element), then
+// every (head, 8-element vector pair) is rotated with 128-bit loads/stores.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ position_map,
+                    uint4* __restrict__ q, uint4* __restrict__ k, uint4* __restrict__ v,
+                    int num_qo_heads, int num_kv_heads, int head_dim, int rotary_dim,
+                    int apply_rope, float rope_scale, float rope_theta) {
+  extern __shared__ float2 cs[];  // [rotary_dim/2] (cos, sin)
+  const int64_t t = blockIdx.x;
+  const int row_vecs = head_dim / 8;
+  const int half_vecs = rotary_dim / 16;  // vectors in one rotary half
+  const int fused_heads = num_qo_heads + 2 * num_kv_heads;
+  if (apply_rope > 0) {
+    const float pos = static_cast<float>(position_map[t]) * rope_scale;
+    for (int d = threadIdx.x; d < rotary_dim / 2; d += blockDim.x) {
+      const float freq = pos / rope_denominator(d, rotary_dim, rope_theta);
+      float s, c;
+      sincosf(freq, &s, &c);
+      cs[d] = make_float2(c, s);
+    }
+    __syncthreads();
+  }
+  const uint4* src = qkv + t * fused_heads * row_vecs;
+  // work item = (head, vector index j in [0, row_vecs)); rotated heads pair j with j +- half_vecs
+  for (int w = threadIdx.x; w < fused_heads * row_vecs; w += blockDim.x) {
+    const int h = w / row_vecs;
+    const int j = w - h * row_vecs;
+    uint4* dst;
+    if (h < num_qo_heads) {
+      dst = q + (t * num_qo_heads + h) * row_vecs + j;
+    } else if (h < num_qo_heads + num_kv_heads) {
+      dst = k + (t * num_kv_heads + (h - num_qo_heads)) * row_vecs + j;
+    } else {
+      dst = v + (t * num_kv_heads + (h - num_qo_heads - num_kv_heads)) * row_vecs + j;
+    }
+    uint4 x = ldg_nc_v4(src + w);
+    const bool rot = apply_rope > 0 && h < num_qo_heads + num_kv_heads && j < 2 * half_vecs;
+    if (rot) {
+      const bool lower = j < half_vecs;
+      const uint4 p = ldg_nc_v4(src + (lower ? w + half_vecs : w - half_vecs));
+      const int d0 = (lower ? j : j - half_vecs) * 8;  // frequency index of element 0
+      const T* xe = reinterpret_cast<const T*>(&x);
+      const T* pe = reinterpret_cast<const T*>(&p);
+      uint4 o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = cs[d0 + e];
+        // reference: cos*x + sin*(d < rd/2 ? -x[d+rd/2] : x[d-rd/2]), negation done in dtype
+        const float partner = DT<T>::to_f(lower ? DT<T>::neg(pe[e]) : pe[e]);
+        oe[e] = DT<T>::from_f(f.x * DT<T>::to_f(xe[e]) + f.y * partner);
+      }
+      x = o;
+    }
+    *dst = x;
+  }
+}
+
+// (V,S) <- merge((V,S),(V',S')).  A block owns whole rows (row = n*H+h): thread = (row, 8-element
+// vector); S[row] is rewritten by the row's vector-0 thread after a block barrier so every thread of
+// the row has read the old value first.
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_state_inplace_kernel(uint4* __restrict__ v, float* __restrict__ s,
+                           const uint4* __restrict__ v_other, const float* __restrict__ s_other,
+                           int64_t rows, int row_vecs, int rows_per_block) {
+  const int r_in = threadIdx.x / row_vecs;
+  const int c = threadIdx.x - r_in * row_vecs;
+  const int64_t row = blockIdx.x * static_cast<int64_t>(rows_per_block) + r_in;
+  const bool active = r_in < rows_per_block && row < rows;
+  float s_max = 0.f, a = 0.f, b = 0.f;
+  if (active) {
+    const float s_val = s[row], so_val = s_other[row];
+    s_max = fmaxf(s_val, so_val);
+    a = exp2f(s_val - s_max);
+    b = exp2f(so_val - s_max);
+    const float scale = a / (a + b);
+    const float other_scale = b / (a + b);
+    const int64_t idx = row * row_vecs + c;
+    uint4 x = v[idx];
+    const uint4 y = ldg_nc_v4(v_other + idx);
+    T* xe = reinterpret_cast<T*>(&x);
+    const T* ye = reinterpret_cast<const T*>(&y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      xe[e] = DT<T>::from_f(DT<T>::to_f(xe[e]) * scale + DT<T>::to_f(ye[e]) * other_scale);
+    v[idx] = x;
+  }
+  __syncthreads();
+  if (active && c == 0) s[row] = log2f(a + b) + s_max;
+}
+
+}  // namespace tvmb200
+
+using namespace tvmb200;
+
+static inline int elem_vec_check(int head_dim) { return head_dim % 8 == 0; }
+
+extern "C" int tvmb200_transpose_append(void* pages, const void* k, const void* v,
+                                        const int32_t* position_map, int64_t ntoken,
+                                        int64_t num_pages, int32_t num_kv_heads, int32_t page_size,
+                                        int32_t head_dim, int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "transpose_append: unsupported dtype %d", dtype);
+  TVMB200_CHECK(elem_vec_check(head_dim), "transpose_append: head_dim %d must be a multiple of 8", head_dim);
+  TVMB200_CHECK(ntoken >= 0 && num_pages >= 0 && num_kv_heads > 0 && page_size > 0, "transpose_append: bad shape");
+  if (ntoken == 0) return 0;
+  const int row_vecs = head_dim / 8;
+  const int64_t total = ntoken * num_kv_heads * row_vecs;
+  const int64_t blocks = (total + 255) / 256;
+  transpose_append_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(pages), static_cast<const uint4*>(k), static_cast<const uint4*>(v),
+      position_map, total, num_kv_heads, page_size, row_vecs);
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_debug_get_kv(const void* pages, const int32_t* position_map, void* k_out,
+                                    void* v_out, int64_t layer_id, int64_t num_layers,
+                                    int64_t seqlen, int64_t num_pages, int32_t num_kv_heads,
+                                    int32_t page_size, int32_t head_dim, int dtype,
+                                    tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "debug_get_kv: unsupported dtype %d", dtype);
+  TVMB200_CHECK(elem_vec_check(head_dim), "debug_get_kv: head_dim %d must be a multiple of 8", head_dim);
+  TVMB200_CHECK(layer_id >= 0 && layer_id < num_layers, "debug_get_kv: layer_id %ld out of range [0,%ld)", (long)layer_id, (long)num_layers);
+  if (seqlen == 0) return 0;
+  const int row_vecs = head_dim / 8;
+  const int64_t total = seqlen * num_kv_heads * row_vecs;
+  const int64_t blocks = (total + 255) / 256;
+  uint4* ko = static_cast<uint4*>(k_out) + layer_id * total;
+  uint4* vo = static_cast<uint4*>(v_out) + layer_id * total;
+  debug_get_kv_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(pages), position_map, ko, vo, total, num_kv_heads, page_size, row_vecs);
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_copy_single_page(void* pages, int64_t src_page_id, int64_t tgt_page_id,
+                                        int64_t copy_length, int64_t num_pages,
+                                        int32_t num_kv_heads, int32_t page_size, int32_t head_dim,
+                                        int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "copy_single_page: unsupported dtype %d", dtype);
+  TVMB200_CHECK(elem_vec_check(head_dim), "copy_single_page: head_dim %d must be a multiple of 8", head_dim);
+  TVMB200_CHECK(src_page_id >= 0 && src_page_id < num_pages && tgt_page_id >= 0 && tgt_page_id < num_pages,
+                "copy_single_page: page id out of range (src %ld, tgt %ld, num_pages %ld)", (long)src_page_id, (long)tgt_page_id, (long)num_pages);
+  TVMB200_CHECK(copy_length >= 0 && copy_length <= page_size, "copy_single_page: copy_length %ld exceeds page_size %d", (long)copy_length, page_size);
+  if (copy_length == 0) return 0;
+  const int row_vecs = head_dim / 8;
+  const int total = 2 * num_kv_heads * static_cast<int>(copy_length) * row_vecs;
+  copy_single_page_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(pages), src_page_id, tgt_page_id, static_cast<int>(copy_length),
+      num_kv_heads, page_size, row_vecs);
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_compact_kv_copy(void* pages, const int32_t* copy_length_indptr,
+                                       const int32_t* copy_src_dst_pos, int32_t batch_size,
+                                       int32_t total_copy_length, int64_t num_pages,
+                                       int32_t num_kv_heads, int32_t page_size, int32_t head_dim,
+                                       int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "compact_kv_copy: unsupported dtype %d", dtype);
+  TVMB200_CHECK(elem_vec_check(head_dim), "compact_kv_copy: head_dim %d must be a multiple of 8", head_dim);
+  if (batch_size <= 0 || total_copy_length <= 0) return 0;
+  const int row_vecs = head_dim / 8;
+  const int total = batch_size * num_kv_heads * row_vecs;
+  compact_kv_copy_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(pages), copy_length_indptr, copy_src_dst_pos, batch_size,
+      total_copy_length, num_kv_heads, page_size, row_vecs);
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_split_rotary(const void* qkv, const int32_t* position_map, void* q, void* k,
+                                    void* v, int64_t ntoken, int32_t num_qo_heads,
+                                    int32_t num_kv_heads, int32_t head_dim, int32_t rotary_dim,
+                                    int64_t apply_rope, float rope_scale, float rope_theta,
+                                    int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "split_rotary: unsupported dtype %d", dtype);
+  if (rotary_dim <= 0) rotary_dim = head_dim;
+  TVMB200_CHECK(head_dim % 8 == 0 && rotary_dim % 16 == 0 && rotary_dim <= head_dim,
+                "split_rotary: head_dim %d / rotary_dim %d unsupported (need D %% 8 == 0, rd %% 16 == 0)", head_dim, rotary_dim);
+  if (ntoken == 0) return 0;
+  const size_t smem = static_cast<size_t>(rotary_dim / 2) * sizeof(float2);
+  const int apply = apply_rope > 0 ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TVMB200_F16) {
+    split_rotary_kernel<__half><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta);
+  } else {
+    split_rotary_kernel<__nv_bfloat16><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta);
+  }
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_merge_state_inplace(void* v, float* s, const void* v_other,
+                                           const float* s_other, int64_t n, int32_t num_heads,
+                                           int32_t head_dim, int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "merge_state_inplace: unsupported dtype %d", dtype);
+  TVMB200_CHECK(elem_vec_check(head_dim), "merge_state_inplace: head_dim %d must be a multiple of 8", head_dim);
+  if (n == 0) return 0;
+  const int row_vecs = head_dim / 8;
+  TVMB200_CHECK(row_vecs <= 256, "merge_state_inplace: head_dim %d too large", head_dim);
+  const int64_t rows = n * num_heads;
+  const int rows_per_block = 256 / row_vecs;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  if (dtype == TVMB200_F16) {
+    merge_state_inplace_kernel<__half><<<blocks, 256, 0, st>>>(
+        static_cast<uint4*>(v), s, static_cast<const uint4*>(v_other), s_other, rows, row_vecs, rows_per_block);
+  } else {
+    merge_state_inplace_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        static_cast<uint4*>(v), s, static_cast<const uint4*>(v_other), s_other, rows, row_vecs, rows_per_block);
+  }
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
