@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- PagedKVCache attention hot path on B200 (contract: see DESIGN.md "Measurement").
+
+A step = one layer-call of the decode hot path over one batch, exactly the callback sequence the
+reference cache issues per layer for a plain decode step (paged_kv_cache.cc:1355-1401):
+    f_split_rotary -> f_transpose_append -> f_attention_decode
+on BASELINE.json configs[1] (C2: Llama-3-8B shape, batch 64 decode at 4K context, bf16 paged KV).
+With --gpus N the sequence batch is split across ranks (64 sequences per rank, global batch 64*N, weak
+scaling) and the per-rank outputs are re-assembled with an NCCL all-gather inside the timed region.
+
+    metric  decode_attn_hbm_gbps = algorithmic bytes of the step (BASELINE.md section 3 formulas) / time
+    value   device-resident inputs (CUDA events, max over ranks)
+    e2e     the same through the tvm-ffi packed functions with HOST inputs: pinned qkv + merged aux
+            arrays copied host->device and O copied device->host every step, inside the timed region
+    roofline  the decode kernel alone against the measured HBM copy peak (MEASURED_PEAKS.json)
+    cpu_baseline  the reference's CPU path (oracle/_ref if built, else the NumPy oracle port) on a slice
+
+`--impl reference` times the CPU path only (rank 0) and prints the same JSON line shape.
+`--workload prefill` reports C3 (ragged causal prefill 16x2048) TFLOP/s instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return d, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload C2: decode
+# ---------------------------------------------------------------------------------------------------
+class DecodeWorkload:
+    """B sequences of L cached tokens (after this step's append), Hq/Hkv heads, D=128, page 16, bf16."""
+
+    def __init__(self, B=64, L=4096, Hq=32, Hkv=8, D=128, page=16, seed=0, device="cuda"):
+        import torch
+
+        self.B, self.L, self.Hq, self.Hkv, self.D, self.page = B, L, Hq, Hkv, D, page
+        rng = np.random.default_rng(seed)
+        ppseq = -(-L // page)
+        self.nnz = B * ppseq
+        P = self.nnz + 1
+        self.P = P
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        self.pages = torch.randn((P, 2, Hkv, page, D), generator=g, device=device, dtype=torch.bfloat16)
+        perm = rng.permutation(P).astype(np.int32)[: self.nnz]  # non-contiguous page ids: a real gather
+        self.h_page_values = perm
+        self.h_page_indptr = (np.arange(B + 1) * ppseq).astype(np.int32)
+        self.h_length_info = np.full(B, ((L - 1) % page) + 1, np.int32)
+        self.h_k_rope_pos_offset = np.zeros(B, np.int32)
+        self.h_q_rope_position = np.full(B, L - 1, np.int32)
+        last_page = perm.reshape(B, ppseq)[:, -1]
+        self.h_append_position = (last_page * page + (L - 1) % page).astype(np.int32)
+        self.h_qkv = torch.randn((B, Hq + 2 * Hkv, D), generator=torch.Generator().manual_seed(seed),
+                                 dtype=torch.float32).to(torch.bfloat16).pin_memory()
+        i32 = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+        self.page_values, self.page_indptr = i32(self.h_page_values), i32(self.h_page_indptr)
+        self.length_info, self.k_rope_pos_offset = i32(self.h_length_info), i32(self.h_k_rope_pos_offset)
+        self.q_rope_position, self.append_position = i32(self.h_q_rope_position), i32(self.h_append_position)
+        self.qkv = self.h_qkv.to(device)
+        self.q = torch.empty((B, Hq, D), device=device, dtype=torch.bfloat16)
+        self.k = torch.empty((B, Hkv, D), device=device, dtype=torch.bfloat16)
+        self.v = torch.empty((B, Hkv, D), device=device, dtype=torch.bfloat16)
+        self.o = torch.empty((B, Hq, D), device=device, dtype=torch.bfloat16)
+        self.lse = torch.empty((B, Hq), device=device, dtype=torch.float32)
+        self.sm_scale = D ** -0.5
+        self.rope_theta, self.rope_scale = 5e5, 1.0
+
+    # algorithmic bytes
+    def decode_bytes(self):
+        e = 2
+        return (self.B * self.L * self.Hkv * self.D * 2 * e + 2 * self.B * self.Hq * self.D * e + 4 * self.B * self.Hq
+                + 4 * (self.nnz + 4 * self.B + 1))
+
+    def append_bytes(self):
+        return self.B * self.Hkv * self.D * 2 * 2 * 2 + 4 * self.B
+
+    def rotary_bytes(self):
+        return 2 * self.B * (self.Hq + 2 * self.Hkv) * self.D * 2 + 4 * self.B
+
+    def step_bytes(self):
+        return self.decode_bytes() + self.append_bytes() + self.rotary_bytes()
+
+    def run_rotary_append(self, capi):
+        capi.split_rotary(self.qkv, self.q_rope_position, self.q, self.k, self.v, 1, self.rope_scale, self.rope_theta)
+        capi.transpose_append(self.pages, self.k, self.v, self.append_position)
+
+    def run_decode(self, capi):
+        capi.attention_decode(self.q, self.pages, self.page_indptr, self.page_values, self.length_info,
+                              self.k_rope_pos_offset, self.q_rope_position, self.o, self.lse, 0, self.rope_scale,
+                              self.rope_theta, self.sm_scale)
+
+
+class PrefillWorkload:
+    """C3: 16 sequences x 2048 new tokens, empty cache -> ragged causal prefill (+ rotary + append)."""
+
+    def __init__(self, nseq=16, L=2048, Hq=32, Hkv=8, D=128, seed=0, device="cuda"):
+        import torch
+
+        self.nseq, self.L, self.Hq, self.Hkv, self.D = nseq, L, Hq, Hkv, D
+        n = nseq * L
+        self.n = n
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        self.q = torch.randn((n, Hq, D), generator=g, device=device, dtype=torch.bfloat16)
+        self.k = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
+        self.v = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
+        ip = (np.arange(nseq + 1) * L).astype(np.int32)
+        self.indptr = torch.from_numpy(ip).to(device)
+        self.qpos = torch.from_numpy(np.tile(np.arange(L, dtype=np.int32), nseq)).to(device)
+        self.kofs = torch.zeros(nseq, dtype=torch.int32, device=device)
+        self.o = torch.empty((n, Hq, D), device=device, dtype=torch.bfloat16)
+        self.lse = torch.empty((n, Hq), device=device, dtype=torch.float32)
+        self.sm_scale = D ** -0.5
+
+    def flops(self):
+        return 4 * self.D * self.Hq * self.nseq * (self.L * (self.L + 1) // 2)
+
+    def run(self, capi):
+        capi.attention_prefill_ragged(self.q, self.indptr, self.k, self.v, self.indptr, self.qpos, self.kofs, self.o,
+                                      self.lse, 1, 0, 1.0, 5e5, self.sm_scale)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling (NVML) during the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index=0, period_s=0.002):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period, self._stop, self._thr, self.h = period_s, threading.Event(), None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline (the reference's CPU path): oracle/_ref if present, else the NumPy oracle port
+# ---------------------------------------------------------------------------------------------------
+def cpu_decode_baseline(L=4096, Hq=32, Hkv=8, D=128, B=1, repeats=1):
+    """Times the CPU decode kernel on a bounded slice (B sequences of the C2 shape, fp16 like the
+    reference's CPU tests).  Returns dict(value GB/s, unit, cores, kind, sample)."""
+    from oracle import cpu_ref
+
+    return cpu_ref.time_decode(B=B, L=L, Hq=Hq, Hkv=Hkv, D=D, repeats=repeats)
+
+
+# ---------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def run_own(args):
+    import torch
+
+    from tvm_b200 import capi
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    capi.lib()
+    peaks, peak_src = measured_peaks()
+    if args.workload == "prefill":
+        return run_prefill(args, capi, rank, world, dev, peaks, peak_src)
+    w = DecodeWorkload(seed=rank, device=dev)
+    dist = None
+    gathered = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        gathered = torch.empty((world * w.B, w.Hq, w.D), device=dev, dtype=torch.bfloat16)
+
+    def step():
+        w.run_rotary_append(capi)
+        w.run_decode(capi)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, w.o)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    K = args.steps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    n0 = capi.launch_count()
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(K):
+            w.run_rotary_append(capi)
+            ev[2 * i + 1].record()
+            w.run_decode(capi)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, w.o)
+            ev[2 * i + 2].record()
+        torch.cuda.synchronize()
+    launches = capi.launch_count() - n0
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[2 * K])
+    decode_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(K)) / K
+    if world > 1:
+        t = torch.tensor([total_ms, decode_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, decode_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / K
+    value = world * w.step_bytes() / (ms_per_step * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+    dec_gbs = w.decode_bytes() / (decode_ms * 1e-3) / 1e9
+    out = {
+        "metric": "decode_attn_hbm_gbps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C2 Llama-3-8B decode: batch 64/GPU x 4096 ctx, 32q/8kv heads, D128, page16, bf16 "
+                               "paged KV; step = split_rotary+append+decode of one layer",
+                   "global_batch": w.B * world, "seq_len": w.L, "parallelism": f"batch-split x{world}",
+                   "l2": "KV working set 1 GiB/GPU > 126 MB L2 (no flush needed)"},
+        "tok_s_layer": round(world * w.B / (ms_per_step * 1e-3), 1),
+        "roofline": {"bound": "hbm", "kernel": "decode_kernel(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
+                     "peak": hbm_peak, "unit": "GB/s", "frac": round(dec_gbs / hbm_peak, 4), "traffic": None,
+                     "peak_source": f"of {peak_src}", "algorithmic_bytes": w.decode_bytes(),
+                     "kernel_ms": round(decode_ms, 5), "frac_of_spec_8000": round(dec_gbs / 8000.0, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if rank == 0:
+        # e2e + cpu baseline on rank 0 only
+        try:
+            out["e2e"] = run_e2e(args, w, world)
+        except Exception as e:  # pragma: no cover
+            out["e2e"] = {"value": None, "error": repr(e)[:200]}
+        if world == 1 and not args.no_cpu:
+            try:
+                out["cpu_baseline"] = cpu_decode_baseline()
+            except Exception as e:  # pragma: no cover
+                out["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, w, world):
+    """Through the tvm-ffi packed functions with host inputs (see module docstring)."""
+    import torch
+
+    from tvm_b200 import ffi
+
+    mod = ffi.module()
+    K = max(10, args.steps // 5)
+    # merged aux array like the reference's CachedPagedKVCacheAuxDataManager (attn_utils.h:907-1052)
+    parts = [w.h_q_rope_position, w.h_page_indptr, w.h_page_values, w.h_length_info, w.h_k_rope_pos_offset,
+             w.h_append_position]
+    offs, tot = [], 0
+    for p in parts:
+        offs.append(tot)
+        tot += (p.size + 3) // 4 * 4  # 16-byte aligned element offsets
+    h_aux = torch.zeros(tot, dtype=torch.int32).pin_memory()
+    for p, o in zip(parts, offs):
+        h_aux[o:o + p.size] = torch.from_numpy(p)
+    d_aux = torch.empty(tot, dtype=torch.int32, device=w.qkv.device)
+    views = [d_aux[o:o + p.size] for p, o in zip(parts, offs)]
+    qpos, pindptr, pvals, linfo, kofs, apos = views
+    h_out = torch.empty(w.o.shape, dtype=torch.bfloat16).pin_memory()
+    d_qkv = torch.empty_like(w.qkv)
+    f_rot, f_app, f_dec = mod["f_split_rotary"], mod["f_transpose_append"], mod["f_attention_decode"]
+    mod["set_rope_params"](float(w.rope_theta), float(w.rope_scale))
+
+    def step():
+        d_qkv.copy_(w.h_qkv, non_blocking=True)
+        d_aux.copy_(h_aux, non_blocking=True)
+        f_rot(d_qkv, qpos, w.q, w.k, w.v, 1)
+        f_app(w.pages, w.k, w.v, apos)
+        f_dec(w.q, w.pages, pindptr, pvals, linfo, kofs, qpos, w.o, w.lse, 0, w.rope_scale, w.rope_theta, w.sm_scale)
+        h_out.copy_(w.o, non_blocking=True)
+
+    with ffi.torch_stream():
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    return {"value": round(world * w.step_bytes() / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+            "h2d_bytes_per_step": int(w.h_qkv.numel() * 2 + tot * 4), "d2h_bytes_per_step": int(h_out.numel() * 2),
+            "ms_per_step": round(ms, 5), "steps": K, "api": "tvm-ffi packed functions f_split_rotary/"
+            "f_transpose_append/f_attention_decode", "n_gpus_measured": 1}
+
+
+def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
+    import torch
+
+    w = PrefillWorkload(seed=rank, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        w.run(capi)
+    torch.cuda.synchronize()
+    K = max(1, min(args.steps, 50))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = capi.launch_count()
+    with ClockSampler(dev.index or 0) as clk:
+        e0.record()
+        for _ in range(K):
+            w.run(capi)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    tf = w.flops() / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+    out = {"metric": "prefill_tflops", "value": round(tf * world, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": K,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "C3 ragged causal prefill 16x2048, 32q/8kv heads, D128, bf16", "l2": "q/k/v/o "
+                      "0.67 GB > L2"},
+           "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": peak, "unit": "TFLOP/s",
+                        "frac": round(tf / peak, 4), "traffic": None, "peak_source": f"of {peak_src}",
+                        "algorithmic_flops": w.flops()},
+           "gpu_launches": int(capi.launch_count() - n0), "clocks": clk.summary()}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def run_reference(args):
+    """The reference's own CPU path on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import cpu_ref
+
+    K, W = args.steps, args.warmup
+    res = cpu_ref.time_decode_steps(steps=min(K, 5), warmup=min(W, 1))
+    out = {"impl": "reference", "metric": "decode_attn_hbm_gbps", "value": res["value"], "unit": "GB/s",
+           "n_gpus": args.gpus, "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": res["dtype"],
+           "data": "synthetic",
+           "config": {"workload": "C2 Llama-3-8B decode: batch 64/GPU x 4096 ctx, 32q/8kv heads, D128, page16; "
+                                  "step = split_rotary+append+decode of one layer", "sample": res["sample"]},
+           "cpu_baseline": {"value": res["value"], "unit": "GB/s", "cores": res["cores"], "kind": res["kind"],
+                            "sample": res["sample"]},
+           "e2e": {"value": res["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="decode", choices=["decode", "prefill"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

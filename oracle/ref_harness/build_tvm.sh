@@ -19,14 +19,14 @@ mkdir -p "$OUT"
 if [ ! -f "$OUT/build/lib/libtvm_runtime_extra.so" ] && [ ! -f "$OUT/build/libtvm_runtime_extra.so" ]; then
   cmake -S "$REF" -B "$OUT/build" -G Ninja -DCMAKE_BUILD_TYPE=Release \
         -DUSE_LLVM=OFF -DUSE_CUDA=OFF -DUSE_GTEST=OFF -DUSE_Z3=OFF -DUSE_CCACHE=OFF -DUSE_RPC=OFF
-  ninja -C "$OUT/build" -j"$(nproc)"
+  ninja -C "$OUT/build" -j"${JOBS:-$(nproc)}"
 fi
 
 # 2. the vendored tvm-ffi python extension (pip has 0.1.9; the reference needs >= 0.1.13)
 if ! ls "$OUT/ffi_build"/core*.so >/dev/null 2>&1 && ! ls "$OUT/ffi_build"/*/core*.so >/dev/null 2>&1; then
   cmake -S "$REF/3rdparty/tvm-ffi" -B "$OUT/ffi_build" -G Ninja -DCMAKE_BUILD_TYPE=Release \
         -DTVM_FFI_BUILD_PYTHON_MODULE=ON -DPython_EXECUTABLE="$PY"
-  ninja -C "$OUT/ffi_build" -j"$(nproc)"
+  ninja -C "$OUT/ffi_build" -j"${JOBS:-$(nproc)}"
 fi
 
 # 3. assemble a python package dir that shadows pip's apache-tvm-ffi 0.1.9

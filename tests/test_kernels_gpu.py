@@ -1,0 +1,391 @@
+"""GPU parity tests: every C-ABI entry point (include/tvm_b200.h) against the CPU oracle on the same
+seeded inputs.  Bar: bit-exact for copies / index work; max-abs 2e-3 / rtol 1e-2 for O and LSE
+(north_star tolerance).  Scenario shapes follow the reference's own test file
+(tests/python/relax/test_runtime_builtin_paged_attention_kv_cache_cpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import kernels as ok
+from tests.util import assert_close, make_paged_cache, rand16, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = ["float16", "bfloat16"]
+
+
+def _i32(x):
+    return to_dev(np.asarray(x, np.int32))
+
+
+@pytest.fixture(scope="module")
+def capi(built_lib):
+    from tvm_b200 import capi
+
+    capi.lib()
+    return capi
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hkv,d", [(8, 128), (4, 64), (1, 128)])
+def test_transpose_append_bit_exact(capi, dtype, hkv, d):
+    import torch
+
+    rng = np.random.default_rng(0)
+    P, page = 37, 16
+    n = 100
+    pages = rand16(rng, (P, 2, hkv, page, d), dtype)
+    k = rand16(rng, (n, hkv, d), dtype)
+    v = rand16(rng, (n, hkv, d), dtype)
+    pm = rng.permutation(P * page)[:n].astype(np.int32)
+    pm[::7] = -1  # "do not append"
+    want = pages.copy()
+    ok.transpose_append(want, k, v, pm)
+    dp = to_dev(pages, dtype)
+    capi.transpose_append(dp, to_dev(k, dtype), to_dev(v, dtype), _i32(pm))
+    torch.cuda.synchronize()
+    assert np.array_equal(ok.to_bits16(to_np(dp), dtype), ok.to_bits16(want, dtype))
+    # debug_get_kv round trip (the reference's verify_cached_kv)
+    live = pm[pm >= 0]
+    ko = torch.zeros((2, len(live), hkv, d), dtype=dp.dtype, device="cuda")
+    vo = torch.zeros_like(ko)
+    capi.debug_get_kv(dp, _i32(live), ko, vo, 1)
+    torch.cuda.synchronize()
+    wk, wv = ok.debug_get_kv(want, live)
+    assert np.array_equal(to_np(ko[1]), wk) and np.array_equal(to_np(vo[1]), wv)
+    assert float(ko[0].abs().sum()) == 0.0
+
+
+def test_transpose_append_empty(capi):
+    import torch
+
+    pages = torch.zeros((3, 2, 8, 16, 128), dtype=torch.float16, device="cuda")
+    k = torch.zeros((0, 8, 128), dtype=torch.float16, device="cuda")
+    capi.transpose_append(pages, k, k, torch.zeros((0,), dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_copy_single_page_and_compact(capi, dtype):
+    import torch
+
+    rng = np.random.default_rng(1)
+    P, hkv, page, d = 9, 8, 16, 128
+    pages = rand16(rng, (P, 2, hkv, page, d), dtype)
+    want = pages.copy()
+    dp = to_dev(pages, dtype)
+    for src, tgt, ln in [(2, 3, 2), (0, 8, 16), (5, 1, 0), (4, 6, 15)]:
+        ok.copy_single_page(want, src, tgt, ln)
+        capi.copy_single_page(dp, src, tgt, ln)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(dp), want)
+    # compaction incl. a chain where a destination is a later source (serial order matters)
+    indptr = np.array([0, 3, 3, 5], np.int32)
+    src_dst = np.array([[20, 21, 5, 100, 33], [5, 20, 6, 101, 34]], np.int32)
+    ok.compact_kv_copy(want, indptr, src_dst, 3)
+    capi.compact_kv_copy(dp, _i32(indptr), _i32(src_dst), 3)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(dp), want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("apply_rope", [0, 1])
+@pytest.mark.parametrize("theta", [1e4, 5e5])
+def test_split_rotary(capi, dtype, apply_rope, theta):
+    import torch
+
+    rng = np.random.default_rng(2)
+    n, hq, hkv, d = 53, 32, 8, 128
+    qkv = rand16(rng, (n, hq + 2 * hkv, d), dtype)
+    pos = rng.integers(0, 4096, n).astype(np.int32)
+    wq, wk, wv = ok.split_rotary(qkv, pos, hq, hkv, apply_rope, theta, 1.0, dtype)
+    tdt = to_dev(qkv, dtype).dtype
+    q = torch.empty((n, hq, d), dtype=tdt, device="cuda")
+    k = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+    v = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+    capi.split_rotary(to_dev(qkv, dtype), _i32(pos), q, k, v, apply_rope, 1.0, theta)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(v), wv)  # v is a pure copy
+    if apply_rope == 0:
+        assert np.array_equal(to_np(q), wq) and np.array_equal(to_np(k), wk)
+    else:
+        # fp32 sin/cos of arguments up to 4096 rad: allow 1 dtype ulp of slack on top of the tolerance
+        assert_close("q", to_np(q), wq, atol=2e-2 if dtype == "bfloat16" else 4e-3)
+        assert_close("k", to_np(k), wk, atol=2e-2 if dtype == "bfloat16" else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_merge_state_inplace(capi, dtype):
+    import torch
+
+    rng = np.random.default_rng(3)
+    n, h, d = 77, 32, 128
+    v = rand16(rng, (n, h, d), dtype)
+    vo = rand16(rng, (n, h, d), dtype)
+    s = (rng.standard_normal((n, h)) * 4).astype(np.float32)
+    so = (rng.standard_normal((n, h)) * 4).astype(np.float32)
+    so[3] = ok.NEG_INIT  # empty other side: merge must be a no-op
+    s[5] = ok.NEG_INIT
+    wv, ws = ok.merge_state_inplace(v, s, vo, so, dtype)
+    dv, ds = to_dev(v, dtype), to_dev(s)
+    capi.merge_state_inplace(dv, ds, to_dev(vo, dtype), to_dev(so))
+    torch.cuda.synchronize()
+    assert_close("merged v", to_np(dv), wv)
+    assert_close("merged s", to_np(ds), ws)
+    assert np.array_equal(to_np(dv)[3], v[3])
+
+
+# ---------------------------------------------------------------------------------------------------
+def _run_decode(capi, rng, kv_lens, hq, hkv, d, dtype, rotary_mode=0, sliding=None, theta=1e4):
+    import torch
+
+    B = len(kv_lens)
+    c = make_paged_cache(rng, kv_lens, hkv, d, dtype, sliding=sliding)
+    q = rand16(rng, (B, hq, d), dtype)
+    kpos = rng.integers(0, 50, B).astype(np.int32)
+    qpos = (kpos + np.array(kv_lens) - 1).astype(np.int32)
+    sm = d ** -0.5
+    wo, wl = ok.attention_decode(q, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kpos, qpos,
+                                 rotary_mode, 1.0, theta, sm, dtype)
+    dq = to_dev(q, dtype)
+    o = torch.full((B, hq, d), float("nan"), dtype=dq.dtype, device="cuda")
+    lse = torch.full((B, hq), float("nan"), dtype=torch.float32, device="cuda")
+    capi.attention_decode(dq, to_dev(c["pages"], dtype), _i32(c["page_indptr"]), _i32(c["page_values"]),
+                          _i32(c["length_info"]), _i32(kpos), _i32(qpos), o, lse, rotary_mode, 1.0, theta, sm)
+    torch.cuda.synchronize()
+    assert_close("decode O", to_np(o), wo)
+    assert_close("decode LSE", to_np(lse), wl)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (32, 4, 128), (8, 8, 128), (32, 8, 64), (8, 1, 128)])
+def test_decode_small(capi, dtype, hq, hkv, d):
+    rng = np.random.default_rng(10)
+    _run_decode(capi, rng, [11, 21, 31, 41], hq, hkv, d, dtype)  # C1 decode lengths
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decode_ragged_lengths_and_empty(capi, dtype):
+    rng = np.random.default_rng(11)
+    # 0 = sequence with no pages at this depth (Appendix C.4): O = 0, lse = -5e4
+    _run_decode(capi, rng, [1, 16, 17, 0, 255, 256, 257, 1000, 0, 5], 32, 8, 128, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decode_split_kv_long(capi, dtype):
+    rng = np.random.default_rng(12)
+    _run_decode(capi, rng, [8192, 3, 4097], 32, 8, 128, dtype)  # few long sequences => split-KV + merge
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decode_batch64(capi, dtype):
+    rng = np.random.default_rng(13)
+    _run_decode(capi, rng, list(rng.integers(1, 700, 64)), 32, 8, 128, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decode_sliding_window(capi, dtype):
+    rng = np.random.default_rng(14)
+    # (slots in pages, (sliding offset, sink)): visible = sink + [off, slots)
+    _run_decode(capi, rng, [40, 100, 64, 33], 32, 8, 128, dtype, sliding=[(0, 0), (37, 4), (16, 16), (20, 0)])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decode_inline_rope(capi, dtype):
+    rng = np.random.default_rng(15)
+    _run_decode(capi, rng, [11, 70, 300], 32, 8, 128, dtype, rotary_mode=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _run_ragged(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=1, rotary_mode=0, tree=None):
+    import torch
+
+    B = len(q_lens)
+    qi = np.zeros(B + 1, np.int32)
+    qi[1:] = np.cumsum(q_lens)
+    ki = np.zeros(B + 1, np.int32)
+    ki[1:] = np.cumsum(kv_lens)
+    n, m = int(qi[-1]), int(ki[-1])
+    q = rand16(rng, (n, hq, d), dtype)
+    k = rand16(rng, (m, hkv, d), dtype)
+    v = rand16(rng, (m, hkv, d), dtype)
+    kofs = rng.integers(0, 30, B).astype(np.int32)
+    qpos = np.concatenate([kofs[b] + kv_lens[b] - q_lens[b] + np.arange(q_lens[b]) for b in range(B)]).astype(np.int32)
+    sm = d ** -0.5
+    dq = to_dev(q, dtype)
+    o = torch.full((n, hq, d), float("nan"), dtype=dq.dtype, device="cuda")
+    lse = torch.full((n, hq), float("nan"), dtype=torch.float32, device="cuda")
+    if tree is None:
+        wo, wl = ok.attention_prefill_ragged(q, qi, k, v, ki, qpos, kofs, causal, rotary_mode, 1.0, 1e4, sm, dtype)
+        capi.attention_prefill_ragged(dq, _i32(qi), to_dev(k, dtype), to_dev(v, dtype), _i32(ki), _i32(qpos),
+                                      _i32(kofs), o, lse, causal, rotary_mode, 1.0, 1e4, sm)
+    else:
+        mn, mask = tree
+        wo, wl = ok.attention_prefill_ragged(q, qi, k, v, ki, qpos, kofs, 0, rotary_mode, 1.0, 1e4, sm, dtype,
+                                             mn_indptr=mn, tree_mask=mask)
+        capi.attention_prefill_tree_ragged(dq, _i32(qi), to_dev(k, dtype), to_dev(v, dtype), _i32(ki), _i32(qpos),
+                                           _i32(mn), _i32(mask), o, lse, rotary_mode, 1.0, 1e4, sm)
+    torch.cuda.synchronize()
+    assert_close("ragged O", to_np(o), wo)
+    assert_close("ragged LSE", to_np(lse), wl)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (32, 4, 64), (8, 8, 128)])
+def test_prefill_ragged_c1(capi, dtype, hq, hkv, d):
+    rng = np.random.default_rng(20)
+    _run_ragged(capi, rng, [10, 20, 30, 40], [10, 20, 30, 40], hq, hkv, d, dtype)  # C1 prefill
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("causal", [0, 1])
+def test_prefill_ragged_uneven(capi, dtype, causal):
+    rng = np.random.default_rng(21)
+    _run_ragged(capi, rng, [1, 129, 64, 300, 7], [5, 129, 200, 300, 7], 32, 8, 128, dtype, causal=causal)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_ragged_inline_rope(capi, dtype):
+    rng = np.random.default_rng(22)
+    _run_ragged(capi, rng, [10, 70], [10, 70], 32, 8, 128, dtype, rotary_mode=1)
+
+
+def _dfs_mask(parents):
+    """(dfs_order, subtree_end) rows as ConstructTokenTreeMask emits them (paged_kv_cache.cc:1900-1918)."""
+    n = len(parents)
+    children = [[] for _ in range(n)]
+    roots = []
+    for i, p in enumerate(parents):
+        (roots if p < 0 else children[p]).append(i)
+    order = [0] * n
+    end = [0] * n
+    cnt = 0
+
+    def visit(u):
+        nonlocal cnt
+        order[u] = cnt
+        cnt += 1
+        for c in children[u]:
+            visit(c)
+        end[u] = cnt
+
+    for r in roots:
+        visit(r)
+    return np.array([[order[i], end[i]] for i in range(n)], np.int32)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_tree_ragged(capi, dtype):
+    rng = np.random.default_rng(23)
+    trees = [[-1, 0, 0, 1], [(k - 1) // 2 if k else -1 for k in range(64)], [-1, 0, 1, 2, 3, 4, 5]]
+    masks = [_dfs_mask(t) for t in trees]
+    mn = np.zeros(len(trees) + 1, np.int32)
+    mn[1:] = np.cumsum([len(t) for t in trees])
+    lens = [len(t) for t in trees]
+    _run_ragged(capi, rng, lens, lens, 32, 8, 128, dtype, tree=(mn, np.concatenate(masks)))
+
+
+def _run_paged_prefill(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=0, rotary_mode=0, sliding=None,
+                       layer_sws=0, tree=None):
+    import torch
+
+    B = len(q_lens)
+    qi = np.zeros(B + 1, np.int32)
+    qi[1:] = np.cumsum(q_lens)
+    n = int(qi[-1])
+    c = make_paged_cache(rng, kv_lens, hkv, d, dtype, sliding=sliding)
+    q = rand16(rng, (n, hq, d), dtype)
+    kofs = rng.integers(0, 30, B).astype(np.int32)
+    qpos = np.concatenate([kofs[b] + kv_lens[b] + np.arange(q_lens[b]) for b in range(B)]).astype(np.int32)
+    sm = d ** -0.5
+    dq = to_dev(q, dtype)
+    o = torch.full((n, hq, d), float("nan"), dtype=dq.dtype, device="cuda")
+    lse = torch.full((n, hq), float("nan"), dtype=torch.float32, device="cuda")
+    args = (dq, _i32(qi), to_dev(c["pages"], dtype), _i32(c["page_indptr"]), _i32(c["page_values"]),
+            _i32(c["length_info"]), _i32(kofs), _i32(qpos), o, lse)
+    if tree is None:
+        wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"],
+                                            kofs, qpos, causal, rotary_mode, 1.0, 1e4, sm, dtype,
+                                            sliding_window_size=layer_sws)
+        capi.attention_prefill_paged(*args, causal, rotary_mode, 1.0, 1e4, sm, layer_sliding_window_size=layer_sws)
+    else:
+        ti, to = tree
+        wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"],
+                                            kofs, qpos, 0, rotary_mode, 1.0, 1e4, sm, dtype, tree_indptr=ti,
+                                            tree_order=to)
+        capi.attention_prefill_tree_paged(*args, rotary_mode, 1.0, 1e4, sm, _i32(ti), _i32(to))
+    torch.cuda.synchronize()
+    # rows whose mask hides every column are outside the comparison (see DESIGN.md "fully masked rows")
+    assert_close("paged prefill O", to_np(o), wo)
+    assert_close("paged prefill LSE", to_np(lse), wl)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("causal", [0, 1])
+def test_prefill_paged(capi, dtype, causal):
+    rng = np.random.default_rng(30)
+    # causal=1 needs kv_len >= qo_len (cache already holds the new tokens)
+    _run_paged_prefill(capi, rng, [3, 17, 1, 64, 5], [16, 18, 0 if not causal else 1, 300, 77], 32, 8, 128, dtype,
+                       causal=causal)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_paged_hd64_gqa8(capi, dtype):
+    rng = np.random.default_rng(31)
+    _run_paged_prefill(capi, rng, [10, 33], [100, 47], 32, 4, 64, dtype, causal=0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_paged_sliding_and_inline_rope(capi, dtype):
+    rng = np.random.default_rng(32)
+    _run_paged_prefill(capi, rng, [4, 9, 2], [100, 64, 33], 32, 8, 128, dtype, causal=0, rotary_mode=1,
+                       sliding=[(37, 4), (16, 16), (0, 0)])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_paged_tree(capi, dtype):
+    rng = np.random.default_rng(33)
+    trees = [[-1, 0, 0, 1], [(k - 1) // 2 if k else -1 for k in range(15)]]
+    masks = [_dfs_mask(t) for t in trees]
+    ti = np.zeros(len(trees) + 1, np.int32)
+    ti[1:] = np.cumsum([len(t) for t in trees])
+    # the tree occupies the trailing columns of the cached KV; q rows = the tree nodes
+    _run_paged_prefill(capi, rng, [4, 15], [4 + 20, 15 + 200], 32, 8, 128, dtype, tree=(ti, np.concatenate(masks)))
+
+
+def test_kat_paged_prefill_layer_sliding_window(capi):
+    """Known-answer test of the reference, literal copy of its inputs:
+    tests/python/relax/test_runtime_builtin_paged_attention_kv_cache_tir.py:96-156
+    (head_dim 64, 2 kv / 4 qo heads, V rows = 1,3,5, zero Q/K, window 3 => output [4, 5])."""
+    import math
+
+    import torch
+
+    head_dim, hkv, hq, page = 64, 2, 4, 16
+    pages = np.zeros((1, 2, hkv, page, head_dim), np.float32)
+    for position, value in enumerate([1, 3, 5]):
+        pages[0, 1, :, position, :] = value
+    q = np.zeros((2, hq, head_dim), np.float32)
+    dq = to_dev(q, "float16")
+    o = torch.zeros((2, hq, head_dim), dtype=torch.float16, device="cuda")
+    lse = torch.zeros((2, hq), dtype=torch.float32, device="cuda")
+    capi.attention_prefill_paged(dq, _i32([0, 2]), to_dev(pages, "float16"), _i32([0, 1]), _i32([0]),
+                                 _i32([[3], [0], [0]]), _i32([0]), _i32([3, 4]), o, lse, 1, 0, 1.0, 10000.0,
+                                 1 / math.sqrt(head_dim), layer_sliding_window_size=3)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(to_np(o)[:, 0, 0], [4.0, 5.0], rtol=1e-3, atol=1e-3)
+    # and the oracle gives the same known answer
+    wo, _ = ok.attention_prefill_paged(q, [0, 2], pages, [0, 1], [0], np.array([[3], [0], [0]]), [0], [3, 4], 1, 0,
+                                       1.0, 1e4, 1 / math.sqrt(head_dim), "float16", sliding_window_size=3)
+    np.testing.assert_allclose(wo[:, 0, 0], [4.0, 5.0], rtol=1e-3, atol=1e-3)
+
+
+def test_errors_are_loud(capi):
+    import torch
+
+    pages = torch.zeros((3, 2, 8, 16, 128), dtype=torch.float32, device="cuda")
+    with pytest.raises(capi.TvmB200Error):
+        capi.transpose_append(pages, pages, pages, pages)  # unsupported dtype
+    cpu = torch.zeros((3, 2, 8, 16, 128), dtype=torch.float16)
+    with pytest.raises(capi.TvmB200Error):
+        capi.transpose_append(cpu, cpu, cpu, cpu)  # no CPU fallback

@@ -1,0 +1,185 @@
+"""ctypes binding of the C ABI declared in include/tvm_b200.h.
+
+Tensors are passed as raw device pointers; the thin helpers below accept torch CUDA tensors (torch is
+only the device-memory / stream plumbing) and launch on torch's current stream.  There is no CPU
+fallback: a missing library raises at load time, a CPU tensor raises at call time.
+"""
+from __future__ import annotations
+
+import ctypes
+import re
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+LIB_PATH = ROOT / "lib" / "libtvm_b200.so"
+HEADER_PATH = ROOT.parent / "include" / "tvm_b200.h"
+
+F16, BF16 = 0, 1
+
+_lib = None
+
+
+class TvmB200Error(RuntimeError):
+    pass
+
+
+def declared_symbols() -> list[str]:
+    """Every `tvmb200_*` entry point declared in include/tvm_b200.h."""
+    text = HEADER_PATH.read_text()
+    return sorted(set(re.findall(r"TVMB200_API[^;]*?\b(tvmb200_\w+)\s*\(", text, flags=re.S)))
+
+
+def lib() -> ctypes.CDLL:
+    """Load tvm_b200/lib/libtvm_b200.so (built by `python -m tvm_b200.build`); fails loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TvmB200Error(
+            f"{LIB_PATH} is missing: the sm_100a kernels are not built (run `python -m tvm_b200.build`). "
+            "There is no CPU fallback."
+        )
+    L = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+    L.tvmb200_last_error.restype = c_char_p
+    L.tvmb200_version.restype = c_char_p
+    L.tvmb200_launch_count.restype = c_int64
+    L.tvmb200_reserve_workspace.argtypes = [c_int, c_int64]
+    L.tvmb200_set_layer_sliding_window_size.argtypes = [c_int32]
+    L.tvmb200_set_layer_sliding_window_size.restype = None
+    P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
+    L.tvmb200_transpose_append.argtypes = [P, P, P, P, I64, I64, I32, I32, I32, c_int, P]
+    L.tvmb200_debug_get_kv.argtypes = [P, P, P, P, I64, I64, I64, I64, I32, I32, I32, c_int, P]
+    L.tvmb200_copy_single_page.argtypes = [P, I64, I64, I64, I64, I32, I32, I32, c_int, P]
+    L.tvmb200_compact_kv_copy.argtypes = [P, P, P, I32, I32, I64, I32, I32, I32, c_int, P]
+    L.tvmb200_split_rotary.argtypes = [P, P, P, P, P, I64, I32, I32, I32, I32, I64, F, F, c_int, P]
+    L.tvmb200_merge_state_inplace.argtypes = [P, P, P, P, I64, I32, I32, c_int, P]
+    L.tvmb200_attention_decode.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
+                                           c_int, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_prefill_paged.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I64, I32, I32,
+                                                  I32, I32, c_int, I32, c_int, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_prefill_ragged.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32,
+                                                   c_int, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_prefill_tree_ragged.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32,
+                                                        I32, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_prefill_tree_paged.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I64, I32,
+                                                       I32, I32, I32, c_int, F, F, F, P, P, c_int, P]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise TvmB200Error(lib().tvmb200_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(lib().tvmb200_launch_count())
+
+
+# ---- torch-tensor helpers -------------------------------------------------------------------------
+def _dt(t) -> int:
+    import torch
+
+    if t.dtype == torch.float16:
+        return F16
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TvmB200Error(f"unsupported dtype {t.dtype}: the sm_100a kernels take float16 / bfloat16")
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TvmB200Error("tensor is not on a CUDA device; tvm_b200 has no CPU fallback")
+    if not t.is_contiguous():
+        raise TvmB200Error("tensor must be compact row-major")
+    return c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    import torch
+
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def transpose_append(pages, k, v, position_map):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_transpose_append(_p(pages), _p(k), _p(v), _p(position_map), k.shape[0], P, Hkv, page, D,
+                                          _dt(pages), _stream(pages)))
+
+
+def debug_get_kv(pages, position_map, k_out, v_out, layer_id):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_debug_get_kv(_p(pages), _p(position_map), _p(k_out), _p(v_out), layer_id, k_out.shape[0],
+                                      k_out.shape[1], P, Hkv, page, D, _dt(pages), _stream(pages)))
+
+
+def copy_single_page(pages, src, tgt, copy_length):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_copy_single_page(_p(pages), src, tgt, copy_length, P, Hkv, page, D, _dt(pages), _stream(pages)))
+
+
+def compact_kv_copy(pages, copy_length_indptr, copy_src_dst_pos, batch_size):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_compact_kv_copy(_p(pages), _p(copy_length_indptr), _p(copy_src_dst_pos), batch_size,
+                                         copy_src_dst_pos.shape[1], P, Hkv, page, D, _dt(pages), _stream(pages)))
+
+
+def split_rotary(qkv, position_map, q, k, v, apply_rope, rope_scale, rope_theta, rotary_dim=0):
+    _check(lib().tvmb200_split_rotary(_p(qkv), _p(position_map), _p(q), _p(k), _p(v), qkv.shape[0], q.shape[1],
+                                      k.shape[1], qkv.shape[2], rotary_dim, apply_rope, rope_scale, rope_theta,
+                                      _dt(qkv), _stream(qkv)))
+
+
+def merge_state_inplace(v, s, v_other, s_other):
+    _check(lib().tvmb200_merge_state_inplace(_p(v), _p(s), _p(v_other), _p(s_other), v.shape[0], v.shape[1],
+                                             v.shape[2], _dt(v), _stream(v)))
+
+
+def attention_decode(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output,
+                     lse, rotary_mode, rope_scale, rope_theta, sm_scale):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_attention_decode(
+        _p(q), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
+        _p(q_rope_position), _p(output), _p(lse), q.shape[0], page_values.shape[0], P, q.shape[1], Hkv, page, D,
+        1 if length_info.dim() == 2 else 0, rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages), _stream(q)))
+
+
+def attention_prefill_paged(q, q_indptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset,
+                            q_rope_position, output, lse, causal, rotary_mode, rope_scale, rope_theta, sm_scale,
+                            layer_sliding_window_size=0):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_attention_prefill_paged(
+        _p(q), _p(q_indptr), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
+        _p(q_rope_position), _p(output), _p(lse), q_indptr.shape[0] - 1, q.shape[0], page_values.shape[0], P,
+        q.shape[1], Hkv, page, D, 1 if length_info.dim() == 2 else 0, layer_sliding_window_size, causal,
+        rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages), _stream(q)))
+
+
+def attention_prefill_ragged(q, q_indptr, k, v, kv_indptr, q_rope_position, k_rope_pos_offset, output, lse, causal,
+                             rotary_mode, rope_scale, rope_theta, sm_scale):
+    _check(lib().tvmb200_attention_prefill_ragged(
+        _p(q), _p(q_indptr), _p(k), _p(v), _p(kv_indptr), _p(q_rope_position), _p(k_rope_pos_offset), _p(output),
+        _p(lse), q_indptr.shape[0] - 1, q.shape[0], k.shape[0], q.shape[1], k.shape[1], q.shape[2], causal,
+        rotary_mode, rope_scale, rope_theta, sm_scale, _dt(q), _stream(q)))
+
+
+def attention_prefill_tree_ragged(q, q_indptr, k, v, kv_indptr, q_rope_position, mn_indptr, mask, output, lse,
+                                  rotary_mode, rope_scale, rope_theta, sm_scale):
+    _check(lib().tvmb200_attention_prefill_tree_ragged(
+        _p(q), _p(q_indptr), _p(k), _p(v), _p(kv_indptr), _p(q_rope_position), _p(mn_indptr), _p(mask), _p(output),
+        _p(lse), q_indptr.shape[0] - 1, q.shape[0], k.shape[0], q.shape[1], k.shape[1], q.shape[2], rotary_mode,
+        rope_scale, rope_theta, sm_scale, _dt(q), _stream(q)))
+
+
+def attention_prefill_tree_paged(q, q_indptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset,
+                                 q_rope_position, output, lse, rotary_mode, rope_scale, rope_theta, sm_scale,
+                                 tree_order_indptr, tree_order):
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_attention_prefill_tree_paged(
+        _p(q), _p(q_indptr), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
+        _p(q_rope_position), _p(output), _p(lse), q_indptr.shape[0] - 1, q.shape[0], page_values.shape[0], P,
+        q.shape[1], Hkv, page, D, rotary_mode, rope_scale, rope_theta, sm_scale, _p(tree_order_indptr),
+        _p(tree_order), _dt(pages), _stream(q)))

@@ -1,0 +1,57 @@
+"""The sm_100a library as a tvm-ffi module: packed functions under the reference's callback names.
+
+`module()["f_attention_decode"]` etc. are `tvm_ffi.Function`s with the exact positional signatures the
+reference's PagedAttentionKVCacheObj calls (src/runtime/vm/attn_backend.h:234-243, 388-396, 507-515,
+618-627, 665-673; paged_kv_cache.cc:1360-1373, 728, 759, 1718, 2292), so they can be handed to
+`vm.builtin.paged_attention_kv_cache_create` as `["tirx", fn]` tuples.
+Kernels launch on the tvm-ffi environment stream (TVMFFIEnvGetStream), like the reference's kernels.
+"""
+from __future__ import annotations
+
+from . import capi
+
+CALLBACKS = [
+    "f_transpose_append", "f_attention_decode", "f_attention_decode_sliding_window", "f_attention_prefill",
+    "f_attention_prefill_sliding_window", "f_attention_prefill_ragged", "f_attention_prefill_with_tree_mask",
+    "f_attention_prefill_with_tree_mask_paged_kv", "f_merge_inplace", "f_split_rotary", "f_copy_single_page",
+    "f_debug_get_kv", "f_compact_copy",
+]
+# global_symbols of the reference PrimFuncs the callbacks replace
+TIR_NAMES = [
+    "tir_kv_cache_transpose_append", "batch_decode_paged_kv", "batch_decode_paged_kv_sliding_window",
+    "batch_prefill_paged_kv", "batch_prefill_paged_kv_sliding_window", "batch_prefill_ragged_kv", "batch_tree_attn",
+    "tree_attn_paged_kv", "merge_state_inplace", "fused_rope", "copy_single_page", "tir_kv_cache_debug_get_kv",
+    "compact_kv_copy",
+]
+STATE = ["set_rope_params", "set_layer_sliding_window_size", "launch_count"]
+
+_mod = None
+
+
+def module():
+    """tvm_ffi.load_module(libtvm_b200.so); fails loudly when the library is not built."""
+    global _mod
+    if _mod is None:
+        import tvm_ffi
+
+        if not capi.LIB_PATH.exists():
+            raise capi.TvmB200Error(f"{capi.LIB_PATH} is missing: run `python -m tvm_b200.build` (no CPU fallback)")
+        _mod = tvm_ffi.load_module(str(capi.LIB_PATH))
+    return _mod
+
+
+def torch_stream(ctx=None):
+    """Context manager that makes the tvm-ffi environment stream follow torch's current stream."""
+    import tvm_ffi
+
+    return tvm_ffi.use_torch_stream(ctx) if ctx is not None else tvm_ffi.use_torch_stream()
+
+
+def register_globals(prefix: str = "tvm_b200.") -> None:
+    """Register every callback as a tvm-ffi global function `<prefix><name>` (how a Relax-VM process
+    would look them up: tvm_ffi.get_global_func)."""
+    import tvm_ffi
+
+    m = module()
+    for name in CALLBACKS + STATE:
+        tvm_ffi.register_global_func(prefix + name, m[name], override=True)
