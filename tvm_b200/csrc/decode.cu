@@ -67,7 +67,7 @@ struct DecodeCfg {
   static constexpr int kHalfBytes = kPage * 128;           // 2 KiB per TMA box
 };
 
-template <typename T, int D, int NW, int NSTAGE>
+template <typename T, int D, int NW, int NSTAGE, bool ROPE>
 __global__ void __launch_bounds__(NW * 32)
 decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   using Cfg = DecodeCfg<D>;
@@ -82,6 +82,10 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   const uint32_t bars_base = smem_base + NW * NSTAGE * Cfg::kStageBytes;
   int* s_chunk_off = reinterpret_cast<int*>(smem_gen + NW * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8);
   int* s_scan_tmp = s_chunk_off + (p.batch + 1);
+  // inline-RoPE scratch (rotary_mode == 1 only): D/2 frequency denominators + the rotated Q group
+  float* s_denom = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(s_scan_tmp + 40) + 15) & ~static_cast<uintptr_t>(15));
+  T* s_q = reinterpret_cast<T*>(s_denom + D / 2);
   auto bar_addr = [&](int w, int s) -> uint32_t { return bars_base + (w * NSTAGE + s) * 8; };
 
   // ---- setup: barriers, work enumeration -----------------------------------------------------
@@ -97,6 +101,10 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   }
   __syncthreads();
   block_exclusive_scan(s_chunk_off, B, s_scan_tmp);
+  if (ROPE) {
+    for (int d = threadIdx.x; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta);
+    __syncthreads();
+  }
   const int total_chunks = s_chunk_off[B];
   if (blockIdx.x == 0) {
     for (int b = threadIdx.x; b <= B; b += blockDim.x) p.chunk_off[b] = s_chunk_off[b];
@@ -144,7 +152,27 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
 
     // ---- Q^T fragments (B operand, [k = d][n = q head]) -----------------------------------------
     uint32_t qf[KS][2];
-    {
+    if (ROPE) {
+      // rotate the group's Q rows at q_rope_position[b] into shared memory (_kernel_common.py:115-127)
+      const float qpos = static_cast<float>(p.q_rope_position[b]) * p.rope_scale;
+      const T* qg = static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g) * D;
+      for (int it = threadIdx.x; it < g * (D / 2); it += blockDim.x) {
+        const int qh = it / (D / 2), d = it - qh * (D / 2);
+        float sn, cs;
+        sincosf(qpos / s_denom[d], &sn, &cs);
+        const T xl = qg[qh * D + d], xh = qg[qh * D + d + D / 2];
+        s_q[qh * D + d] = DT<T>::from_f(cs * DT<T>::to_f(xl) + sn * DT<T>::to_f(DT<T>::neg(xh)));
+        s_q[qh * D + d + D / 2] = DT<T>::from_f(cs * DT<T>::to_f(xh) + sn * DT<T>::to_f(xl));
+      }
+      __syncthreads();
+      const bool qv = qrow < g;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int d0 = ks * 16 + (lane & 3) * 2;
+        qf[ks][0] = qv ? *reinterpret_cast<const uint32_t*>(s_q + qrow * D + d0) : 0u;
+        qf[ks][1] = qv ? *reinterpret_cast<const uint32_t*>(s_q + qrow * D + d0 + 8) : 0u;
+      }
+    } else {
       const T* qp = static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g + qrow) * D;
       const bool qv = qrow < g;
 #pragma unroll
@@ -225,6 +253,40 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
             }
           }
+        }
+        fence_proxy_async();  // generic-proxy writes before the next TMA refill of this stage
+        __syncwarp();
+      }
+
+      if (ROPE) {
+        // rotate the 16 K rows of this page in place at position k_rope_pos_offset[b] + kv row index
+        // (kv row index = position in the visible KV, i.e. slot mapped back through sink / window)
+        const int kofs = p.k_rope_pos_offset[b];
+        constexpr int HC = D / 16;  // 16-byte chunk pairs per row
+        for (int it = lane; it < 16 * HC; it += 32) {
+          const int r = it / HC, j = it - r * HC;
+          if (!((vmask >> r) & 1u)) continue;
+          const int slot = slot0 + r;
+          const int row_idx = slot < sink ? slot : slot - sw_off + sink;
+          const float pos = static_cast<float>(kofs + row_idx) * p.rope_scale;
+          const int cl = j, ch = j + HC;
+          const uint32_t al = kb + (cl >> 3) * Cfg::kHalfBytes + r * 128 + (((cl & 7) ^ (r & 7)) << 4);
+          const uint32_t ah = kb + (ch >> 3) * Cfg::kHalfBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+          uint4 lo, hi;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(al));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(ah));
+          T* le = reinterpret_cast<T*>(&lo);
+          T* he = reinterpret_cast<T*>(&hi);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float sn, cs;
+            sincosf(pos / s_denom[j * 8 + e], &sn, &cs);
+            const float xl = DT<T>::to_f(le[e]), xh = DT<T>::to_f(he[e]);
+            le[e] = DT<T>::from_f(cs * xl + sn * DT<T>::to_f(DT<T>::neg(he[e])));
+            he[e] = DT<T>::from_f(cs * xh + sn * xl);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(al), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ah), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
         }
         fence_proxy_async();  // generic-proxy writes before the next TMA refill of this stage
         __syncwarp();
@@ -469,13 +531,14 @@ int get_tmap_2d_cached(CUtensorMap* out, const void* base, int dtype, uint64_t r
   return 0;
 }
 
-template <typename T, int D, int NW, int NSTAGE>
-static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
+template <typename T, int D, int NW, int NSTAGE, bool ROPE>
+static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
                          cudaStream_t st) {
   using Cfg = DecodeCfg<D>;
   const size_t smem = 1024 + static_cast<size_t>(NW) * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8 +
-                      (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
-  auto kern = decode_kernel<T, D, NW, NSTAGE>;
+                      (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int) + 16 + (D / 2) * sizeof(float) +
+                      8 * D * sizeof(T);
+  auto kern = decode_kernel<T, D, NW, NSTAGE, ROPE>;
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<grid, NW * 32, smem, st>>>(tmap, p);
   TVMB200_LAUNCH_OK();
@@ -485,6 +548,14 @@ static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int gri
     TVMB200_LAUNCH_OK();
   }
   return 0;
+}
+
+template <typename T, int D, int NW, int NSTAGE>
+static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
+                         cudaStream_t st) {
+  // inline RoPE is a separate instantiation so the default (pre-rotated K) path keeps its register budget
+  return p.rotary_mode == 1 ? launch_decode_impl<T, D, NW, NSTAGE, true>(tmap, p, grid, need_merge, st)
+                            : launch_decode_impl<T, D, NW, NSTAGE, false>(tmap, p, grid, need_merge, st);
 }
 
 }  // namespace tvmb200
@@ -507,7 +578,7 @@ extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const 
   const int group = num_qo_heads / num_kv_heads;
   TVMB200_CHECK(group <= 8, "attention_decode: GQA group size %d > 8 unsupported", group);
   TVMB200_CHECK(batch_size <= kMaxBatchSmem, "attention_decode: batch %d exceeds %d", batch_size, kMaxBatchSmem);
-  TVMB200_CHECK(rotary_mode == 0, "attention_decode: inline RoPE (rotary_mode=1) is not implemented in the sm_100a path yet");
+  TVMB200_CHECK(rotary_mode == 0 || rotary_mode == 1, "attention_decode: rotary_mode %d (0 or 1)", rotary_mode);
   if (batch_size <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 

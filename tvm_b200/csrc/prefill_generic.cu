@@ -19,6 +19,8 @@
 //  * online softmax in the base-2 domain with the reference's -5e4 sentinel; LSE = m + log2(d).
 #include "prefill.cuh"
 
+#include <type_traits>
+
 namespace tvmb200 {
 
 constexpr int BM = 64;  // Q rows per CTA (4 warps x 16)
@@ -316,15 +318,25 @@ prefill_generic_kernel(const PrefillParams p) {
     for (int i = 0; i < NT_O; ++i) {
       o[i][0] *= f_a; o[i][1] *= f_a; o[i][2] *= f_b; o[i][3] *= f_b;
     }
+    // bf16 keeps only 8 mantissa bits of P; the reference keeps P in fp32.  Split P = hi + lo (two bf16
+    // parts, ~16 bits) so that rows dominated by a few keys stay inside the 2e-3 parity bar.
+    constexpr bool kSplitP = std::is_same<T, __nv_bfloat16>::value;
     uint32_t pf[BN / 16][4];
+    uint32_t pl[kSplitP ? BN / 16 : 1][4];
 #pragma unroll
     for (int i = 0; i < BN / 8; ++i) {
       const float p0 = fast_exp2(s[i][0] - m_a), p1 = fast_exp2(s[i][1] - m_a);
       const float p2 = fast_exp2(s[i][2] - m_b), p3 = fast_exp2(s[i][3] - m_b);
       d_a += p0 + p1;
       d_b += p2 + p3;
-      pf[i >> 1][(i & 1) * 2 + 0] = DT<T>::pack(p0, p1);
-      pf[i >> 1][(i & 1) * 2 + 1] = DT<T>::pack(p2, p3);
+      const uint32_t h01 = DT<T>::pack(p0, p1), h23 = DT<T>::pack(p2, p3);
+      pf[i >> 1][(i & 1) * 2 + 0] = h01;
+      pf[i >> 1][(i & 1) * 2 + 1] = h23;
+      if (kSplitP) {
+        const float2 f01 = DT<T>::to_f2(h01), f23 = DT<T>::to_f2(h23);
+        pl[i >> 1][(i & 1) * 2 + 0] = DT<T>::pack(p0 - f01.x, p1 - f01.y);
+        pl[i >> 1][(i & 1) * 2 + 1] = DT<T>::pack(p2 - f23.x, p3 - f23.y);
+      }
     }
 
     // ---- O += P V ----------------------------------------------------------------------------------
@@ -339,6 +351,10 @@ prefill_generic_kernel(const PrefillParams p) {
         ldmatrix_x4_trans(vb + swz<D>(row, np * 2 + (mi >> 1)), b0, b1, b2, b3);
         mma_16816<T>(o[np * 2], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
         mma_16816<T>(o[np * 2 + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
+        if (kSplitP) {
+          mma_16816<T>(o[np * 2], pl[kk][0], pl[kk][1], pl[kk][2], pl[kk][3], b0, b1);
+          mma_16816<T>(o[np * 2 + 1], pl[kk][0], pl[kk][1], pl[kk][2], pl[kk][3], b2, b3);
+        }
       }
     }
     __syncthreads();  // everyone is done with this stage before it is refilled
