@@ -117,22 +117,24 @@ class DecodeWorkload:
 class PrefillWorkload:
     """C3: 16 sequences x 2048 new tokens, empty cache -> ragged causal prefill (+ rotary + append)."""
 
-    def __init__(self, nseq=16, L=2048, Hq=32, Hkv=8, D=128, seed=0, device="cuda"):
+    def __init__(self, nseq=16, L=2048, Hq=32, Hkv=8, D=128, seed=0, device="cuda", dtype="bf16"):
         import torch
+
+        tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
 
         self.nseq, self.L, self.Hq, self.Hkv, self.D = nseq, L, Hq, Hkv, D
         n = nseq * L
         self.n = n
         g = torch.Generator(device=device)
         g.manual_seed(seed)
-        self.q = torch.randn((n, Hq, D), generator=g, device=device, dtype=torch.bfloat16)
-        self.k = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
-        self.v = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
+        self.q = torch.randn((n, Hq, D), generator=g, device=device, dtype=tdt)
+        self.k = torch.randn((n, Hkv, D), generator=g, device=device, dtype=tdt)
+        self.v = torch.randn((n, Hkv, D), generator=g, device=device, dtype=tdt)
         ip = (np.arange(nseq + 1) * L).astype(np.int32)
         self.indptr = torch.from_numpy(ip).to(device)
         self.qpos = torch.from_numpy(np.tile(np.arange(L, dtype=np.int32), nseq)).to(device)
         self.kofs = torch.zeros(nseq, dtype=torch.int32, device=device)
-        self.o = torch.empty((n, Hq, D), device=device, dtype=torch.bfloat16)
+        self.o = torch.empty((n, Hq, D), device=device, dtype=tdt)
         self.lse = torch.empty((n, Hq), device=device, dtype=torch.float32)
         self.sm_scale = D ** -0.5
 
@@ -368,7 +370,7 @@ def run_e2e(args, w, world):
 def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
     import torch
 
-    w = PrefillWorkload(seed=rank, device=dev)
+    w = PrefillWorkload(seed=rank, device=dev, dtype=args.dtype)
     for _ in range(max(args.warmup, 3)):
         w.run(capi)
     torch.cuda.synchronize()
@@ -386,7 +388,7 @@ def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
     peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
     out = {"metric": "prefill_tflops", "value": round(tf * world, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": K,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
            "config": {"workload": "C3 ragged causal prefill 16x2048, 32q/8kv heads, D128, bf16", "l2": "q/k/v/o "
                       "0.67 GB > L2"},
            "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": peak, "unit": "TFLOP/s",
@@ -424,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="decode", choices=["decode", "prefill"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -65,6 +65,15 @@ TVMB200_API int tvmb200_reserve_workspace(int device_id, int64_t bytes);
 TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
 
 /*!
+ * \brief Prefill implementation selector (test / profiling hook): 0 = auto (tcgen05 path for eligible shapes
+ *        with >= 2048 folded rows, generic mma.sync path otherwise), 1 = force generic, 2 = force tcgen05
+ *        wherever it is eligible (head_dim 128, rotary_mode 0, mask none/causal, no sliding window).
+ */
+TVMB200_API void tvmb200_set_prefill_impl(int impl);
+/*! \brief bf16 inputs on the tcgen05 path: 1 (default) keeps P in fp16 for the PV product, 0 uses bf16. */
+TVMB200_API void tvmb200_set_tc05_p_f16(int on);
+
+/*!
  * \brief f_transpose_append  (ctor arg 13; _page_kernels.py:40-74; called paged_kv_cache.cc:1371,1399)
  *  pages[pos/page_size, 0|1, h, pos%page_size, :] = k|v[t, h, :]  for pos = position_map[t] != -1.
  *  pages: [num_pages, 2, num_kv_heads, page_size, head_dim]; k, v: [ntoken, num_kv_heads, head_dim].

@@ -286,7 +286,7 @@ def test_prefill_tree_ragged(capi, dtype):
 
 
 def _run_paged_prefill(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=0, rotary_mode=0, sliding=None,
-                       layer_sws=0, tree=None):
+                       layer_sws=0, tree=None, nan_tail=False):
     import torch
 
     B = len(q_lens)
@@ -301,7 +301,13 @@ def _run_paged_prefill(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=0, 
     dq = to_dev(q, dtype)
     o = torch.full((n, hq, d), float("nan"), dtype=dq.dtype, device="cuda")
     lse = torch.full((n, hq), float("nan"), dtype=torch.float32, device="cuda")
-    args = (dq, _i32(qi), to_dev(c["pages"], dtype), _i32(c["page_indptr"]), _i32(c["page_values"]),
+    dpages = to_dev(c["pages"], dtype)
+    if nan_tail:  # poison every slot past kv_len of each sequence's last page (never visible to the oracle)
+        for b in range(B):
+            if kv_lens[b] % 16:
+                last = int(c["page_values"][c["page_indptr"][b + 1] - 1])
+                dpages[last, :, :, kv_lens[b] % 16:, :] = float("nan")
+    args = (dq, _i32(qi), dpages, _i32(c["page_indptr"]), _i32(c["page_values"]),
             _i32(c["length_info"]), _i32(kofs), _i32(qpos), o, lse)
     if tree is None:
         wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"],

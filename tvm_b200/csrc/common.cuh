@@ -49,6 +49,12 @@ int num_sms();  // SM count of the current device (cached)
 int get_workspace(int64_t bytes, void** out);
 int32_t layer_sliding_window_size();
 
+// TMA tensor maps (decode.cu): 2-D [rows][cols] with box [box_rows][64], cached by (base, shape); 3-D uncached
+int get_tmap_2d_cached(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows);
+int make_tmap_3d(CUtensorMap* out, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2);
+
 // ---------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------

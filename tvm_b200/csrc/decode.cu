@@ -495,6 +495,25 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, u
   return 0;
 }
 
+// 3-D view [d2][d1][d0] of a 16-bit tensor with byte strides (stride1, stride2); box = [b2][b1][64], 128B swizzle
+int make_tmap_3d(CUtensorMap* out, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2) {
+  PFN_encodeTiled fn = get_encode_fn();
+  TVMB200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TVMB200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA needs a 16-byte aligned base pointer");
+  TVMB200_CHECK(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA needs 16-byte aligned strides");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {64, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, dtype == TVMB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TVMB200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
 struct TmapKey {
   const void* base;
   uint64_t rows, cols;

@@ -43,4 +43,9 @@ struct PrefillParams {
 int launch_prefill_generic(const PrefillParams& p, bool paged, int total_q_len, int head_dim, int dtype,
                            cudaStream_t st);
 
+// tcgen05 / TMEM path (prefill_tc05.cu): D = 128, rotary_mode 0, mask none / causal, no sliding window
+bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim);
+int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int total_kv_len, int64_t num_pages,
+                        int dtype, cudaStream_t st);
+
 }  // namespace tvmb200

@@ -60,6 +60,8 @@ extern "C" int tvmb200_attention_prefill_paged(
   } else {
     p.mask_mode = causal > 0 ? kMaskCausal : kMaskNone;
   }
+  if (tc05_eligible(p, true, total_q_len, head_dim))
+    return launch_prefill_tc05(p, true, total_q_len, 0, num_pages, dtype, static_cast<cudaStream_t>(stream));
   return launch_prefill_generic(p, true, total_q_len, head_dim, dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -80,6 +82,8 @@ extern "C" int tvmb200_attention_prefill_ragged(
   p.k_rope_pos_offset = k_rope_pos_offset;
   p.q_rope_position = q_rope_position;
   p.mask_mode = causal > 0 ? kMaskCausal : kMaskNone;
+  if (tc05_eligible(p, false, total_q_len, head_dim))
+    return launch_prefill_tc05(p, false, total_q_len, total_kv_len, 0, dtype, static_cast<cudaStream_t>(stream));
   return launch_prefill_generic(p, false, total_q_len, head_dim, dtype, static_cast<cudaStream_t>(stream));
 }
 

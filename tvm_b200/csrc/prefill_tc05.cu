@@ -1,0 +1,450 @@
+// Batch prefill attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Serves f_attention_prefill_ragged (K4) and f_attention_prefill (K3) for the hot configurations:
+// head_dim 128, rotary_mode 0 (K pre-rotated: RoPEMode::kNormal / kNone), mask none or causal, no
+// per-sequence sliding window, GQA group in {1,2,4,8,16}.  Everything else runs on prefill_generic.cu.
+// Reference semantics: python/tvm/relax/frontend/nn/llm/_prefill_kernels.py:217-391 (paged), :795-923
+// (ragged); numerics per _kernel_common.py:222-334 (base-2 online softmax, fp32 accumulate, LSE = m + log2 d).
+//
+// Design (one CTA = 256 GQA-folded query rows of one sequence x one KV head = two 128-row UMMA tiles):
+//   warp 0      TMA producer: Q tiles (3-D box: 64 cols x g heads x 128/g tokens = the reference's row fold
+//               row = token*g + head, _prefill_kernels.py:318-324) once, then K_j / V_j tiles of 128 KV rows
+//               through a 4-slot shared-memory ring (ragged: one 3-D box per 64-col half; paged: eight
+//               16-row page boxes per half, page ids looked up by the producer lanes).
+//   warp 1      MMA issuer (one elected thread): S_t = Q_t K_j^T (SS, K-major operands) into TMEM, and
+//               O_t += P_t V_j (TS: P read from TMEM, V as an MN-major shared-memory operand).  Issue order per
+//               KV tile: PV_0(j), QK_0(j+1), PV_1(j), QK_1(j+1) so the tensor pipe always has the other
+//               tile's work while one tile is in softmax.
+//   warp 2      TMEM allocator (512 columns: S_0,S_1,O_0,O_1; P_t aliases the first 64 columns of S_t).
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; tcgen05.ld the S row,
+//               mask (diagonal / tail tiles only), running max with LAZY rescale (O in TMEM is only rescaled
+//               when the max grows by more than 2^8), exp2, pack to 16-bit, tcgen05.st P, arrive.
+//               The same threads normalise and store O / LSE at the end.
+// All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); no __syncthreads in the loop.
+#include "prefill.cuh"
+#include "tc05.cuh"
+
+#include <type_traits>
+
+namespace tvmb200 {
+
+namespace {
+
+constexpr int kRows = 128;                 // rows of a UMMA tile (M)
+constexpr int kKV = 128;                   // KV rows per tile (N of QK^T, K of PV)
+constexpr int kD = 128;                    // head dim
+constexpr int kHalfBytes = kRows * 128;    // one 64-column half of a 128-row tile: 16 KiB
+constexpr int kTileBytes = 2 * kHalfBytes; // 32 KiB
+constexpr int kSlots = 4;                  // K/V ring
+constexpr int kThreads = 384;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
+
+struct SmemLayout {
+  static constexpr int q = 0;
+  static constexpr int kv = q + 2 * kTileBytes;
+  static constexpr int bars = kv + kSlots * kTileBytes;
+  static constexpr int tmem_ptr = bars + 128;
+  static constexpr int scan = bars + 256;
+};
+enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 11, PV_DONE = 13, NUM_BARS = 15 };
+
+template <typename PT>
+__device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
+  return DT<PT>::pack(lo, hi);
+}
+
+}  // namespace
+
+template <typename T, typename PT, bool PAGED>
+__global__ void __launch_bounds__(kThreads, 1)
+prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const PrefillParams p, const uint32_t idesc_qk,
+                    const uint32_t idesc_pv) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int B = p.batch, g = p.group;
+  int* s_tiles = reinterpret_cast<int*>(sgen + SmemLayout::scan);
+  int* s_tmp = s_tiles + B + 1;
+  auto bar = [&](int i) -> uint32_t { return sbase + SmemLayout::bars + i * 8; };
+
+  // ---- which (sequence, 256-row tile pair, kv head) is this CTA? --------------------------------------------
+  for (int b = tid; b < B; b += kThreads) {
+    const int rows = (p.q_indptr[b + 1] - p.q_indptr[b]) * g;
+    s_tiles[b] = (rows + 2 * kRows - 1) / (2 * kRows);
+  }
+  __syncthreads();
+  block_exclusive_scan(s_tiles, B, s_tmp);
+  const int n_items = s_tiles[B] * p.num_kv_heads;
+  if (static_cast<int>(blockIdx.x) >= n_items) return;
+  const int ritem = n_items - 1 - blockIdx.x;  // late (= long-KV under a causal mask) tiles first
+  const int tg = ritem / p.num_kv_heads;
+  const int h = ritem - tg * p.num_kv_heads;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_tiles[mid] <= tg) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int pair = tg - s_tiles[b];
+  const int q_beg = p.q_indptr[b];
+  const int qo_len = p.q_indptr[b + 1] - q_beg;
+  const int row0 = pair * 2 * kRows;            // first folded row of the CTA
+  const int tok0 = row0 / g;                    // first query token (relative to the sequence)
+  const int tok_per_tile = kRows / g;
+  const int nqt = (qo_len * g - row0 > kRows) ? 2 : 1;  // second tile entirely outside the sequence?
+
+  int kv_len, kv_beg = 0, pg_beg = 0, n_pages = 0;
+  if (PAGED) {
+    pg_beg = p.page_indptr[b];
+    n_pages = p.page_indptr[b + 1] - pg_beg;
+    kv_len = n_pages > 0 ? (n_pages - 1) * 16 + p.length_info[b] : 0;
+  } else {
+    kv_beg = p.kv_indptr[b];
+    kv_len = p.kv_indptr[b + 1] - kv_beg;
+  }
+  const bool causal = p.mask_mode == kMaskCausal;
+  // visible KV extent of the CTA's last valid token bounds the KV loop
+  const int tok_last = min(qo_len, tok0 + nqt * tok_per_tile) - 1;
+  const int kv_end = causal ? max(0, min(kv_len, kv_len - qo_len + tok_last + 1)) : kv_len;
+  const int n_kv = (kv_end + kKV - 1) / kKV;
+
+  // ---- one-time setup ------------------------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    if (!PAGED) tma_prefetch_desc(&tm_v);
+    mbar_init(bar(Q_FULL), 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(bar(KV_FULL + i), 1);
+      mbar_init(bar(KV_EMPTY + i), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(S_FULL + t), 1);
+      mbar_init(bar(P_READY + t), kRows);
+      mbar_init(bar(PV_DONE + t), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tc05::tmem_alloc(sbase + SmemLayout::tmem_ptr, 512);
+    tc05::tmem_relinquish();
+  }
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + SmemLayout::tmem_ptr);
+  const uint32_t sq = sbase + SmemLayout::q, skv = sbase + SmemLayout::kv;
+
+  if (warp < 4) {
+    tc05::setmaxnreg_dec<56>();
+    if (warp == 0) {
+      // =========================== TMA producer ===========================
+      if (n_kv > 0) {
+        if (lane == 0) {
+          mbar_expect_tx(bar(Q_FULL), nqt * kTileBytes);
+          for (int t = 0; t < nqt; ++t)
+            for (int hf = 0; hf < 2; ++hf)
+              tc05::tma_load_3d(sq + t * kTileBytes + hf * kHalfBytes, &tm_q, hf * 64, h * g,
+                                q_beg + tok0 + t * tok_per_tile, bar(Q_FULL), kEvictFirst);
+        }
+        for (int f = 0; f < 2 * n_kv; ++f) {
+          const int j = f >> 1, is_v = f & 1, slot = f & (kSlots - 1);
+          mbar_wait(bar(KV_EMPTY + slot), ((f / kSlots) & 1) ^ 1);
+          const uint32_t dst = skv + slot * kTileBytes;
+          if (!PAGED) {
+            if (lane == 0) {
+              mbar_expect_tx(bar(KV_FULL + slot), kTileBytes);
+              const CUtensorMap* tm = is_v ? &tm_v : &tm_k;
+              for (int hf = 0; hf < 2; ++hf)
+                tc05::tma_load_3d(dst + hf * kHalfBytes, tm, hf * 64, h, kv_beg + j * kKV, bar(KV_FULL + slot),
+                                  kEvictLast);
+            }
+          } else {
+            if (lane == 0) mbar_expect_tx(bar(KV_FULL + slot), kTileBytes);
+            __syncwarp();
+            if (lane < 16) {
+              const int i = lane >> 1, hf = lane & 1;
+              const int pi = min(j * 8 + i, n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
+              const int pid = __ldg(p.page_values + pg_beg + pi);
+              const int row = ((pid * 2 + is_v) * p.num_kv_heads + h) * 16;
+              tma_load_2d(dst + hf * kHalfBytes + i * 16 * 128, &tm_k, hf * 64, row, bar(KV_FULL + slot), kEvictLast);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // =========================== MMA issuer ===========================
+      if (n_kv > 0) {
+        auto issue_qk = [&](int t, uint32_t kslot) {
+          const uint32_t a0 = sq + t * kTileBytes, b0 = skv + kslot * kTileBytes;
+#pragma unroll
+          for (int s = 0; s < kD / 16; ++s) {
+            const uint32_t off = (s >> 2) * kHalfBytes + (s & 3) * 32;
+            tc05::mma_ss(tmem + t * 128, tc05::make_smem_desc(a0 + off, 16, 1024),
+                         tc05::make_smem_desc(b0 + off, 16, 1024), idesc_qk, s > 0);
+          }
+        };
+        auto issue_pv = [&](int t, uint32_t vslot, bool acc) {
+          const uint32_t b0 = skv + vslot * kTileBytes;
+#pragma unroll
+          for (int s = 0; s < kKV / 16; ++s) {
+            // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
+            tc05::mma_ts(tmem + 256 + t * 128, tmem + t * 128 + s * 8,
+                         tc05::make_smem_desc(b0 + s * 16 * 128, kHalfBytes, 1024), idesc_pv, (acc || s > 0) ? 1u : 0u);
+          }
+        };
+        mbar_wait(bar(Q_FULL), 0);
+        mbar_wait(bar(KV_FULL + 0), 0);  // K_0
+        tc05::fence_after_sync();
+        if (lane == 0) {
+          for (int t = 0; t < nqt; ++t) {
+            issue_qk(t, 0);
+            tc05::commit(bar(S_FULL + t));
+          }
+          tc05::commit(bar(KV_EMPTY + 0));
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+          const int fv = 2 * j + 1, fk = 2 * j + 2;
+          const int vslot = fv & (kSlots - 1), kslot = fk & (kSlots - 1);
+          const bool more = j + 1 < n_kv;
+          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
+          if (PAGED && !more) {
+            // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
+            // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
+            const int valid = kv_len - j * kKV;
+            if (valid < kKV) {
+              for (int it = lane; it < (kKV - valid) * 16; it += 32) {
+                const int r = valid + (it >> 4), c = it & 15;
+                const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+              }
+              fence_proxy_async();
+              __syncwarp();
+            }
+          }
+          if (more) mbar_wait(bar(KV_FULL + kslot), (fk / kSlots) & 1);
+          for (int t = 0; t < nqt; ++t) {
+            mbar_wait(bar(P_READY + t), j & 1);
+            tc05::fence_after_sync();
+            if (lane == 0) {
+              issue_pv(t, vslot, j > 0);
+              tc05::commit(bar(PV_DONE + t));
+              if (more) {
+                issue_qk(t, kslot);
+                tc05::commit(bar(S_FULL + t));
+              }
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            tc05::commit(bar(KV_EMPTY + vslot));
+            if (more) tc05::commit(bar(KV_EMPTY + kslot));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =========================== softmax / correction / epilogue ===========================
+    tc05::setmaxnreg_inc<216>();
+    const int t = (warp - 4) >> 2;          // which Q tile
+    const int wq = warp & 3;                // TMEM lane quarter of this warp
+    const int r = wq * 32 + lane;           // row within the tile
+    const int R = row0 + t * kRows + r;     // folded row within the sequence
+    const int tok = R / g;
+    const bool valid = t < nqt && tok < qo_len;
+    const int limit = causal ? max(0, min(kv_len, kv_len - qo_len + tok + 1)) : kv_len;  // visible columns [0, limit)
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t t_s = tmem + lane_addr + t * 128;
+    const uint32_t t_o = tmem + lane_addr + 256 + t * 128;
+    float m_used = kNegInit, l = 0.f;
+    const float sc = p.scale_log2;
+
+    if (t < nqt) {
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar(S_FULL + t), j & 1);
+        tc05::fence_after_sync();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tc05::ld32(t_s + 0, s0);
+        tc05::ld32(t_s + 32, s1);
+        tc05::ld32(t_s + 64, s2);
+        tc05::ld32(t_s + 96, s3);
+        tc05::wait_ld();
+        const int rem = limit - j * kKV;  // columns [0, rem) of this tile are visible
+        if (__any_sync(0xffffffffu, rem < kKV)) {
+          const uint32_t ninf = __float_as_uint(-INFINITY);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c >= rem) s0[c] = ninf;
+            if (c + 32 >= rem) s1[c] = ninf;
+            if (c + 64 >= rem) s2[c] = ninf;
+            if (c + 96 >= rem) s3[c] = ninf;
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+          mx = fmaxf(mx, fmaxf(__uint_as_float(s2[c]), __uint_as_float(s3[c])));
+        }
+        const float m_new = fmaxf(m_used, mx * sc);
+        // lazy rescale: keep the old reference max while the true max is within 2^8 of it
+        const bool grow = m_new - m_used > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
+          if (grow) {
+            m_used = m_new;
+            l *= alpha;
+          }
+          if (j > 0) {
+            mbar_wait(bar(PV_DONE + t), (j - 1) & 1);  // O_t must be complete before it is rescaled
+            tc05::fence_after_sync();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[32];
+              tc05::ld32(t_o + cc * 32, o);
+              tc05::wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tc05::st32(t_o + cc * 32, o);
+            }
+          }
+        }
+        const float mneg = -m_used;
+        float sum = 0.f;
+        uint32_t pk[64];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float a0 = fast_exp2(fmaf(__uint_as_float(s0[c]), sc, mneg));
+          const float a1 = fast_exp2(fmaf(__uint_as_float(s0[c + 1]), sc, mneg));
+          const float b0 = fast_exp2(fmaf(__uint_as_float(s1[c]), sc, mneg));
+          const float b1 = fast_exp2(fmaf(__uint_as_float(s1[c + 1]), sc, mneg));
+          const float c0 = fast_exp2(fmaf(__uint_as_float(s2[c]), sc, mneg));
+          const float c1 = fast_exp2(fmaf(__uint_as_float(s2[c + 1]), sc, mneg));
+          const float d0 = fast_exp2(fmaf(__uint_as_float(s3[c]), sc, mneg));
+          const float d1 = fast_exp2(fmaf(__uint_as_float(s3[c + 1]), sc, mneg));
+          sum += (a0 + a1) + (b0 + b1) + (c0 + c1) + (d0 + d1);
+          pk[(c >> 1)] = pack_p<PT>(a0, a1);
+          pk[16 + (c >> 1)] = pack_p<PT>(b0, b1);
+          pk[32 + (c >> 1)] = pack_p<PT>(c0, c1);
+          pk[48 + (c >> 1)] = pack_p<PT>(d0, d1);
+        }
+        l += sum;
+        tc05::st16(t_s + 0, pk);
+        tc05::st16(t_s + 16, pk + 16);
+        tc05::st16(t_s + 32, pk + 32);
+        tc05::st16(t_s + 48, pk + 48);
+        tc05::wait_st();
+        tc05::fence_before_sync();
+        mbar_arrive(bar(P_READY + t));
+      }
+      // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
+      T* orow = nullptr;
+      if (valid) {
+        const int hq = h * g + (R - tok * g);
+        orow = static_cast<T*>(p.output) + (static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq) * kD;
+        p.lse[static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq] = l > 0.f ? m_used + log2f(l) : kNegInit;
+      }
+      if (n_kv > 0) {
+        mbar_wait(bar(PV_DONE + t), (n_kv - 1) & 1);
+        tc05::fence_after_sync();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t o[32];
+          tc05::ld32(t_o + cc * 32, o);
+          tc05::wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              uint4 v;
+              v.x = DT<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+              v.y = DT<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+              v.z = DT<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+              v.w = DT<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + cc * 32 + c) = v;
+            }
+          }
+        }
+      } else if (valid) {
+        // no visible KV at all: O = 0, LSE = -5e4 (the reference's empty result)
+#pragma unroll
+        for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------------------
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc05::fence_after_sync();
+    tc05::tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static std::atomic<int> g_prefill_impl{0};   // 0 auto, 1 force generic, 2 force tcgen05 (where eligible)
+static std::atomic<int> g_tc05_p_f16{0};     // (experiment) mixed f16 x bf16 operands raise an illegal instruction on sm_100a
+
+bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim) {
+  const int impl = g_prefill_impl.load();
+  if (impl == 1) return false;
+  if (head_dim != kD || p.rotary_mode != 0 || p.sliding) return false;
+  if (p.mask_mode != kMaskNone && p.mask_mode != kMaskCausal) return false;
+  const int g = p.group;
+  if (!(g == 1 || g == 2 || g == 4 || g == 8 || g == 16)) return false;
+  if (p.batch > 2048) return false;
+  if (impl == 2) return true;
+  // auto: the 256-row tiles only pay off once there is enough work to fill them
+  return static_cast<int64_t>(total_q_len) * g >= 2048;
+}
+
+template <typename T, typename PT, bool PAGED>
+static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         int total_q_len, cudaStream_t st) {
+  const int64_t max_pairs = (static_cast<int64_t>(total_q_len) * p.group + 2 * kRows - 1) / (2 * kRows) + p.batch;
+  const int64_t grid = max_pairs * p.num_kv_heads;
+  const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
+  auto kern = prefill_tc05_kernel<T, PT, PAGED>;
+  TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
+  constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
+  const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
+  const uint32_t idesc_pv = tc05::make_idesc(fp, fa, 0, 1, kRows, kD);
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv);
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int total_kv_len, int64_t num_pages,
+                        int dtype, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  const int g = p.group;
+  const uint64_t row_q = static_cast<uint64_t>(p.num_qo_heads) * kD * 2;
+  if (int rc = make_tmap_3d(&tq, p.q, dtype, kD, p.num_qo_heads, total_q_len, kD * 2, row_q, g, kRows / g)) return rc;
+  if (paged) {
+    const uint64_t rows = static_cast<uint64_t>(num_pages) * 2 * p.num_kv_heads * 16;
+    if (int rc = get_tmap_2d_cached(&tk, p.pages, dtype, rows, kD, 16)) return rc;
+    tv = tk;
+  } else {
+    const uint64_t row_kv = static_cast<uint64_t>(p.num_kv_heads) * kD * 2;
+    if (int rc = make_tmap_3d(&tk, p.k, dtype, kD, p.num_kv_heads, total_kv_len, kD * 2, row_kv, 1, kKV)) return rc;
+    if (int rc = make_tmap_3d(&tv, p.v, dtype, kD, p.num_kv_heads, total_kv_len, kD * 2, row_kv, 1, kKV)) return rc;
+  }
+  if (dtype == TVMB200_F16)
+    return paged ? launch_tc05_t<__half, __half, true>(p, tq, tk, tv, total_q_len, st)
+                 : launch_tc05_t<__half, __half, false>(p, tq, tk, tv, total_q_len, st);
+  return paged ? launch_tc05_t<__nv_bfloat16, __nv_bfloat16, true>(p, tq, tk, tv, total_q_len, st)
+               : launch_tc05_t<__nv_bfloat16, __nv_bfloat16, false>(p, tq, tk, tv, total_q_len, st);
+}
+
+}  // namespace tvmb200
+
+extern "C" void tvmb200_set_prefill_impl(int impl) { tvmb200::g_prefill_impl.store(impl); }
+extern "C" void tvmb200_set_tc05_p_f16(int on) { tvmb200::g_tc05_p_f16.store(on ? 1 : 0); }
