@@ -70,8 +70,6 @@ TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
  *        wherever it is eligible (head_dim 128, rotary_mode 0, mask none/causal, no sliding window).
  */
 TVMB200_API void tvmb200_set_prefill_impl(int impl);
-/*! \brief bf16 inputs on the tcgen05 path: 1 (default) keeps P in fp16 for the PV product, 0 uses bf16. */
-TVMB200_API void tvmb200_set_tc05_p_f16(int on);
 
 /*!
  * \brief f_transpose_append  (ctor arg 13; _page_kernels.py:40-74; called paged_kv_cache.cc:1371,1399)

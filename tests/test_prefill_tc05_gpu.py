@@ -15,10 +15,8 @@ def tc05(built_lib):
 
     capi.lib()
     capi.set_prefill_impl(2)
-    capi.set_tc05_p_f16(True)
     yield capi
     capi.set_prefill_impl(0)
-    capi.set_tc05_p_f16(True)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -39,16 +37,6 @@ def test_tc05_ragged_groups(tc05, dtype, hq, hkv):
 def test_tc05_ragged_long(tc05, dtype):
     rng = np.random.default_rng(42)
     _run_ragged(tc05, rng, [700, 513], [700, 900], 32, 8, 128, dtype, causal=1)
-
-
-def test_tc05_ragged_bf16_p_bf16(tc05):
-    """P kept in bf16 (8 mantissa bits): still finite and close, but outside the parity bar for short rows --
-    this documents why the default keeps P in fp16."""
-    tc05.set_tc05_p_f16(False)
-    rng = np.random.default_rng(43)
-    with pytest.raises(AssertionError):
-        for _ in range(4):
-            _run_ragged(tc05, rng, [10, 20, 30, 40], [10, 20, 30, 40], 32, 8, 128, "bfloat16", causal=1)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

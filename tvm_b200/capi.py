@@ -49,8 +49,6 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_set_layer_sliding_window_size.restype = None
     L.tvmb200_set_prefill_impl.argtypes = [c_int]
     L.tvmb200_set_prefill_impl.restype = None
-    L.tvmb200_set_tc05_p_f16.argtypes = [c_int]
-    L.tvmb200_set_tc05_p_f16.restype = None
     P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
     L.tvmb200_transpose_append.argtypes = [P, P, P, P, I64, I64, I32, I32, I32, c_int, P]
     L.tvmb200_debug_get_kv.argtypes = [P, P, P, P, I64, I64, I64, I64, I32, I32, I32, c_int, P]
@@ -80,10 +78,6 @@ def _check(rc: int) -> None:
 def set_prefill_impl(impl: int) -> None:
     """0 auto, 1 force the generic mma.sync kernel, 2 force the tcgen05 kernel where eligible."""
     lib().tvmb200_set_prefill_impl(impl)
-
-
-def set_tc05_p_f16(on: bool) -> None:
-    lib().tvmb200_set_tc05_p_f16(1 if on else 0)
 
 
 def launch_count() -> int:

@@ -38,12 +38,18 @@ constexpr int kTileBytes = 2 * kHalfBytes; // 32 KiB
 constexpr int kSlots = 4;                  // K/V ring
 constexpr int kThreads = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
+// bf16 keeps 8 mantissa bits of P (the reference keeps P in fp32).  When a row of a tile has a weight
+// p > kLoTau * l (a few keys dominate: short rows, peaked attention) the tile gets a second PV pass with the
+// rounding residual P_lo = P - bf16(P) (stored next to P_hi in TMEM), which restores ~16 bits.  Flat tiles
+// (the common case at long context) keep the single pass: the rounding error there is << the 2e-3 parity bar.
+constexpr float kLoTau = 1.0f / 16.0f;
 
 struct SmemLayout {
   static constexpr int q = 0;
   static constexpr int kv = q + 2 * kTileBytes;
   static constexpr int bars = kv + kSlots * kTileBytes;
   static constexpr int tmem_ptr = bars + 128;
+  static constexpr int lo_flag = bars + 144;  // int[2]: tile t's current P has a P_lo part
   static constexpr int scan = bars + 256;
 };
 enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 11, PV_DONE = 13, NUM_BARS = 15 };
@@ -55,6 +61,17 @@ __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
 
 }  // namespace
 
+__device__ __forceinline__ bool wg_any(bool pred, int barrier_id) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %1, 0;\n\t"
+      "bar.red.or.pred pout, %2, 128, pin;\n\tselp.u32 %0, 1, 0, pout;\n\t}"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "r"(barrier_id)
+      : "memory");
+  return out != 0;
+}
+
 template <typename T, typename PT, bool PAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -65,6 +82,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int B = p.batch, g = p.group;
+  constexpr bool kLoPass = std::is_same<PT, __nv_bfloat16>::value;
   int* s_tiles = reinterpret_cast<int*>(sgen + SmemLayout::scan);
   int* s_tmp = s_tiles + B + 1;
   auto bar = [&](int i) -> uint32_t { return sbase + SmemLayout::bars + i * 8; };
@@ -186,13 +204,19 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                          tc05::make_smem_desc(b0 + off, 16, 1024), idesc_qk, s > 0);
           }
         };
-        auto issue_pv = [&](int t, uint32_t vslot, bool acc) {
+        auto issue_pv = [&](int t, uint32_t vslot, bool acc, bool with_lo) {
           const uint32_t b0 = skv + vslot * kTileBytes;
 #pragma unroll
           for (int s = 0; s < kKV / 16; ++s) {
             // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
             tc05::mma_ts(tmem + 256 + t * 128, tmem + t * 128 + s * 8,
                          tc05::make_smem_desc(b0 + s * 16 * 128, kHalfBytes, 1024), idesc_pv, (acc || s > 0) ? 1u : 0u);
+          }
+          if (with_lo) {
+#pragma unroll
+            for (int s = 0; s < kKV / 16; ++s)
+              tc05::mma_ts(tmem + 256 + t * 128, tmem + t * 128 + 64 + s * 8,
+                           tc05::make_smem_desc(b0 + s * 16 * 128, kHalfBytes, 1024), idesc_pv, 1u);
           }
         };
         mbar_wait(bar(Q_FULL), 0);
@@ -229,8 +253,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           for (int t = 0; t < nqt; ++t) {
             mbar_wait(bar(P_READY + t), j & 1);
             tc05::fence_after_sync();
+            const bool with_lo = kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * t) != 0;
             if (lane == 0) {
-              issue_pv(t, vslot, j > 0);
+              issue_pv(t, vslot, j > 0, with_lo);
               tc05::commit(bar(PV_DONE + t));
               if (more) {
                 issue_qk(t, kslot);
@@ -315,28 +340,47 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         const float mneg = -m_used;
         float sum = 0.f;
-        uint32_t pk[64];
+        // p in place (s regs), P_hi packed and stored 32 columns at a time
+        auto exp_pack_store = [&](uint32_t (&sr)[32], int chunk) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float a0 = fast_exp2(fmaf(__uint_as_float(s0[c]), sc, mneg));
-          const float a1 = fast_exp2(fmaf(__uint_as_float(s0[c + 1]), sc, mneg));
-          const float b0 = fast_exp2(fmaf(__uint_as_float(s1[c]), sc, mneg));
-          const float b1 = fast_exp2(fmaf(__uint_as_float(s1[c + 1]), sc, mneg));
-          const float c0 = fast_exp2(fmaf(__uint_as_float(s2[c]), sc, mneg));
-          const float c1 = fast_exp2(fmaf(__uint_as_float(s2[c + 1]), sc, mneg));
-          const float d0 = fast_exp2(fmaf(__uint_as_float(s3[c]), sc, mneg));
-          const float d1 = fast_exp2(fmaf(__uint_as_float(s3[c + 1]), sc, mneg));
-          sum += (a0 + a1) + (b0 + b1) + (c0 + c1) + (d0 + d1);
-          pk[(c >> 1)] = pack_p<PT>(a0, a1);
-          pk[16 + (c >> 1)] = pack_p<PT>(b0, b1);
-          pk[32 + (c >> 1)] = pack_p<PT>(c0, c1);
-          pk[48 + (c >> 1)] = pack_p<PT>(d0, d1);
-        }
+          for (int c = 0; c < 32; c += 2) {
+            const float a0 = fast_exp2(fmaf(__uint_as_float(sr[c]), sc, mneg));
+            const float a1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), sc, mneg));
+            sum += a0 + a1;
+            sr[c] = __float_as_uint(a0);
+            sr[c + 1] = __float_as_uint(a1);
+            pk[c >> 1] = pack_p<PT>(a0, a1);
+          }
+          tc05::st16(t_s + chunk * 16, pk);
+        };
+        exp_pack_store(s0, 0);
+        exp_pack_store(s1, 1);
+        exp_pack_store(s2, 2);
+        exp_pack_store(s3, 3);
         l += sum;
-        tc05::st16(t_s + 0, pk);
-        tc05::st16(t_s + 16, pk + 16);
-        tc05::st16(t_s + 32, pk + 32);
-        tc05::st16(t_s + 48, pk + 48);
+        if (kLoPass) {
+          // largest weight of this row in this tile vs. the running denominator
+          const float p_max = fast_exp2(fmaf(mx, sc, mneg));
+          const bool need_lo = wg_any(p_max > kLoTau * l, 1 + t);
+          if (need_lo) {
+            auto lo_store = [&](const uint32_t (&sr)[32], int chunk) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int c = 0; c < 32; c += 2) {
+                const float a0 = __uint_as_float(sr[c]), a1 = __uint_as_float(sr[c + 1]);
+                const float2 hi2 = DT<PT>::to_f2(pack_p<PT>(a0, a1));
+                pk[c >> 1] = pack_p<PT>(a0 - hi2.x, a1 - hi2.y);
+              }
+              tc05::st16(t_s + 64 + chunk * 16, pk);
+            };
+            lo_store(s0, 0);
+            lo_store(s1, 1);
+            lo_store(s2, 2);
+            lo_store(s3, 3);
+          }
+          if (r == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * t) = need_lo ? 1 : 0;
+        }
         tc05::wait_st();
         tc05::fence_before_sync();
         mbar_arrive(bar(P_READY + t));
@@ -390,7 +434,6 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static std::atomic<int> g_prefill_impl{0};   // 0 auto, 1 force generic, 2 force tcgen05 (where eligible)
-static std::atomic<int> g_tc05_p_f16{0};     // (experiment) mixed f16 x bf16 operands raise an illegal instruction on sm_100a
 
 bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim) {
   const int impl = g_prefill_impl.load();
@@ -447,4 +490,3 @@ int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int
 }  // namespace tvmb200
 
 extern "C" void tvmb200_set_prefill_impl(int impl) { tvmb200::g_prefill_impl.store(impl); }
-extern "C" void tvmb200_set_tc05_p_f16(int on) { tvmb200::g_tc05_p_f16.store(on ? 1 : 0); }
