@@ -1,0 +1,309 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference:
+its C++ PagedAttentionKVCacheObj (src/runtime/vm/paged_kv_cache.cc) over its own CPU TIR kernels.
+
+    bash oracle/ref_harness/build_tvm.sh /tmp/tvm_ref          # once, ~25 min
+    source /tmp/tvm_ref/env.sh && python oracle/ref_harness/gen_golden.py
+
+Each fixture holds a scenario "program" (the op list of one of the reference's own scenario tests,
+tests/python/relax/test_runtime_builtin_paged_attention_kv_cache_cpu.py:706-1104), and for every op what the
+reference did: the exact callback sequence with every int32 aux array and scalar it passed (bit-exact targets for
+our host cache), the attention outputs, and debug_get_kv dumps.  Inputs are regenerated from the recorded seeds
+(`qkv_for`), so only outputs are stored.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+OUT = os.path.join(HERE, "..", "..", "tests", "golden")
+
+
+def qkv_for(seed, num_layers, n, hq, hkv, d, dtype="float16"):
+    """The step's fused qkv input, [num_layers, n, hq + 2 hkv, d], U[0,1) like the reference tests."""
+    rng = np.random.default_rng(seed)
+    return rng.random((num_layers, n, hq + 2 * hkv, d), dtype=np.float32).astype(dtype)
+
+
+# ---- programs (op lists) -------------------------------------------------------------------------------------------
+class Program:
+    def __init__(self):
+        self.ops = []
+        self.known = set()
+        self.seed = 1000
+
+    def clear(self):
+        self.ops.append({"op": "clear"})
+        self.known = set()
+
+    def forward(self, batch, trees=None, leaves=None):
+        """batch items: (seq_id, len) or ((seq_id, parent, fork_pos), len) -- the reference's apply_attention."""
+        seq_ids, lens = [], []
+        for item, ln in batch:
+            if isinstance(item, tuple):
+                sid, parent, pos = item
+                self.ops.append({"op": "fork", "parent": parent, "child": sid, "pos": pos})
+                self.known.add(sid)
+            else:
+                sid = item
+                if sid not in self.known:
+                    self.ops.append({"op": "add", "seq": sid})
+                    self.known.add(sid)
+            seq_ids.append(sid)
+            lens.append(ln)
+        flat = None
+        if trees is not None:
+            flat = []
+            for t, ln in zip(trees, lens):
+                flat += t[-ln:]
+        self.seed += 1
+        self.ops.append({"op": "forward", "seq_ids": seq_ids, "lens": lens, "tree": flat, "seed": self.seed})
+        if leaves is not None:
+            self.ops.append({"op": "commit", "seq_ids": seq_ids, "leaves": leaves})
+
+    def op(self, **kw):
+        self.ops.append(kw)
+        if kw["op"] == "add":
+            self.known.add(kw["seq"])
+        if kw["op"] == "fork":
+            self.known.add(kw["child"])
+        if kw["op"] == "remove":
+            self.known.discard(kw["seq"])
+
+    def dump_all(self, lengths):
+        for sid, ln in lengths.items():
+            if ln > 0:
+                self.ops.append({"op": "debug_get_kv", "seq": sid, "start": 0, "end": ln})
+
+
+def prog_prefill_and_decode():
+    p = Program()
+    seqs = [[(0, 6)], [(1, 8)], [(2, 11)], [(3, 16)], [(4, 19), (5, 20)], [(6, 21), (7, 24)],
+            [(2, 5), (4, 7), (8, 24)], [(6, 13)], [(8, 19)], [(0, 1)], [(1, 3), (3, 8), (5, 12), (7, 11)]]
+    seqs += [[(i, 1) for i in range(9)]] * 2 + [[(0, 1), (2, 1), (4, 1), (6, 1), (8, 1)], [(4, 1), (5, 1), (6, 1), (7, 1), (8, 1)]]
+    ln = {}
+    for b in seqs:
+        p.forward(list(b))
+        for s, n in b:
+            ln[s] = ln.get(s, 0) + n
+    p.dump_all(ln)
+    return p
+
+
+def prog_remove_and_popn():
+    p = Program()
+    p.forward([(0, 35), (1, 88), (2, 17), (3, 4)])
+    p.forward([((4, 3, -1), 35)])
+    ln = {0: 35, 1: 88, 2: 17, 3: 4, 4: 39}
+    for sid, n in [(0, 17), (1, 57), (2, 16), (3, 0), (4, 37)]:
+        p.op(op="popn", seq=sid, n=n)
+        ln[sid] -= n
+    p.dump_all(ln)
+    p.forward([(0, 3), (1, 1), (2, 20), (4, 1)])
+    p.op(op="remove", seq=1)
+    p.forward([(0, 1), (2, 1), (3, 1), (4, 1)])
+    for s in (0, 2, 3, 4):
+        p.op(op="remove", seq=s)
+    p.op(op="query")
+    return p
+
+
+def prog_fork():
+    p = Program()
+    p.forward([(0, 60), (1, 88), (2, 17), (3, 4)])
+    p.forward([((4, 3, -1), 35)])
+    p.forward([((5, 0, -1), 20)])
+    p.forward([((6, 5, -1), 102)])
+    p.forward([((7, 0, -1), 3)])
+    p.forward([((8, 5, -1), 71), ((9, 5, -1), 20)])
+    for b in [[(2, 1), (4, 1), (7, 1), (6, 1), (8, 1), (9, 1)], [(7, 1), (6, 1), (8, 1), (9, 1)],
+              [(7, 1), (1, 1), (6, 1), (2, 1), (8, 1), (4, 1), (9, 1)], [(7, 10), (6, 2), (8, 3), (9, 4)]]:
+        p.forward(b)
+    p.forward([((10, 1, 33), 11)])
+    p.forward([((11, 0, 60), 45), ((12, 0, 15), 14)])
+    p.forward([((13, 0, 16), 19), ((14, 0, 17), 19)])
+    p.forward([((15, 5, 60), 8), ((16, 5, 80), 10)])
+    p.forward([((17, 5, 75), 11), ((18, 5, 76), 45), ((19, 5, 77), 14)])
+    for b in [[(6, 1), (11, 1), (13, 1), (9, 1)], [(10, 1), (16, 1), (18, 1), (19, 1)],
+              [(8, 1), (15, 1), (17, 1), (12, 1), (14, 1)], [(10, 10), (6, 2), (8, 3), (19, 4)]]:
+        p.forward(b)
+    p.op(op="debug_get_kv", seq=19, start=0, end=77 + 14 + 1 + 4)
+    p.op(op="debug_get_kv", seq=13, start=0, end=16 + 19 + 1)
+    for i in range(20):
+        p.op(op="remove", seq=i)
+    p.op(op="query")
+    # fork after page recycle
+    p.forward([(0, 7), (1, 24)])
+    p.forward([((2, 1, -1), 10)])
+    p.forward([((3, 0, -1), 20)])
+    p.forward([(2, 1), (3, 1)])
+    p.forward([(10, 7), (11, 24)])
+    p.forward([((12, 11, -1), 200)])
+    p.forward([(10, 1), (12, 1)])
+    return p
+
+
+def prog_unlimited_depth():
+    p = Program()
+    p.forward([(0, 30)])
+    for child, parent, n in [(1, 0, 15), (2, 1, 5), (3, 2, 20), (4, 3, 26), (5, 3, 18), (6, 5, 22), (7, 5, 12),
+                             (8, 7, 29), (9, 7, 9), (10, 9, 31), (11, 9, 4)]:
+        p.forward([((child, parent, -1), n)])
+    for b in [[(3, 1), (6, 1), (9, 1)], [(4, 1), (8, 1), (10, 1)], [(5, 1), (7, 1), (11, 1)]]:
+        p.forward(b)
+    p.op(op="debug_get_kv", seq=11, start=0, end=30 + 15 + 5 + 20 + 18 + 12 + 9 + 4 + 1)
+    for i in range(12):
+        p.op(op="remove", seq=i)
+    p.op(op="query")
+    return p
+
+
+def prog_sliding_window():
+    p = Program()
+    sw, sink = [20, 25, 30, 35, 40], [6, 4, 8, 3, 7]
+    for sid, (w, s) in enumerate(zip(sw, sink)):
+        p.op(op="add", seq=sid)
+        p.op(op="enable_sw", seq=sid, window=w, sink=s)
+    for b in [[(0, 4)], [(1, 6)], [(2, 6), (3, 7), (4, 7)], [(0, 20), (1, 19), (2, 30), (3, 35), (4, 40)],
+              [(0, 6), (1, 5), (2, 4), (3, 3), (4, 2)]]:
+        p.forward(b)
+    for _ in range(6):
+        p.forward([(i, 1) for i in range(5)])
+    for sid, w in enumerate(sw):
+        p.op(op="debug_get_kv", seq=sid, start=0, end=w)
+    return p
+
+
+def prog_sliding_window_fork():
+    p = Program()
+    for sid, (w, s) in enumerate(zip([30, 35, 40], [15, 20, 25])):
+        p.op(op="add", seq=sid)
+        p.op(op="enable_sw", seq=sid, window=w, sink=s)
+    p.forward([(0, 12), (1, 18), (2, 28)])
+    p.forward([((3, 0, 10), 8), ((4, 1, -1), 20), ((5, 2, 18), 18)])
+    p.forward([(0, 9), (1, 15), (2, 4), (3, 10), (4, 3), (5, 7)])
+    p.op(op="fork", parent=3, child=6, pos=18)
+    p.op(op="enable_sw", seq=6, window=25, sink=24)
+    p.forward([(3, 10), (6, 12)])
+    return p
+
+
+def prog_tree_attn():
+    p = Program()
+    p.forward([(0, 10), (1, 20), (2, 30), (3, 40)])
+    trees = [[-1, 0, 0, 1, 1, 2, 2], [-1, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6], [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8],
+             [-1, 0, 0, 1, 1, 2, 2, -1, 7, 7, 8, 8, 9, 9]]
+    p.forward([(0, 7), (1, 15), (2, 10), (3, 14)], trees=trees, leaves=[6, 11, 6, 13])
+    p.op(op="debug_get_kv", seq=1, start=0, end=20 + 4)
+    for _ in range(2):
+        p.forward([(i, 1) for i in range(4)])
+    # all chains
+    p.clear()
+    p.forward([(0, 10), (1, 20), (2, 30), (3, 40)])
+    chains = [list(range(-1, 6)), list(range(-1, 14)), list(range(-1, 9)), list(range(-1, 13))]
+    p.forward([(0, 7), (1, 15), (2, 10), (3, 14)], trees=chains, leaves=[2, 6, -1, 4])
+    p.forward([(i, 1) for i in range(4)])
+    # multi-round trees over cached kv
+    p.clear()
+    p.forward([(0, 10), (1, 20), (2, 30), (3, 40)])
+    for i in range(5):
+        nleaf = 2 ** i
+        parent = [(k - 1) // 2 for k in range(0, 2 * nleaf - 1)]
+        p.forward([(s, nleaf) for s in range(4)], trees=[parent] * 4, leaves=None if i != 4 else [2, 6, -1, 4])
+    p.op(op="debug_get_kv", seq=1, start=0, end=20 + 3)
+    p.forward([(i, 1) for i in range(4)])
+    return p
+
+
+SCENARIOS = {
+    # name: (program builder, cache kwargs)
+    "prefill_and_decode": (prog_prefill_and_decode, dict(rope_mode=1)),
+    "remove_and_popn": (prog_remove_and_popn, dict(rope_mode=1)),
+    "fork": (prog_fork, dict(rope_mode=1)),
+    "unlimited_depth": (prog_unlimited_depth, dict(rope_mode=0)),
+    "prefill_and_decode_inline_rope_2layers": (prog_prefill_and_decode, dict(rope_mode=2, num_layers=2)),
+    "sliding_window": (prog_sliding_window, dict(rope_mode=2, support_sliding_window=True)),
+    "sliding_window_fork": (prog_sliding_window_fork, dict(rope_mode=2, support_sliding_window=True)),
+    "tree_attn": (prog_tree_attn, dict(rope_mode=1)),
+}
+BASE = dict(num_layers=1, num_qo_heads=4, num_kv_heads=1, head_dim=128, dtype="float16", reserved_nseq=32,
+            max_total_seq=2048, prefill_chunk=512, page_size=16, rope_scale=1.0, rope_theta=1e4)
+
+
+def run_reference(name):
+    import tvm
+    import tvm_ffi
+    from refenv import RefCache
+
+    builder, kw = SCENARIOS[name]
+    cfg = dict(BASE)
+    cfg.update(kw)
+    prog = builder()
+    rc = RefCache(**cfg)
+    L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
+    arrays = {}
+    results = []
+    for idx, op in enumerate(prog.ops):
+        del rc.trace[:]
+        res = {}
+        k = op["op"]
+        if k == "clear":
+            rc.call("kv_state_clear")
+        elif k == "add":
+            rc.call("kv_state_add_sequence", op["seq"])
+        elif k == "remove":
+            rc.call("kv_state_remove_sequence", op["seq"])
+        elif k == "fork":
+            rc.call("kv_state_fork_sequence", op["parent"], op["child"], op["pos"])
+        elif k == "popn":
+            rc.call("kv_state_popn", op["seq"], op["n"])
+        elif k == "enable_sw":
+            rc.call("attention_kv_cache_enable_sliding_window_for_seq", op["seq"], op["window"], op["sink"])
+        elif k == "commit":
+            rc.call("attention_kv_cache_commit_accepted_token_tree_nodes", tvm_ffi.Shape(op["seq_ids"]),
+                    tvm_ffi.Shape(op["leaves"]))
+        elif k == "query":
+            res["empty"] = bool(rc.call("attention_kv_cache_empty"))
+            res["num_available_pages"] = int(rc.call("attention_kv_cache_get_num_available_pages"))
+            res["total_sequence_length"] = int(rc.call("attention_kv_cache_get_total_sequence_length"))
+        elif k == "debug_get_kv":
+            n = op["end"] - op["start"]
+            kk = tvm.runtime.empty((L, n, hkv, d), cfg["dtype"], device=rc.dev)
+            vv = tvm.runtime.empty((L, n, hkv, d), cfg["dtype"], device=rc.dev)
+            rc.call("attention_kv_cache_debug_get_kv", op["seq"], op["start"], op["end"], kk, vv)
+            arrays[f"k_{idx}"] = kk.numpy()
+            arrays[f"v_{idx}"] = vv.numpy()
+        elif k == "forward":
+            tree = tvm_ffi.Shape(op["tree"]) if op["tree"] is not None else None
+            rc.call("kv_state_begin_forward", tvm_ffi.Shape(op["seq_ids"]), tvm_ffi.Shape(op["lens"]), tree)
+            n = sum(op["lens"])
+            qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
+            outs = []
+            for layer in range(L):
+                o = tvm.runtime.empty((n, hq, d), cfg["dtype"], device=rc.dev)
+                rc.call("attention_kv_cache_attention_with_fused_qkv", layer, d ** -0.5,
+                        tvm.runtime.tensor(qkv[layer], device=rc.dev), o)
+                outs.append(o.numpy())
+            rc.call("kv_state_end_forward")
+            arrays[f"o_{idx}"] = np.stack(outs)
+            res["num_available_pages"] = int(rc.call("attention_kv_cache_get_num_available_pages"))
+        else:
+            raise ValueError(k)
+        res["trace"] = [dict(r) for r in rc.trace]
+        results.append(res)
+    meta = {"name": name, "config": cfg, "ops": prog.ops, "results": results,
+            "reference": "apache/tvm @ /root/reference, C++ PagedAttentionKVCacheObj + CPU TIR kernels (c target, gcc -O3)"}
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, f"kvcache_{name}.npz")
+    np.savez_compressed(path, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+    print(f"{name}: {len(prog.ops)} ops, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SCENARIOS)
+    for nm in names:
+        run_reference(nm)

@@ -1,0 +1,124 @@
+"""Pins the CPU oracle (oracle/kernels.py) against the REAL reference: the callback traces captured from the reference
+cache (tests/golden/kvcache_*.npz) are re-executed with the oracle kernels on the reference's exact int32 arguments, and
+the attention outputs / cache dumps must match what the reference's own CPU TIR kernels produced (fp16).
+Tolerance: the reference's own test tolerance for its kernels vs. its NumPy oracle, rtol = atol = 1e-3
+(test_runtime_builtin_paged_attention_kv_cache_cpu.py:530-535) plus one fp16 ulp of output rounding."""
+import numpy as np
+import pytest
+
+from oracle import kernels as ok
+from tests.golden_replay import load, qkv_for, scenario_names
+
+
+def _arr(a):
+    return np.array(a["v"], np.int32).reshape(a["shape"])
+
+
+def _close(name, got, want, atol=2e-3, rtol=2e-3):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    err = np.abs(got - want)
+    assert (err <= atol + rtol * np.abs(want)).all(), f"{name}: max abs err {err.max():.3e}"
+
+
+class OracleMachine:
+    """Executes traced callbacks with the oracle kernels."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.dt = cfg["dtype"]
+        L, hkv, d, ps = cfg["num_layers"], cfg["num_kv_heads"], cfg["head_dim"], cfg["page_size"]
+        npages = (cfg["max_total_seq"] + ps - 1) // ps + 1 + (2 * cfg["reserved_nseq"] if cfg.get("support_sliding_window") else 0)
+        self.pages = [np.zeros((npages, 2, hkv, ps, d), np.float32) for _ in range(L)]
+        self.theta, self.scale = cfg["rope_theta"], cfg["rope_scale"]
+
+    def run_forward(self, trace, qkv):
+        hq, hkv = self.cfg["num_qo_heads"], self.cfg["num_kv_heads"]
+        outs, layer = [], -1
+        q = k = v = o = lse = tmp = None
+        for c in trace:
+            fn, a = c["fn"], c["args"]
+            if fn == "split_rotary":
+                if layer >= 0:
+                    outs.append(o)
+                layer += 1
+                q, k, v = ok.split_rotary(qkv[layer].astype(np.float32), _arr(a[1]), hq, hkv, a[5]["s"], self.theta, self.scale, self.dt)
+                o = lse = tmp = None
+            elif fn == "transpose_append":
+                ok.transpose_append(self.pages[layer], k, v, _arr(a[3]))
+            elif fn in ("prefill_ragged", "tree_ragged"):
+                if fn == "prefill_ragged":
+                    o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), _arr(a[6]), a[9]["s"],
+                                                         a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], self.dt)
+                else:
+                    o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), None, 0, a[10]["s"],
+                                                         a[11]["s"], a[12]["s"], a[13]["s"], self.dt, mn_indptr=_arr(a[6]),
+                                                         tree_mask=_arr(a[7]))
+            elif fn in ("prefill", "prefill_sliding_window", "decode", "decode_sliding_window", "tree_paged"):
+                P = self.pages[layer]
+                if fn.startswith("decode"):
+                    r = ok.attention_decode(q, P, _arr(a[2]), _arr(a[3]), _arr(a[4]), _arr(a[5]), _arr(a[6]), a[9]["s"],
+                                            a[10]["s"], a[11]["s"], a[12]["s"], self.dt)
+                elif fn == "tree_paged":
+                    r = ok.attention_prefill_paged(q, _arr(a[1]), P, _arr(a[3]), _arr(a[4]), _arr(a[5]), _arr(a[6]), _arr(a[7]),
+                                                   0, a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], self.dt,
+                                                   tree_indptr=_arr(a[14]), tree_order=_arr(a[15]))
+                else:
+                    r = ok.attention_prefill_paged(q, _arr(a[1]), P, _arr(a[3]), _arr(a[4]), _arr(a[5]), _arr(a[6]), _arr(a[7]),
+                                                   a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], a[14]["s"], self.dt,
+                                                   sliding_window_size=1024 if fn.endswith("sliding_window") else 0)
+                if o is None:
+                    o, lse = r
+                else:
+                    tmp = r
+            elif fn == "merge":
+                o, lse = ok.merge_state_inplace(o, lse, tmp[0], tmp[1], self.dt)
+            else:
+                raise AssertionError(f"unexpected callback {fn} inside a forward")
+        outs.append(o)
+        return outs
+
+    def run_other(self, trace):
+        dumps, layer = [], 0
+        for c in trace:
+            fn, a = c["fn"], c["args"]
+            if fn == "copy_single_page":
+                ok.copy_single_page(self.pages[layer % len(self.pages)], a[1]["s"], a[2]["s"], a[3]["s"])
+                layer += 1
+            elif fn == "compact_copy":
+                ok.compact_kv_copy(self.pages[layer % len(self.pages)], _arr(a[1]), _arr(a[2]), a[3]["s"])
+                layer += 1
+            elif fn == "debug_get_kv":
+                dumps.append(ok.debug_get_kv(self.pages[a[4]["s"]], _arr(a[1])))
+            else:
+                raise AssertionError(f"unexpected callback {fn}")
+        return dumps
+
+
+@pytest.mark.parametrize("name", scenario_names())
+def test_oracle_matches_reference_outputs(name):
+    meta, z = load(name)
+    cfg = meta["config"]
+    m = OracleMachine(cfg)
+    L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
+    checked = 0
+    for idx, (op, res) in enumerate(zip(meta["ops"], meta["results"])):
+        if op["op"] == "clear":
+            m = OracleMachine(cfg)
+        elif op["op"] == "forward":
+            n = sum(op["lens"])
+            qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
+            outs = m.run_forward(res["trace"], qkv)
+            want = z[f"o_{idx}"].astype(np.float32)
+            for layer in range(L):
+                _close(f"{name} op {idx} layer {layer} O", outs[layer], want[layer])
+            checked += 1
+        else:
+            dumps = m.run_other(res["trace"])
+            if op["op"] == "debug_get_kv":
+                for layer, (kk, vv) in enumerate(dumps):
+                    assert np.array_equal(vv, z[f"v_{idx}"][layer].astype(np.float32)), f"{name} op {idx}: V dump differs"
+                    if cfg["rope_mode"] == 1:  # K was rotated by fused_rope in fp32 before the fp16 cast
+                        _close(f"{name} op {idx} K", kk, z[f"k_{idx}"][layer].astype(np.float32), atol=1e-3, rtol=2e-3)
+                    else:
+                        assert np.array_equal(kk, z[f"k_{idx}"][layer].astype(np.float32)), f"{name} op {idx}: K dump differs"
+    assert checked > 0

@@ -25,6 +25,7 @@ SOURCES = [
     "prefill_generic.cu",
     "prefill_tc05.cu",
     "prefill_api.cu",
+    "kv_cache_host.cc",
     "ffi_api.cc",
 ]
 

@@ -25,8 +25,8 @@ class TvmB200Error(RuntimeError):
 
 
 def declared_symbols() -> list[str]:
-    """Every `tvmb200_*` entry point declared in include/tvm_b200.h."""
-    text = HEADER_PATH.read_text()
+    """Every `tvmb200_*` entry point declared in include/*.h."""
+    text = "\n".join(p.read_text() for p in sorted(HEADER_PATH.parent.glob("*.h")))
     return sorted(set(re.findall(r"TVMB200_API[^;]*?\b(tvmb200_\w+)\s*\(", text, flags=re.S)))
 
 
