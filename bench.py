@@ -201,7 +201,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline (the reference's CPU path): oracle/_ref if present, else the NumPy oracle port
 # ---------------------------------------------------------------------------------------------------
-def cpu_decode_baseline(L=4096, Hq=32, Hkv=8, D=128, B=1, repeats=1):
+def cpu_decode_baseline(L=4096, Hq=32, Hkv=8, D=128, B=1, repeats=50):
     """Times the CPU decode kernel on a bounded slice (B sequences of the C2 shape, fp16 like the
     reference's CPU tests).  Returns dict(value GB/s, unit, cores, kind, sample)."""
     from oracle import cpu_ref
@@ -237,6 +237,8 @@ def run_own(args):
     peaks, peak_src = measured_peaks()
     if args.workload == "prefill":
         return run_prefill(args, capi, rank, world, dev, peaks, peak_src)
+    if args.workload == "c4":
+        return run_c4(args, capi, rank, world, dev, peaks, peak_src)
     w = DecodeWorkload(seed=rank, device=dev)
     dist = None
     gathered = None
@@ -299,12 +301,12 @@ def run_own(args):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    try:
+        e2e = run_e2e(args, w, world, dist)
+    except Exception as e:  # pragma: no cover
+        e2e = {"value": None, "error": repr(e)[:300]}
     if rank == 0:
-        # e2e + cpu baseline on rank 0 only
-        try:
-            out["e2e"] = run_e2e(args, w, world)
-        except Exception as e:  # pragma: no cover
-            out["e2e"] = {"value": None, "error": repr(e)[:200]}
+        out["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             try:
                 out["cpu_baseline"] = cpu_decode_baseline()
@@ -316,55 +318,75 @@ def run_own(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, w, world):
-    """Through the tvm-ffi packed functions with host inputs (see module docstring)."""
+def run_e2e(args, w, world, dist=None):
+    """End to end through the repo's public API -- the C++ host cache (tvm_b200.kv_cache.PagedKVCache, the drop-in for
+    the reference's PagedAttentionKVCacheObj) -- with HOST inputs: every step does begin_forward (host page-table
+    bookkeeping), copies the step's fused qkv from pinned host memory, runs attention_with_fused_qkv (one merged H2D
+    copy of the aux arrays + split_rotary + append + decode on the sm_100a kernels), copies O back to pinned host
+    memory and pops the appended token again so that every step sees the same 4096-token context."""
     import torch
 
-    from tvm_b200 import ffi
+    from tvm_b200.kv_cache import PagedKVCache
 
-    mod = ffi.module()
-    K = max(10, args.steps // 5)
-    # merged aux array like the reference's CachedPagedKVCacheAuxDataManager (attn_utils.h:907-1052)
-    parts = [w.h_q_rope_position, w.h_page_indptr, w.h_page_values, w.h_length_info, w.h_k_rope_pos_offset,
-             w.h_append_position]
-    offs, tot = [], 0
-    for p in parts:
-        offs.append(tot)
-        tot += (p.size + 3) // 4 * 4  # 16-byte aligned element offsets
-    h_aux = torch.zeros(tot, dtype=torch.int32).pin_memory()
-    for p, o in zip(parts, offs):
-        h_aux[o:o + p.size] = torch.from_numpy(p)
-    d_aux = torch.empty(tot, dtype=torch.int32, device=w.qkv.device)
-    views = [d_aux[o:o + p.size] for p, o in zip(parts, offs)]
-    qpos, pindptr, pvals, linfo, kofs, apos = views
-    h_out = torch.empty(w.o.shape, dtype=torch.bfloat16).pin_memory()
+    dev = w.qkv.device
+    B, L, Hq, Hkv, D = w.B, w.L, w.Hq, w.Hkv, w.D
+    chunk = 8192
+    cache = PagedKVCache(reserved_num_seqs=B, total_token_capacity=B * L + 16, prefill_chunk_size=chunk, num_layers=1,
+                         num_qo_heads=Hq, num_kv_heads=Hkv, head_dim=D, rope_mode=1, rotary_theta=w.rope_theta,
+                         dtype="bfloat16", device=dev.index or 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    fill = torch.randn((chunk, Hq + 2 * Hkv, D), generator=g, device=dev, dtype=torch.bfloat16)
+    fill_o = torch.empty((chunk, Hq, D), device=dev, dtype=torch.bfloat16)
+    for sid in range(B):  # build the 4095-token context of every sequence through the cache itself (chunked prefill)
+        cache.add_sequence(sid)
+        left = L - 1
+        while left > 0:
+            n = min(left, chunk)
+            cache.begin_forward([sid], [n])
+            cache.attention_with_fused_qkv(0, w.sm_scale, fill[:n], fill_o[:n])
+            cache.end_forward()
+            left -= n
+    torch.cuda.synchronize()
+    seq_ids, ones = list(range(B)), [1] * B
     d_qkv = torch.empty_like(w.qkv)
-    f_rot, f_app, f_dec = mod["f_split_rotary"], mod["f_transpose_append"], mod["f_attention_decode"]
-    mod["set_rope_params"](float(w.rope_theta), float(w.rope_scale))
+    h_out = torch.empty(w.o.shape, dtype=torch.bfloat16).pin_memory()
+    gathered = torch.empty((world * B, Hq, D), device=dev, dtype=torch.bfloat16) if world > 1 else None
 
     def step():
+        cache.begin_forward(seq_ids, ones)
         d_qkv.copy_(w.h_qkv, non_blocking=True)
-        d_aux.copy_(h_aux, non_blocking=True)
-        f_rot(d_qkv, qpos, w.q, w.k, w.v, 1)
-        f_app(w.pages, w.k, w.v, apos)
-        f_dec(w.q, w.pages, pindptr, pvals, linfo, kofs, qpos, w.o, w.lse, 0, w.rope_scale, w.rope_theta, w.sm_scale)
+        cache.attention_with_fused_qkv(0, w.sm_scale, d_qkv, w.o)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, w.o)
         h_out.copy_(w.o, non_blocking=True)
+        cache.end_forward()
+        for sid in seq_ids:
+            cache.popn(sid, 1)
 
-    with ffi.torch_stream():
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
+    K = max(10, args.steps // 3)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    aux_ints = B + 3 * (B + 1) + w.nnz + 2 * B + B + 2 * B  # q_rope, indptrs, page ids, len/rope arrays, append map
+    del cache
     return {"value": round(world * w.step_bytes() / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
-            "h2d_bytes_per_step": int(w.h_qkv.numel() * 2 + tot * 4), "d2h_bytes_per_step": int(h_out.numel() * 2),
-            "ms_per_step": round(ms, 5), "steps": K, "api": "tvm-ffi packed functions f_split_rotary/"
-            "f_transpose_append/f_attention_decode", "n_gpus_measured": 1}
+            "h2d_bytes_per_step": int(w.h_qkv.numel() * 2 + aux_ints * 4), "d2h_bytes_per_step": int(h_out.numel() * 2),
+            "ms_per_step": round(ms, 5), "steps": K,
+            "api": "tvm_b200.kv_cache.PagedKVCache.begin_forward/attention_with_fused_qkv (C ABI tvmb200_cache_*)"}
 
 
 def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
@@ -399,6 +421,67 @@ def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
         print(json.dumps(out), flush=True)
 
 
+def run_c4(args, capi, rank, world, dev, peaks, peak_src):
+    """C4: Llama-3-70B GQA decode (64 q / 8 kv heads), batch 256 at 8K context, KV-head groups sharded across the ranks
+    (strong scaling: total work fixed), per-head outputs re-assembled with one NCCL all-gather per step."""
+    import torch
+
+    from tvm_b200 import sharding
+
+    Hq, Hkv, B, L = 64, 8, 256, 8192
+    q0, q1, k0, k1 = sharding.head_shard(Hq, Hkv, world, rank)
+    w = DecodeWorkload(B=B, L=L, Hq=q1 - q0, Hkv=k1 - k0, seed=0, device=dev)  # same page table on every rank
+    if world > 1:
+        import torch.distributed as dist
+
+    def step():
+        w.run_rotary_append(capi)
+        w.run_decode(capi)
+        if world > 1:
+            return sharding.all_gather_heads(w.o)
+        return w.o
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = capi.launch_count()
+    with ClockSampler(dev.index or 0) as clk:
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    total_bytes = world * w.step_bytes()
+    gbs = total_bytes / (ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+    out = {"metric": "decode_attn_hbm_gbps", "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world, "steps": K,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "C4 Llama-3-70B GQA decode: batch 256 x 8192 ctx, 64q/8kv heads sharded by KV-head group, "
+                                  "D128, page16, bf16; step = split_rotary+append+decode (+all-gather of O)",
+                      "global_batch": B, "seq_len": L, "parallelism": f"tp{world} (KV-head groups)",
+                      "l2": "KV working set >= 1 GiB/GPU > 126 MB L2"},
+           "tok_s_layer": round(B / (ms * 1e-3), 1),
+           "roofline": {"bound": "hbm", "achieved": round(gbs / world, 1), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(gbs / world / hbm_peak, 4), "traffic": None, "peak_source": f"of {peak_src}",
+                        "note": "whole step per GPU incl. all-gather"},
+           "gpu_launches": int(capi.launch_count() - n0), "clocks": clk.summary()}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """The reference's own CPU path on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -406,7 +489,7 @@ def run_reference(args):
     from oracle import cpu_ref
 
     K, W = args.steps, args.warmup
-    res = cpu_ref.time_decode_steps(steps=min(K, 5), warmup=min(W, 1))
+    res = cpu_ref.time_decode_steps(steps=K, warmup=min(max(W, 1), 2), budget_s=90.0)
     out = {"impl": "reference", "metric": "decode_attn_hbm_gbps", "value": res["value"], "unit": "GB/s",
            "n_gpus": args.gpus, "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": res["dtype"],
@@ -425,7 +508,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="decode", choices=["decode", "prefill"])
+    ap.add_argument("--workload", default="decode", choices=["decode", "prefill", "c4"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -25,8 +25,13 @@ def _ref_module(dtype="float16", hq=32, hkv=8, d=128):
     if not p.exists():
         return None
     try:
+        import ctypes
+
         import tvm_ffi
 
+        shim = REF_DIR / "libref_shim.so"  # TVMBackendAllocWorkspace/FreeWorkspace (oracle/ref_shim.c)
+        if shim.exists():
+            ctypes.CDLL(str(shim), mode=ctypes.RTLD_GLOBAL)
         return tvm_ffi.load_module(str(p))
     except Exception:
         return None
@@ -70,7 +75,7 @@ def _one_step_ref(mod, t, Hq, Hkv, D, theta=5e5):
                                      t["kofs"], t["qpos"], t["o"], t["lse"], 0, 1.0, theta, D ** -0.5)
 
 
-def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128):
+def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128, budget_s=60.0):
     """One step = split_rotary + append + decode of one layer on a B-sequence slice of C2."""
     dtype = "float16"  # the reference's CPU path is tested in fp16/fp32 only (no bf16 CPU codegen)
     inp = _decode_inputs(B, L, Hq, Hkv, D, dtype)
@@ -89,8 +94,11 @@ def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128):
         run = lambda: _one_step_ref(mod, t, Hq, Hkv, D)  # noqa: E731
     else:
         run = lambda: _one_step_port(inp, Hq, Hkv, D, dtype)  # noqa: E731
-    for _ in range(warmup):
+    t0 = time.perf_counter()
+    for _ in range(max(warmup, 1)):
         run()
+    t_one = (time.perf_counter() - t0) / max(warmup, 1)
+    steps = max(1, min(steps, int(budget_s / max(t_one, 1e-6))))  # bounded: the whole run ends within ~budget_s
     t0 = time.perf_counter()
     for _ in range(steps):
         run()
@@ -103,6 +111,6 @@ def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128):
                       f"host has {os.cpu_count()} cores"}
 
 
-def time_decode(B=1, L=4096, Hq=32, Hkv=8, D=128, repeats=1):
-    r = time_decode_steps(steps=max(1, repeats), warmup=1, B=B, L=L, Hq=Hq, Hkv=Hkv, D=D)
+def time_decode(B=1, L=4096, Hq=32, Hkv=8, D=128, repeats=20):
+    r = time_decode_steps(steps=max(1, repeats), warmup=1, B=B, L=L, Hq=Hq, Hkv=Hkv, D=D, budget_s=20.0)
     return {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
