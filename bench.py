@@ -260,6 +260,7 @@ def run_own(args):
         dist.barrier()
     K = args.steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    ev_end = torch.cuda.Event(enable_timing=True)
     n0 = capi.launch_count()
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
@@ -268,14 +269,15 @@ def run_own(args):
             w.run_rotary_append(capi)
             ev[2 * i + 1].record()
             w.run_decode(capi)
+            ev[2 * i + 2].record()
             if world > 1:
                 dist.all_gather_into_tensor(gathered, w.o)
-            ev[2 * i + 2].record()
+        ev_end.record()
         torch.cuda.synchronize()
     launches = capi.launch_count() - n0
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[2 * K])
+    total_ms = ev[0].elapsed_time(ev_end)
     decode_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(K)) / K
     if world > 1:
         t = torch.tensor([total_ms, decode_ms], device=dev, dtype=torch.float64)
@@ -323,7 +325,7 @@ def run_e2e(args, w, world, dist=None):
     the reference's PagedAttentionKVCacheObj) -- with HOST inputs: every step does begin_forward (host page-table
     bookkeeping), copies the step's fused qkv from pinned host memory, runs attention_with_fused_qkv (one merged H2D
     copy of the aux arrays + split_rotary + append + decode on the sm_100a kernels), copies O back to pinned host
-    memory and pops the appended token again so that every step sees the same 4096-token context."""
+    memory.  The context grows by one token per step (4096 .. 4096+K) and the byte count follows it."""
     import torch
 
     from tvm_b200.kv_cache import PagedKVCache
@@ -331,7 +333,8 @@ def run_e2e(args, w, world, dist=None):
     dev = w.qkv.device
     B, L, Hq, Hkv, D = w.B, w.L, w.Hq, w.Hkv, w.D
     chunk = 8192
-    cache = PagedKVCache(reserved_num_seqs=B, total_token_capacity=B * L + 16, prefill_chunk_size=chunk, num_layers=1,
+    K = max(10, args.steps // 3)
+    cache = PagedKVCache(reserved_num_seqs=B, total_token_capacity=B * (L + K + 32), prefill_chunk_size=chunk, num_layers=1,
                          num_qo_heads=Hq, num_kv_heads=Hkv, head_dim=D, rope_mode=1, rotary_theta=w.rope_theta,
                          dtype="bfloat16", device=dev.index or 0)
     g = torch.Generator(device=dev)
@@ -361,11 +364,8 @@ def run_e2e(args, w, world, dist=None):
             dist.all_gather_into_tensor(gathered, w.o)
         h_out.copy_(w.o, non_blocking=True)
         cache.end_forward()
-        for sid in seq_ids:
-            cache.popn(sid, 1)
 
-    K = max(10, args.steps // 3)
-    for _ in range(3):
+    for _ in range(3):  # context is now L + 2 after warm-up; every timed step appends one more token per sequence
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -383,7 +383,9 @@ def run_e2e(args, w, world, dist=None):
         ms = float(t[0])
     aux_ints = B + 3 * (B + 1) + w.nnz + 2 * B + B + 2 * B  # q_rope, indptrs, page ids, len/rope arrays, append map
     del cache
-    return {"value": round(world * w.step_bytes() / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+    # algorithmic bytes with the real context lengths: step s (0-based, after 3 warm-up steps) reads L + 3 + s tokens
+    extra_kv = (3 + (K - 1) / 2.0) * B * Hkv * D * 2 * 2
+    return {"value": round(world * (w.step_bytes() + extra_kv) / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
             "h2d_bytes_per_step": int(w.h_qkv.numel() * 2 + aux_ints * 4), "d2h_bytes_per_step": int(h_out.numel() * 2),
             "ms_per_step": round(ms, 5), "steps": K,
             "api": "tvm_b200.kv_cache.PagedKVCache.begin_forward/attention_with_fused_qkv (C ABI tvmb200_cache_*)"}

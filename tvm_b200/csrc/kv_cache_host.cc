@@ -174,8 +174,14 @@ class Cache {
 
   // merged aux buffer: host staging (pinned when on a device) + device copy, and the views into it
   IVec stage_;
-  int32_t* stage_pinned_ = nullptr;
-  int32_t* aux_dev_ = nullptr;
+  // two device copies + two pinned staging buffers, alternated per step, so that the H2D copy of step i+1 does not
+  // have to wait for the kernels of step i (which still read the other buffer)
+  int32_t* stage_pinned_[2] = {nullptr, nullptr};
+  int32_t* aux_dev_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_aux_copied_[2] = {nullptr, nullptr};   // H2D from stage_pinned_[i] has completed
+  cudaEvent_t ev_aux_readers_[2] = {nullptr, nullptr};  // last kernels that read aux_dev_[i] have completed
+  bool aux_used_[2] = {false, false};
+  int aux_cur_ = 0;
   int64_t aux_capacity_ = 0;
   int32_t* compact_pinned_ = nullptr;
   int32_t* compact_dev_ = nullptr;
@@ -200,7 +206,7 @@ class Cache {
   std::string trace_json_;
 
   bool planning_only() const { return device_ < 0; }
-  int32_t* dev(const View& v) const { return aux_dev_ ? aux_dev_ + v.offset : nullptr; }
+  int32_t* dev(const View& v) const { return aux_dev_[aux_cur_] ? aux_dev_[aux_cur_] + v.offset : nullptr; }
   const int32_t* hostv(const View& v) const { return stage_.data() + v.offset; }
 
   int32_t GetFreePage() {
@@ -380,8 +386,12 @@ Cache::Cache(const tvmb200_cache_config& c)
     HCUDA(cudaMalloc(&tmp_o_, qb));
     HCUDA(cudaMalloc(reinterpret_cast<void**>(&tmp_lse_), static_cast<size_t>(prefill_chunk_) * num_qo_heads_ * 4));
     HCUDA(cudaMalloc(reinterpret_cast<void**>(&merged_lse_), static_cast<size_t>(prefill_chunk_) * num_qo_heads_ * 4));
-    HCUDA(cudaMalloc(reinterpret_cast<void**>(&aux_dev_), aux_capacity_ * 4));
-    HCUDA(cudaMallocHost(reinterpret_cast<void**>(&stage_pinned_), aux_capacity_ * 4));
+    for (int i = 0; i < 2; ++i) {
+      HCUDA(cudaMalloc(reinterpret_cast<void**>(&aux_dev_[i]), aux_capacity_ * 4));
+      HCUDA(cudaMallocHost(reinterpret_cast<void**>(&stage_pinned_[i]), aux_capacity_ * 4));
+      HCUDA(cudaEventCreateWithFlags(&ev_aux_copied_[i], cudaEventDisableTiming));
+      HCUDA(cudaEventCreateWithFlags(&ev_aux_readers_[i], cudaEventDisableTiming));
+    }
     const int64_t ccap = al(reserved_seqs_ + 1) + al(2 * std::min<int64_t>(kMaxTreeSize * reserved_seqs_, prefill_chunk_)) + 16;
     HCUDA(cudaMalloc(reinterpret_cast<void**>(&compact_dev_), ccap * 4));
     HCUDA(cudaMallocHost(reinterpret_cast<void**>(&compact_pinned_), ccap * 4));
@@ -404,10 +414,14 @@ Cache::~Cache() {
   cudaFree(tmp_o_);
   cudaFree(tmp_lse_);
   cudaFree(merged_lse_);
-  cudaFree(aux_dev_);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(aux_dev_[i]);
+    cudaFreeHost(stage_pinned_[i]);
+    if (ev_aux_copied_[i]) cudaEventDestroy(ev_aux_copied_[i]);
+    if (ev_aux_readers_[i]) cudaEventDestroy(ev_aux_readers_[i]);
+  }
   cudaFree(compact_dev_);
   cudaFree(dbg_pos_dev_);
-  cudaFreeHost(stage_pinned_);
   cudaFreeHost(compact_pinned_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (ev_copy_) cudaEventDestroy(ev_copy_);
@@ -961,13 +975,18 @@ void Cache::SyncAux(cudaStream_t compute) {
     dirty_ = false;
     return;
   }
-  // the copy stream must not overwrite the aux buffer while earlier kernels on the compute stream still read it
-  HCUDA(cudaEventRecord(ev_compute_, compute));
-  HCUDA(cudaStreamWaitEvent(copy_stream_, ev_compute_, 0));
-  std::memcpy(stage_pinned_, stage_.data(), static_cast<size_t>(stage_off_) * 4);
-  HCUDA(cudaMemcpyAsync(aux_dev_, stage_pinned_, static_cast<size_t>(stage_off_) * 4, cudaMemcpyHostToDevice, copy_stream_));
-  HCUDA(cudaEventRecord(ev_copy_, copy_stream_));
-  HCUDA(cudaStreamWaitEvent(compute, ev_copy_, 0));
+  const int i = aux_cur_ ^ 1;  // the buffer pair not used by the previous step
+  if (aux_used_[i]) {
+    HCUDA(cudaEventSynchronize(ev_aux_copied_[i]));                     // host: the old DMA out of stage_pinned_[i] is done
+    HCUDA(cudaStreamWaitEvent(copy_stream_, ev_aux_readers_[i], 0));   // device: kernels that read aux_dev_[i] are done
+  }
+  std::memcpy(stage_pinned_[i], stage_.data(), static_cast<size_t>(stage_off_) * 4);
+  HCUDA(cudaMemcpyAsync(aux_dev_[i], stage_pinned_[i], static_cast<size_t>(stage_off_) * 4, cudaMemcpyHostToDevice, copy_stream_));
+  HCUDA(cudaEventRecord(ev_aux_copied_[i], copy_stream_));
+  // the copy stream also carries page copies / compactions issued since the last step: one wait orders them all
+  HCUDA(cudaStreamWaitEvent(compute, ev_aux_copied_[i], 0));
+  aux_used_[i] = true;
+  aux_cur_ = i;
   dirty_ = false;
 }
 
@@ -1082,7 +1101,10 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   }
   HCHECK(self_done || cross_done, "Both self-attention and cross-attention are not computed.");
   if (!append_before_attn_) append();
-  if (!plan) HCUDA(cudaEventRecord(ev_attn_done_, st));
+  if (!plan) {
+    HCUDA(cudaEventRecord(ev_attn_done_, st));
+    HCUDA(cudaEventRecord(ev_aux_readers_[aux_cur_], st));
+  }
 }
 
 void Cache::CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n) {
