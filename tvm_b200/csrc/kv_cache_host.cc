@@ -312,6 +312,11 @@ class Cache {
     snprintf(b, sizeof(b), "{\"s\":%.17g}", v);
     return {b};
   }
+  // the argument strings (every int32 array as text) are only built while a trace is being recorded
+#define TRACE(fn, ...)                       \
+  do {                                       \
+    if (tracing_) Trace(fn, __VA_ARGS__);    \
+  } while (0)
   void Trace(const char* fn, std::initializer_list<Arg> args) {
     if (!tracing_) return;
     std::string s = std::string("{\"fn\":\"") + fn + "\",\"args\":[";
@@ -541,7 +546,7 @@ void Cache::ForkSequence(int64_t parent_id, int64_t child_id, int64_t fork_pos) 
 
 void Cache::CopySinglePage(int32_t src, int32_t tgt, int64_t len) {
   for (int64_t l = 0; l < num_layers_; ++l)
-    Trace("copy_single_page", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), SI(src), SI(tgt), SI(len)});
+    TRACE("copy_single_page", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), SI(src), SI(tgt), SI(len)});
   if (planning_only()) return;
   // runs on the copy stream, after the last attention's appends; the next SyncAux orders it before any later
   // attention (paged_kv_cache.cc:721-734)
@@ -1005,12 +1010,12 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
 
   // Part 2: split fused qkv (+ RoPE when the mode is "normal")
   const int64_t apply_rope = rope_mode_ == TVMB200_ROPE_NORMAL;
-  Trace("split_rotary", {TF({n, hq + 2 * hkv, d}), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hkv, d}), TF({n, hkv, d}), SI(apply_rope)});
+  TRACE("split_rotary", {TF({n, hq + 2 * hkv, d}), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hkv, d}), TF({n, hkv, d}), SI(apply_rope)});
   if (!plan)
     Rc(tvmb200_split_rotary(qkv, dev(v_q_rope_pos_), tmp_q_, tmp_k_, tmp_v_, n, hq, hkv, d, 0, apply_rope,
                             static_cast<float>(rotary_scale_), static_cast<float>(rotary_theta_), dtype_, st));
   auto append = [&]() {
-    Trace("transpose_append", {TF({num_total_pages_, 2, hkv, ps, d}), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_append_pos_)});
+    TRACE("transpose_append", {TF({num_total_pages_, 2, hkv, ps, d}), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_append_pos_)});
     if (!plan) Rc(tvmb200_transpose_append(pages, tmp_k_, tmp_v_, dev(v_append_pos_), n, num_total_pages_, hkv, ps, d, dtype_, st));
   };
   if (append_before_attn_) append();
@@ -1021,7 +1026,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   if (!append_before_attn_) {
     is_first = false;
     if (is_chain_on_depths_[0]) {
-      Trace("prefill_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
+      TRACE("prefill_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
                                TI(v_q_rope_pos_), TI(v_k_ragged_rope_off_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(1),
                                SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
       if (!plan)
@@ -1031,7 +1036,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
                                             hq, hkv, d, 1, rot, static_cast<float>(rotary_scale_),
                                             static_cast<float>(rotary_theta_), static_cast<float>(sm_scale), dtype_, st));
     } else {
-      Trace("tree_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
+      TRACE("tree_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
                             TI(v_q_rope_pos_), TI(v_tree_mn_[0]), TI(v_tree_mask_[0]), TF({n, hq, d}), TF({n, hq}, "float32"),
                             SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
       if (!plan)
@@ -1061,7 +1066,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
       const int32_t B = static_cast<int32_t>(v_qo_indptr_[dd].size - 1);
       const int32_t nnz = static_cast<int32_t>(piv.size);
       if (append_before_attn_ && !is_chain_on_depths_[dd]) {
-        Trace("tree_paged", {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li),
+        TRACE("tree_paged", {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li),
                              TI(kro), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta),
                              SF(sm_scale), TI(v_tree_mn_[dd]), TI(v_tree_mask_[dd])});
         if (!plan)
@@ -1071,7 +1076,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
                                                   static_cast<float>(theta), static_cast<float>(sm_scale), dev(v_tree_mn_[dd]),
                                                   dev(v_tree_mask_[dd]), dtype_, st));
       } else if (use_decode_kernel_[dd]) {
-        Trace(sw_flavour ? "decode_sliding_window" : "decode",
+        TRACE(sw_flavour ? "decode_sliding_window" : "decode",
               {TF({n, hq, d}), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro), TI(v_q_rope_pos_),
                TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta), SF(sm_scale)});
         if (!plan)
@@ -1079,7 +1084,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
                                       nnz, num_total_pages_, hq, hkv, ps, d, sw_flavour ? 1 : 0, rot, static_cast<float>(scale),
                                       static_cast<float>(theta), static_cast<float>(sm_scale), dtype_, st));
       } else {
-        Trace(sw_flavour ? "prefill_sliding_window" : "prefill",
+        TRACE(sw_flavour ? "prefill_sliding_window" : "prefill",
               {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro),
                TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(causal ? 1 : 0), SI(rot), SF(scale), SF(theta),
                SF(sm_scale)});
@@ -1091,7 +1096,7 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
                                              static_cast<float>(sm_scale), dtype_, st));
       }
       if (!is_first) {
-        Trace("merge", {TF({n, hq, d}), TF({n, hq}, "float32"), TF({n, hq, d}), TF({n, hq}, "float32")});
+        TRACE("merge", {TF({n, hq, d}), TF({n, hq}, "float32"), TF({n, hq, d}), TF({n, hq}, "float32")});
         if (!plan) Rc(tvmb200_merge_state_inplace(o, merged_lse_, tmp_o_, tmp_lse_, n, hq, d, dtype_, st));
       } else {
         is_first = false;
@@ -1171,7 +1176,7 @@ void Cache::CompactKVCopy() {
   std::memcpy(tmp.data() + vsd.offset, commit_src_.data(), total * 4);
   std::memcpy(tmp.data() + vsd.offset + total, commit_dst_.data(), total * 4);
   for (int64_t l = 0; l < num_layers_; ++l)
-    Trace("compact_copy", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), TI(vi, tmp.data()),
+    TRACE("compact_copy", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), TI(vi, tmp.data()),
                            TI(vsd, tmp.data() + vsd.offset), SI(cur_batch_)});
   if (planning_only()) return;
   HCUDA(cudaStreamWaitEvent(copy_stream_, ev_attn_done_, 0));
@@ -1202,7 +1207,7 @@ void Cache::DebugGetKV(int64_t seq_id, int64_t start, int64_t end, void* k_out, 
   View v;
   v.size = end - start;
   for (int64_t l = 0; l < num_layers_; ++l)
-    Trace("debug_get_kv", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), TI(v, pos.data() + start),
+    TRACE("debug_get_kv", {TF({num_total_pages_, 2, num_kv_heads_, page_size_, head_dim_}), TI(v, pos.data() + start),
                            TF({num_layers_, end - start, num_kv_heads_, head_dim_}),
                            TF({num_layers_, end - start, num_kv_heads_, head_dim_}), SI(l)});
   if (planning_only()) return;

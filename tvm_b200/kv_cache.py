@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes
 import json
+
+import numpy as np
 from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int32, c_int64, c_void_p
 
 from . import capi
@@ -51,10 +53,10 @@ def _lib():
         L.tvmb200_cache_remove_sequence.argtypes = [P, I64]
         L.tvmb200_cache_fork_sequence.argtypes = [P, I64, I64, I64]
         L.tvmb200_cache_popn.argtypes = [P, I64, I32]
-        L.tvmb200_cache_begin_forward.argtypes = [P, POINTER(I64), POINTER(I64), I32, POINTER(I64), I32]
+        L.tvmb200_cache_begin_forward.argtypes = [P, P, P, I32, P, I32]
         L.tvmb200_cache_end_forward.argtypes = [P]
         L.tvmb200_cache_enable_sliding_window_for_seq.argtypes = [P, I64, I32, I32]
-        L.tvmb200_cache_commit_accepted_token_tree_nodes.argtypes = [P, POINTER(I64), POINTER(I64), I32]
+        L.tvmb200_cache_commit_accepted_token_tree_nodes.argtypes = [P, P, P, I32]
         L.tvmb200_cache_empty.argtypes = [P, POINTER(I32)]
         L.tvmb200_cache_get_num_available_pages.argtypes = [P, POINTER(I32)]
         L.tvmb200_cache_get_total_sequence_length.argtypes = [P, POINTER(I32)]
@@ -68,8 +70,18 @@ def _lib():
     return L
 
 
+class _I64Array:
+    """int64 view of a Python sequence / numpy array for the C ABI (kept alive by the caller for the call's duration)."""
+
+    __slots__ = ("arr", "_as_parameter_")
+
+    def __init__(self, xs):
+        self.arr = np.ascontiguousarray(xs, dtype=np.int64)
+        self._as_parameter_ = ctypes.c_void_p(self.arr.__array_interface__["data"][0])
+
+
 def _i64(xs):
-    return (c_int64 * len(xs))(*[int(x) for x in xs])
+    return _I64Array(xs)
 
 
 class PagedKVCache:
