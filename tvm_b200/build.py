@@ -15,8 +15,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
-OBJDIR = ROOT / "lib" / "obj"
-LIB = LIBDIR / "libtvm_b200.so"
+# tuning knobs: TVMB200_LIB_SUFFIX names a variant library (libtvm_b200<suffix>.so, also honoured by capi.py) and
+# TVMB200_EXTRA_FLAGS adds -D... defines to it; the product build uses neither.
+SUFFIX = os.environ.get("TVMB200_LIB_SUFFIX", "")
+LIB = LIBDIR / f"libtvm_b200{SUFFIX}.so"
+OBJDIR = ROOT / "lib" / f"obj{SUFFIX}"
 
 SOURCES = [
     "core.cu",
@@ -45,6 +48,7 @@ def _flags(verbose: bool) -> list[str]:
          "--expt-relaxed-constexpr", "-Xptxas", "-warn-spills"]
     if verbose:
         f += ["-Xptxas", "-v"]
+    f += os.environ.get("TVMB200_EXTRA_FLAGS", "").split()
     return f
 
 
@@ -62,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted((ROOT.parent / "include").glob("*.h"))
     flags = _flags(verbose) + ARCH + _ffi_includes()
-    stamp = LIBDIR / "build.stamp"
+    stamp = LIBDIR / f"build{SUFFIX}.stamp"
     digest = _digest(srcs + hdrs, " ".join(flags))
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB

@@ -6,13 +6,14 @@ fallback: a missing library raises at load time, a CPU tensor raises at call tim
 """
 from __future__ import annotations
 
+import os
 import ctypes
 import re
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
-LIB_PATH = ROOT / "lib" / "libtvm_b200.so"
+LIB_PATH = ROOT / "lib" / ("libtvm_b200" + os.environ.get("TVMB200_LIB_SUFFIX", "") + ".so")  # suffix: tuning variants only
 HEADER_PATH = ROOT.parent / "include" / "tvm_b200.h"
 
 F16, BF16 = 0, 1

@@ -11,14 +11,19 @@
 //               row = token*g + head, _prefill_kernels.py:318-324) once, then K_j / V_j tiles of 128 KV rows
 //               through a 4-slot shared-memory ring (ragged: one 3-D box per 64-col half; paged: eight
 //               16-row page boxes per half, page ids looked up by the producer lanes).
-//   warp 1      MMA issuer (one elected thread): S_t = Q_t K_j^T (SS, K-major operands) into TMEM, and
-//               O_t += P_t V_j (TS: P read from TMEM, V as an MN-major shared-memory operand).  Issue order per
-//               KV tile: PV_0(j), QK_0(j+1), PV_1(j), QK_1(j+1) so the tensor pipe always has the other
-//               tile's work while one tile is in softmax.
-//   warp 2      TMEM allocator (512 columns: S_0,S_1,O_0,O_1; P_t aliases the first 64 columns of S_t).
-//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; tcgen05.ld the S row,
-//               mask (diagonal / tail tiles only), running max with LAZY rescale (O in TMEM is only rescaled
+//   warp 1      MMA issuer (one elected thread).  The KV axis advances in STEPS of 64 columns (half a KV tile):
+//               S_t(s) = Q_t K[64s..64s+63]^T (SS, K-major operands, N = 64) into one of TWO S buffers per tile, and
+//               O_t += P_t(s) V[64s..] (TS: P read from TMEM, V as an MN-major shared-memory operand, K = 64).
+//               Because S is double-buffered, QK of step s+2 is issued right behind PV of step s, i.e. S(s+1) is
+//               already in TMEM when the softmax warps finish step s: the softmax never waits for the tensor pipe
+//               and the tensor pipe always has PV/QK work of both tiles queued (the single-buffered version put
+//               QK -> softmax -> PV of a tile on one serial chain and reached 47 % of peak).
+//   warp 2      TMEM allocator (512 columns: S_0[2], S_1[2] of 64 columns each, O_0, O_1 of 128; P_t(s) aliases
+//               the S buffer it was computed from: P_hi in its first 32 columns, P_lo in the last 32).
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; tcgen05.ld the 64 S values,
+//               mask (diagonal / tail steps only), running max with LAZY rescale (O in TMEM is only rescaled
 //               when the max grows by more than 2^8), exp2, pack to 16-bit, tcgen05.st P, arrive.
+//               Each tile stops at its own last visible step under a causal mask.
 //               The same threads normalise and store O / LSE at the end.
 // All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); no __syncthreads in the loop.
 #include "prefill.cuh"
@@ -31,7 +36,8 @@ namespace tvmb200 {
 namespace {
 
 constexpr int kRows = 128;                 // rows of a UMMA tile (M)
-constexpr int kKV = 128;                   // KV rows per tile (N of QK^T, K of PV)
+constexpr int kKV = 128;                   // KV rows per shared-memory tile
+constexpr int kStep = 64;                  // KV columns per softmax step (N of QK^T, K of PV)
 constexpr int kD = 128;                    // head dim
 constexpr int kHalfBytes = kRows * 128;    // one 64-column half of a 128-row tile: 16 KiB
 constexpr int kTileBytes = 2 * kHalfBytes; // 32 KiB
@@ -43,16 +49,23 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
 // rounding residual P_lo = P - bf16(P) (stored next to P_hi in TMEM), which restores ~16 bits.  Flat tiles
 // (the common case at long context) keep the single pass: the rounding error there is << the 2e-3 parity bar.
 constexpr float kLoTau = 1.0f / 16.0f;
+#ifndef TVMB200_POLY_PAIRS
+#define TVMB200_POLY_PAIRS 4
+#endif
+constexpr int kPolyPairs = TVMB200_POLY_PAIRS;  // of every 16 column pairs, how many take the FMA-pipe exp2
 
 struct SmemLayout {
   static constexpr int q = 0;
   static constexpr int kv = q + 2 * kTileBytes;
   static constexpr int bars = kv + kSlots * kTileBytes;
-  static constexpr int tmem_ptr = bars + 128;
-  static constexpr int lo_flag = bars + 144;  // int[2]: tile t's current P has a P_lo part
+  static constexpr int tmem_ptr = bars + 192;
+  static constexpr int lo_flag = bars + 208;  // int[2][2]: P of (tile t, S buffer h) has a P_lo part
   static constexpr int scan = bars + 256;
 };
-enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 11, PV_DONE = 13, NUM_BARS = 15 };
+// S_FULL / P_READY / PV_DONE: one barrier per (tile, S buffer) = index 2 t + h.  A waiter may only ever be one phase
+// behind its barrier (parity waits alias after two); with QK(s+2) queued behind PV(s) the softmax can finish step s
+// while PV(s-1) is still running, so PV_DONE must be per buffer as well.
+enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, NUM_BARS = 21 };
 
 template <typename PT>
 __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
@@ -123,10 +136,16 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     kv_len = p.kv_indptr[b + 1] - kv_beg;
   }
   const bool causal = p.mask_mode == kMaskCausal;
-  // visible KV extent of the CTA's last valid token bounds the KV loop
-  const int tok_last = min(qo_len, tok0 + nqt * tok_per_tile) - 1;
-  const int kv_end = causal ? max(0, min(kv_len, kv_len - qo_len + tok_last + 1)) : kv_len;
-  const int n_kv = (kv_end + kKV - 1) / kKV;
+  // visible KV extent of each tile's last valid token bounds that tile's step count
+  auto steps_of = [&](int t) {
+    const int tok_last = min(qo_len, tok0 + (t + 1) * tok_per_tile) - 1;
+    const int kv_end = causal ? max(0, min(kv_len, kv_len - qo_len + tok_last + 1)) : kv_len;
+    return (t < nqt) ? (kv_end + kStep - 1) / kStep : 0;
+  };
+  const int ns0 = steps_of(0), ns1 = steps_of(1);
+  auto ns = [&](int t) { return t ? ns1 : ns0; };
+  const int max_ns = max(ns0, ns1);
+  const int n_kv = (max_ns + 1) >> 1;  // 128-row K / V tiles to load
 
   // ---- one-time setup ------------------------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -139,9 +158,11 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(bar(KV_EMPTY + i), 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(bar(S_FULL + t), 1);
-      mbar_init(bar(P_READY + t), kRows);
-      mbar_init(bar(PV_DONE + t), 1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(bar(S_FULL + 2 * t + h), 1);
+        mbar_init(bar(P_READY + 2 * t + h), kRows);
+        mbar_init(bar(PV_DONE + 2 * t + h), 1);
+      }
     }
     mbar_fence_init();
   }
@@ -156,7 +177,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t sq = sbase + SmemLayout::q, skv = sbase + SmemLayout::kv;
 
   if (warp < 4) {
-    tc05::setmaxnreg_dec<56>();
+    tc05::setmaxnreg_dec<64>();
     if (warp == 0) {
       // =========================== TMA producer ===========================
       if (n_kv > 0) {
@@ -194,79 +215,94 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     } else if (warp == 1) {
       // =========================== MMA issuer ===========================
-      if (n_kv > 0) {
-        auto issue_qk = [&](int t, uint32_t kslot) {
-          const uint32_t a0 = sq + t * kTileBytes, b0 = skv + kslot * kTileBytes;
+      if (max_ns > 0) {
+        // descriptors: high words are constant per operand kind, low words = (address >> 4) | LBO field
+        const uint64_t dkm = tc05::make_smem_desc(0, 16, 1024);          // K-major operands (Q, K)
+        const uint64_t dmn = tc05::make_smem_desc(0, kHalfBytes, 1024);  // MN-major operand (V)
+        const uint32_t kmaj_hi = static_cast<uint32_t>(dkm >> 32), kmaj_lo = static_cast<uint32_t>(dkm);
+        const uint32_t mnmaj_hi = static_cast<uint32_t>(dmn >> 32), mnmaj_lo = static_cast<uint32_t>(dmn);
+        const uint32_t q_lo = kmaj_lo + (sq >> 4), k_lo = kmaj_lo + (skv >> 4), v_lo = mnmaj_lo + (skv >> 4);
+        // S buffer `buf` of tile t = Q_t x (rows [64 half, 64 half + 64) of the K tile in `kslot`)^T
+        auto issue_qk = [&](int t, uint32_t kslot, int half, int buf) {
+          const uint32_t a0 = q_lo + ((t * kTileBytes) >> 4);
+          const uint32_t b0 = k_lo + ((kslot * kTileBytes + half * (kStep * 128)) >> 4);
+          const uint32_t d = tmem + t * 128 + buf * kStep;
 #pragma unroll
           for (int s = 0; s < kD / 16; ++s) {
-            const uint32_t off = (s >> 2) * kHalfBytes + (s & 3) * 32;
-            tc05::mma_ss(tmem + t * 128, tc05::make_smem_desc(a0 + off, 16, 1024),
-                         tc05::make_smem_desc(b0 + off, 16, 1024), idesc_qk, s > 0);
+            const uint32_t off = ((s >> 2) * kHalfBytes + (s & 3) * 32) >> 4;
+            tc05::mma_ss_w(d, a0 + off, kmaj_hi, b0 + off, kmaj_hi, idesc_qk, s > 0);
           }
         };
-        auto issue_pv = [&](int t, uint32_t vslot, bool acc, bool with_lo) {
-          const uint32_t b0 = skv + vslot * kTileBytes;
+        auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc, bool with_lo) {
+          const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
+          const uint32_t p0 = tmem + t * 128 + half * kStep;
+          const uint32_t d = tmem + 256 + t * 128;
 #pragma unroll
-          for (int s = 0; s < kKV / 16; ++s) {
+          for (int s = 0; s < kStep / 16; ++s) {
             // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
-            tc05::mma_ts(tmem + 256 + t * 128, tmem + t * 128 + s * 8,
-                         tc05::make_smem_desc(b0 + s * 16 * 128, kHalfBytes, 1024), idesc_pv, (acc || s > 0) ? 1u : 0u);
+            tc05::mma_ts_w(d, p0 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv, (acc || s > 0) ? 1u : 0u);
           }
           if (with_lo) {
 #pragma unroll
-            for (int s = 0; s < kKV / 16; ++s)
-              tc05::mma_ts(tmem + 256 + t * 128, tmem + t * 128 + 64 + s * 8,
-                           tc05::make_smem_desc(b0 + s * 16 * 128, kHalfBytes, 1024), idesc_pv, 1u);
+            for (int s = 0; s < kStep / 16; ++s)
+              tc05::mma_ts_w(d, p0 + 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv, 1u);
           }
         };
         mbar_wait(bar(Q_FULL), 0);
         mbar_wait(bar(KV_FULL + 0), 0);  // K_0
         tc05::fence_after_sync();
-        if (lane == 0) {
-          for (int t = 0; t < nqt; ++t) {
-            issue_qk(t, 0);
-            tc05::commit(bar(S_FULL + t));
-          }
+        if (tc05::elect_one()) {
+          for (int s0 = 0; s0 < 2; ++s0)
+            for (int t = 0; t < 2; ++t)
+              if (s0 < ns(t)) {
+                issue_qk(t, 0, s0, s0);
+                tc05::commit(bar(S_FULL + 2 * t + s0));
+              }
           tc05::commit(bar(KV_EMPTY + 0));
         }
         __syncwarp();
-        for (int j = 0; j < n_kv; ++j) {
+        for (int s = 0; s < max_ns; ++s) {
+          const int j = s >> 1, h = s & 1;
           const int fv = 2 * j + 1, fk = 2 * j + 2;
           const int vslot = fv & (kSlots - 1), kslot = fk & (kSlots - 1);
-          const bool more = j + 1 < n_kv;
-          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
-          if (PAGED && !more) {
-            // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
-            // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-            const int valid = kv_len - j * kKV;
-            if (valid < kKV) {
-              for (int it = lane; it < (kKV - valid) * 16; it += 32) {
-                const int r = valid + (it >> 4), c = it & 15;
-                const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+          const bool more_k = 2 * j + 2 < max_ns;  // K_{j+1} exists (steps 2j+2, 2j+3 read it)
+          if (h == 0) {
+            mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
+            if (PAGED && j == n_kv - 1) {
+              // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
+              // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
+              const int valid = kv_len - j * kKV;
+              if (valid < kKV) {
+                for (int it = lane; it < (kKV - valid) * 16; it += 32) {
+                  const int r = valid + (it >> 4), c = it & 15;
+                  const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
+                  asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
               }
-              fence_proxy_async();
-              __syncwarp();
             }
+            if (more_k) mbar_wait(bar(KV_FULL + kslot), (fk / kSlots) & 1);
           }
-          if (more) mbar_wait(bar(KV_FULL + kslot), (fk / kSlots) & 1);
-          for (int t = 0; t < nqt; ++t) {
-            mbar_wait(bar(P_READY + t), j & 1);
+          for (int t = 0; t < 2; ++t) {
+            if (s >= ns(t)) continue;
+            mbar_wait(bar(P_READY + 2 * t + h), (s >> 1) & 1);
             tc05::fence_after_sync();
-            const bool with_lo = kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * t) != 0;
-            if (lane == 0) {
-              issue_pv(t, vslot, j > 0, with_lo);
-              tc05::commit(bar(PV_DONE + t));
-              if (more) {
-                issue_qk(t, kslot);
-                tc05::commit(bar(S_FULL + t));
+            const bool with_lo =
+                kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) != 0;
+            if (tc05::elect_one()) {
+              issue_pv(t, vslot, h, s > 0, with_lo);
+              tc05::commit(bar(PV_DONE + 2 * t + h));
+              if (s + 2 < ns(t)) {
+                issue_qk(t, kslot, h, h);
+                tc05::commit(bar(S_FULL + 2 * t + h));
               }
             }
             __syncwarp();
           }
-          if (lane == 0) {
+          if ((h == 1 || s == max_ns - 1) && tc05::elect_one()) {
             tc05::commit(bar(KV_EMPTY + vslot));
-            if (more) tc05::commit(bar(KV_EMPTY + kslot));
+            if (more_k) tc05::commit(bar(KV_EMPTY + kslot));
           }
           __syncwarp();
         }
@@ -288,33 +324,36 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     float m_used = kNegInit, l = 0.f;
     const float sc = p.scale_log2;
 
+    const int my_ns = ns(t);
     if (t < nqt) {
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(bar(S_FULL + t), j & 1);
+      for (int s = 0; s < my_ns; ++s) {
+        const int hb = s & 1;                       // S buffer of this step
+        const uint32_t t_sb = t_s + hb * kStep;
+        mbar_wait(bar(S_FULL + 2 * t + hb), (s >> 1) & 1);
         tc05::fence_after_sync();
-        uint32_t s0[32], s1[32], s2[32], s3[32];
-        tc05::ld32(t_s + 0, s0);
-        tc05::ld32(t_s + 32, s1);
-        tc05::ld32(t_s + 64, s2);
-        tc05::ld32(t_s + 96, s3);
+        uint32_t s0[32], s1[32];
+        tc05::ld32(t_sb + 0, s0);
+        tc05::ld32(t_sb + 32, s1);
         tc05::wait_ld();
-        const int rem = limit - j * kKV;  // columns [0, rem) of this tile are visible
-        if (__any_sync(0xffffffffu, rem < kKV)) {
+        const int rem = limit - s * kStep;  // columns [0, rem) of this step are visible
+        if (__any_sync(0xffffffffu, rem < kStep)) {
           const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             if (c >= rem) s0[c] = ninf;
             if (c + 32 >= rem) s1[c] = ninf;
-            if (c + 64 >= rem) s2[c] = ninf;
-            if (c + 96 >= rem) s3[c] = ninf;
           }
         }
-        float mx = -INFINITY;
+        // four independent FMNMX3 chains, 8 deep each
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
-          mx = fmaxf(mx, fmaxf(__uint_as_float(s2[c]), __uint_as_float(s3[c])));
+        for (int c = 0; c < 32; c += 4) {
+          mx0 = tc05::fmax3(mx0, __uint_as_float(s0[c]), __uint_as_float(s0[c + 1]));
+          mx1 = tc05::fmax3(mx1, __uint_as_float(s0[c + 2]), __uint_as_float(s0[c + 3]));
+          mx2 = tc05::fmax3(mx2, __uint_as_float(s1[c]), __uint_as_float(s1[c + 1]));
+          mx3 = tc05::fmax3(mx3, __uint_as_float(s1[c + 2]), __uint_as_float(s1[c + 3]));
         }
+        const float mx = fmaxf(tc05::fmax3(mx0, mx1, mx2), mx3);
         const float m_new = fmaxf(m_used, mx * sc);
         // lazy rescale: keep the old reference max while the true max is within 2^8 of it
         const bool grow = m_new - m_used > kRescaleThreshold;
@@ -324,8 +363,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             m_used = m_new;
             l *= alpha;
           }
-          if (j > 0) {
-            mbar_wait(bar(PV_DONE + t), (j - 1) & 1);  // O_t must be complete before it is rescaled
+          if (s > 0) {
+            mbar_wait(bar(PV_DONE + 2 * t + ((s - 1) & 1)), ((s - 1) >> 1) & 1);  // O_t must be complete before it is rescaled
             tc05::fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -339,51 +378,58 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         const float mneg = -m_used;
-        float sum = 0.f;
-        // p in place (s regs), P_hi packed and stored 32 columns at a time
-        auto exp_pack_store = [&](uint32_t (&sr)[32], int chunk) {
-          uint32_t pk[16];
+        const float2 sc2 = make_float2(sc, sc), mneg2 = make_float2(mneg, mneg);
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+        // p in place (s regs), P_hi packed into 32 columns.  Scale/subtract and the row sum run as packed
+        // FFMA2 / FADD2; kPolyPairs of every 16 pairs take 2^x on the FMA pipe instead of the MUFU unit
+        // (the MUFU needs as many cycles per tile as the tensor core: 128x128 ex2 at 16/clk/SM = 1024 clk).
+        uint32_t pk[32];
+        auto exp_pack = [&](uint32_t (&sr)[32], int chunk) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float a0 = fast_exp2(fmaf(__uint_as_float(sr[c]), sc, mneg));
-            const float a1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), sc, mneg));
-            sum += a0 + a1;
-            sr[c] = __float_as_uint(a0);
-            sr[c + 1] = __float_as_uint(a1);
-            pk[c >> 1] = pack_p<PT>(a0, a1);
+            const int pi = c >> 1;
+            const bool poly = ((pi + 1) * kPolyPairs) / 16 != (pi * kPolyPairs) / 16;
+            const float2 x = tc05::ffma2(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, mneg2);
+            float2 a;
+            if (poly) {
+              a = tc05::exp2_poly2(x);
+            } else {
+              a.x = fast_exp2(x.x);
+              a.y = fast_exp2(x.y);
+            }
+            if (pi & 1) sum_b = tc05::fadd2(sum_b, a); else sum_a = tc05::fadd2(sum_a, a);
+            sr[c] = __float_as_uint(a.x);
+            sr[c + 1] = __float_as_uint(a.y);
+            pk[chunk * 16 + pi] = pack_p<PT>(a.x, a.y);
           }
-          tc05::st16(t_s + chunk * 16, pk);
         };
-        exp_pack_store(s0, 0);
-        exp_pack_store(s1, 1);
-        exp_pack_store(s2, 2);
-        exp_pack_store(s3, 3);
-        l += sum;
+        exp_pack(s0, 0);
+        exp_pack(s1, 1);
+        tc05::st32(t_sb, pk);
+        sum_a = tc05::fadd2(sum_a, sum_b);
+        l += sum_a.x + sum_a.y;
         if (kLoPass) {
-          // largest weight of this row in this tile vs. the running denominator
+          // largest weight of this row in this step vs. the running denominator
           const float p_max = fast_exp2(fmaf(mx, sc, mneg));
           const bool need_lo = wg_any(p_max > kLoTau * l, 1 + t);
           if (need_lo) {
-            auto lo_store = [&](const uint32_t (&sr)[32], int chunk) {
-              uint32_t pk[16];
+            auto lo_pack = [&](const uint32_t (&sr)[32], int chunk) {
 #pragma unroll
               for (int c = 0; c < 32; c += 2) {
                 const float a0 = __uint_as_float(sr[c]), a1 = __uint_as_float(sr[c + 1]);
-                const float2 hi2 = DT<PT>::to_f2(pack_p<PT>(a0, a1));
-                pk[c >> 1] = pack_p<PT>(a0 - hi2.x, a1 - hi2.y);
+                const float2 hi2 = DT<PT>::to_f2(pk[chunk * 16 + (c >> 1)]);
+                pk[chunk * 16 + (c >> 1)] = pack_p<PT>(a0 - hi2.x, a1 - hi2.y);
               }
-              tc05::st16(t_s + 64 + chunk * 16, pk);
             };
-            lo_store(s0, 0);
-            lo_store(s1, 1);
-            lo_store(s2, 2);
-            lo_store(s3, 3);
+            lo_pack(s0, 0);
+            lo_pack(s1, 1);
+            tc05::st32(t_sb + 32, pk);
           }
-          if (r == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * t) = need_lo ? 1 : 0;
+          if (r == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = need_lo ? 1 : 0;
         }
         tc05::wait_st();
         tc05::fence_before_sync();
-        mbar_arrive(bar(P_READY + t));
+        mbar_arrive(bar(P_READY + 2 * t + hb));
       }
       // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
       T* orow = nullptr;
@@ -392,8 +438,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         orow = static_cast<T*>(p.output) + (static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq) * kD;
         p.lse[static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq] = l > 0.f ? m_used + log2f(l) : kNegInit;
       }
-      if (n_kv > 0) {
-        mbar_wait(bar(PV_DONE + t), (n_kv - 1) & 1);
+      if (my_ns > 0) {
+        mbar_wait(bar(PV_DONE + 2 * t + ((my_ns - 1) & 1)), ((my_ns - 1) >> 1) & 1);
         tc05::fence_after_sync();
         const float inv = l > 0.f ? 1.0f / l : 0.f;
 #pragma unroll
@@ -458,7 +504,7 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
-  const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
+  const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kStep);
   const uint32_t idesc_pv = tc05::make_idesc(fp, fa, 0, 1, kRows, kD);
   kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv);
   TVMB200_LAUNCH_OK();

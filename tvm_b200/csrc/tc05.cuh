@@ -48,6 +48,15 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt
          ((M >> 4) << 24);
 }
 
+// one lane of a converged warp; ptxas knows the guarded region runs on a single thread, so tcgen05 operands stay
+// in uniform registers without a per-thread replay loop (an `if (lane == 0)` guard costs ~10 extra
+// instructions per MMA, which is more than the 32-64 clk the tensor pipe needs for one)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {
@@ -64,6 +73,24 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with descriptors given as (low word, high word): the high word is constant per operand kind and the low
+// word is base + (byte offset >> 4), i.e. one uniform add per MMA instead of re-encoding the descriptor
+__device__ __forceinline__ void mma_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on an mbarrier when every tcgen05 op issued so far by this thread has completed
@@ -111,6 +138,56 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst_smem),
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
       : "memory");
+}
+
+// ---- packed fp32 pairs (FFMA2 / FADD2) and 3-input max (FMNMX3): halve the issue slots of the softmax ---------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {  // round toward -inf
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+      "add.rm.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// 2^x for a pair on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [0,1), 2^f by a degree-3 minimax
+// polynomial (max relative error 8.8e-5, far below the 2^-9 / 2^-11 rounding of the 16-bit P operand), and n added
+// straight into the exponent field.  x <= 126 is assumed (the lazy rescale keeps it <= 8); x is clamped at -126.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xr = fadd2_rm(x, make_float2(kMagic, kMagic));
+  const float2 xf = fadd2(xr, make_float2(-kMagic, -kMagic));  // floor(x)
+  const float2 f = ffma2(xf, make_float2(-1.0f, -1.0f), x);
+  float2 pl = ffma2(f, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                    make_float2(0.227564394474029541f, 0.227564394474029541f));
+  pl = ffma2(pl, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  pl = ffma2(pl, f, make_float2(1.0f, 1.0f));
+  float2 r;
+  r.x = __int_as_float((__float_as_int(xr.x) << 23) + __float_as_int(pl.x));
+  r.y = __int_as_float((__float_as_int(xr.y) << 23) + __float_as_int(pl.y));
+  return r;
 }
 
 template <int N>
