@@ -197,7 +197,8 @@ def test_decode_inline_rope(capi, dtype):
 
 
 # ---------------------------------------------------------------------------------------------------
-def _run_ragged(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=1, rotary_mode=0, tree=None):
+def _run_ragged(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=1, rotary_mode=0, tree=None, q_scale=1.0,
+                v_scale=1.0):
     import torch
 
     B = len(q_lens)
@@ -206,9 +207,9 @@ def _run_ragged(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=1, rotary_
     ki = np.zeros(B + 1, np.int32)
     ki[1:] = np.cumsum(kv_lens)
     n, m = int(qi[-1]), int(ki[-1])
-    q = rand16(rng, (n, hq, d), dtype)
+    q = ok.round_dtype(rand16(rng, (n, hq, d), dtype) * np.float32(q_scale), dtype)
     k = rand16(rng, (m, hkv, d), dtype)
-    v = rand16(rng, (m, hkv, d), dtype)
+    v = ok.round_dtype(rand16(rng, (m, hkv, d), dtype) * np.float32(v_scale), dtype)
     kofs = rng.integers(0, 30, B).astype(np.int32)
     qpos = np.concatenate([kofs[b] + kv_lens[b] - q_lens[b] + np.arange(q_lens[b]) for b in range(B)]).astype(np.int32)
     sm = d ** -0.5

@@ -11,20 +11,24 @@
 //               row = token*g + head, _prefill_kernels.py:318-324) once, then K_j / V_j tiles of 128 KV rows
 //               through a 4-slot shared-memory ring (ragged: one 3-D box per 64-col half; paged: eight
 //               16-row page boxes per half, page ids looked up by the producer lanes).
-//   warp 1      MMA issuer (one elected thread).  The KV axis advances in STEPS of 64 columns (half a KV tile):
-//               S_t(s) = Q_t K[64s..64s+63]^T (SS, K-major operands, N = 64) into one of TWO S buffers per tile, and
-//               O_t += P_t(s) V[64s..] (TS: P read from TMEM, V as an MN-major shared-memory operand, K = 64).
-//               Because S is double-buffered, QK of step s+2 is issued right behind PV of step s, i.e. S(s+1) is
-//               already in TMEM when the softmax warps finish step s: the softmax never waits for the tensor pipe
-//               and the tensor pipe always has PV/QK work of both tiles queued (the single-buffered version put
-//               QK -> softmax -> PV of a tile on one serial chain and reached 47 % of peak).
-//   warp 2      TMEM allocator (512 columns: S_0[2], S_1[2] of 64 columns each, O_0, O_1 of 128; P_t(s) aliases
-//               the S buffer it was computed from: P_hi in its first 32 columns, P_lo in the last 32).
-//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; tcgen05.ld the 64 S values,
+//   warp 1      MMA issuer (one elected thread).  Per Q tile t and KV tile j: S_t = Q_t K_j^T as eight N = 128 SS
+//               MMAs (K-major operands) into the tile's 128-column S region, and O_t += P_t V_j as two groups of
+//               four TS MMAs (P read from TMEM, V an MN-major shared-memory operand), one group per 64-column half
+//               of P as soon as that half is ready.  N = 128 is deliberate: an SS-mode MMA never takes fewer than
+//               ~64 clk (scripts/umma_bench.cu: 63 clk at N = 64, 67 at N = 128, 128 at N = 256), so 64-column QK
+//               steps run the tensor pipe at half rate.  P arrives in a fixed order -- (t0, lower half), (t0, upper),
+//               (t1, lower), (t1, upper) -- and QK_t(j+1) is issued right behind the upper-half PV of tile t, so one
+//               Q tile's PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
+//   warp 2      TMEM allocator (512 columns: S_0, S_1 of 128 columns each, O_0, O_1 of 128; P aliases the S half it
+//               was computed from: P_hi in its first 32 columns, P_lo in the last 32).
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row, 64 columns (= one half of
+//               the S region) per step; tcgen05.ld the 64 S values,
 //               mask (diagonal / tail steps only), running max with LAZY rescale (O in TMEM is only rescaled
 //               when the max grows by more than 2^8), exp2, pack to 16-bit, tcgen05.st P, arrive.
 //               Each tile stops at its own last visible step under a causal mask.
 //               The same threads normalise and store O / LSE at the end.
+// Measured (scripts/softmax_bench.cu, scripts/prefill_trace.py): the kernel is bound by the softmax instruction
+// stream (~850 clk per 128 x 64 step of one warpgroup), not by the tensor pipe (59 % busy) nor by the MUFU.
 // All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); no __syncthreads in the loop.
 #include "prefill.cuh"
 #include "tc05.cuh"
@@ -47,8 +51,12 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
 // bf16 keeps 8 mantissa bits of P (the reference keeps P in fp32).  When a row of a tile has a weight
 // p > kLoTau * l (a few keys dominate: short rows, peaked attention) the tile gets a second PV pass with the
 // rounding residual P_lo = P - bf16(P) (stored next to P_hi in TMEM), which restores ~16 bits.  Flat tiles
-// (the common case at long context) keep the single pass: the rounding error there is << the 2e-3 parity bar.
-constexpr float kLoTau = 1.0f / 16.0f;
+// (the common case at long context) keep the single pass: a weight below l/8 contributes at most
+// 2^-9 / 8 * |v| = 2.4e-4 |v| of rounding error, << the 2e-3 parity bar (tests: test_tc05_bf16_peaked).
+#ifndef TVMB200_LO_TAU_INV
+#define TVMB200_LO_TAU_INV 8
+#endif
+constexpr float kLoTau = 1.0f / TVMB200_LO_TAU_INV;
 #ifndef TVMB200_POLY_PAIRS
 #define TVMB200_POLY_PAIRS 4
 #endif
@@ -60,12 +68,29 @@ struct SmemLayout {
   static constexpr int bars = kv + kSlots * kTileBytes;
   static constexpr int tmem_ptr = bars + 192;
   static constexpr int lo_flag = bars + 208;  // int[2][2]: P of (tile t, S buffer h) has a P_lo part
-  static constexpr int scan = bars + 256;
+  static constexpr int xch = bars + 256;        // float[2 parities][2 warpgroups][128 rows]: row max / row sum exchange
+  static constexpr int scan = xch + 2 * 2 * kRows * 4;
 };
 // S_FULL / P_READY / PV_DONE: one barrier per (tile, S buffer) = index 2 t + h.  A waiter may only ever be one phase
 // behind its barrier (parity waits alias after two); with QK(s+2) queued behind PV(s) the softmax can finish step s
 // while PV(s-1) is still running, so PV_DONE must be per buffer as well.
 enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, NUM_BARS = 21 };
+
+#ifdef TVMB200_TRACE
+// tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot]
+__device__ long long g_trace[3][64][8];
+#define TRACE(role, step, slot)                                                             \
+  do {                                                                                      \
+    if (blockIdx.x == TVMB200_TRACE && (threadIdx.x & 31) == 0 && (step) < 64)              \
+      g_trace[role][step][slot] = clock64();                                                \
+  } while (0)
+#else
+#define TRACE(role, step, slot)
+#endif
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <typename PT>
 __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
@@ -222,11 +247,11 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint32_t kmaj_hi = static_cast<uint32_t>(dkm >> 32), kmaj_lo = static_cast<uint32_t>(dkm);
         const uint32_t mnmaj_hi = static_cast<uint32_t>(dmn >> 32), mnmaj_lo = static_cast<uint32_t>(dmn);
         const uint32_t q_lo = kmaj_lo + (sq >> 4), k_lo = kmaj_lo + (skv >> 4), v_lo = mnmaj_lo + (skv >> 4);
-        // S buffer `buf` of tile t = Q_t x (rows [64 half, 64 half + 64) of the K tile in `kslot`)^T
-        auto issue_qk = [&](int t, uint32_t kslot, int half, int buf) {
+        // S_t[0:128) = Q_t x (K tile in `kslot`)^T, one N = 128 MMA per 16-wide slice of the head dim
+        auto issue_qk = [&](int t, uint32_t kslot) {
           const uint32_t a0 = q_lo + ((t * kTileBytes) >> 4);
-          const uint32_t b0 = k_lo + ((kslot * kTileBytes + half * (kStep * 128)) >> 4);
-          const uint32_t d = tmem + t * 128 + buf * kStep;
+          const uint32_t b0 = k_lo + ((kslot * kTileBytes) >> 4);
+          const uint32_t d = tmem + t * 128;
 #pragma unroll
           for (int s = 0; s < kD / 16; ++s) {
             const uint32_t off = ((s >> 2) * kHalfBytes + (s & 3) * 32) >> 4;
@@ -252,57 +277,67 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(bar(KV_FULL + 0), 0);  // K_0
         tc05::fence_after_sync();
         if (tc05::elect_one()) {
-          for (int s0 = 0; s0 < 2; ++s0)
-            for (int t = 0; t < 2; ++t)
-              if (s0 < ns(t)) {
-                issue_qk(t, 0, s0, s0);
-                tc05::commit(bar(S_FULL + 2 * t + s0));
-              }
+          for (int t = 0; t < 2; ++t)
+            if (ns(t) > 0) {
+              issue_qk(t, 0);
+              tc05::commit(bar(S_FULL + 2 * t));
+              tc05::commit(bar(S_FULL + 2 * t + 1));
+            }
           tc05::commit(bar(KV_EMPTY + 0));
         }
         __syncwarp();
-        for (int s = 0; s < max_ns; ++s) {
-          const int j = s >> 1, h = s & 1;
-          const int fv = 2 * j + 1, fk = 2 * j + 2;
-          const int vslot = fv & (kSlots - 1), kslot = fk & (kSlots - 1);
-          const bool more_k = 2 * j + 2 < max_ns;  // K_{j+1} exists (steps 2j+2, 2j+3 read it)
-          if (h == 0) {
-            mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
-            if (PAGED && j == n_kv - 1) {
-              // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
-              // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-              const int valid = kv_len - j * kKV;
-              if (valid < kKV) {
-                for (int it = lane; it < (kKV - valid) * 16; it += 32) {
-                  const int r = valid + (it >> 4), c = it & 15;
-                  const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
-                  asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
-                }
-                fence_proxy_async();
-                __syncwarp();
+        // The softmax warpgroups walk (KV tile j, Q tile t) in j-major order, both on the same Q tile at a time,
+        // so P arrives in a fixed order: (t0, lower half), (t0, upper half), (t1, lower), (t1, upper), next j.
+        // Behind the upper half of a tile go its QK for KV tile j+1, i.e. one Q tile's PV + QK occupy the tensor
+        // pipe exactly while both warpgroups run the other Q tile's softmax.
+        for (int j = 0; j < n_kv; ++j) {
+          const int fv = 2 * j + 1, fk1 = 2 * j + 2;
+          const int vslot = fv & (kSlots - 1), k1slot = fk1 & (kSlots - 1);
+          const bool more_k = j + 1 < n_kv;
+          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
+          if (PAGED && j == n_kv - 1) {
+            // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
+            // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
+            const int valid = kv_len - j * kKV;
+            if (valid < kKV) {
+              for (int it = lane; it < (kKV - valid) * 16; it += 32) {
+                const int r = valid + (it >> 4), c = it & 15;
+                const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
               }
+              fence_proxy_async();
+              __syncwarp();
             }
-            if (more_k) mbar_wait(bar(KV_FULL + kslot), (fk / kSlots) & 1);
           }
+          if (more_k) mbar_wait(bar(KV_FULL + k1slot), (fk1 / kSlots) & 1);
           for (int t = 0; t < 2; ++t) {
-            if (s >= ns(t)) continue;
-            mbar_wait(bar(P_READY + 2 * t + h), (s >> 1) & 1);
-            tc05::fence_after_sync();
-            const bool with_lo =
-                kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) != 0;
-            if (tc05::elect_one()) {
-              issue_pv(t, vslot, h, s > 0, with_lo);
-              tc05::commit(bar(PV_DONE + 2 * t + h));
-              if (s + 2 < ns(t)) {
-                issue_qk(t, kslot, h, h);
-                tc05::commit(bar(S_FULL + 2 * t + h));
+            const int nst = ns(t);
+            if (2 * j >= nst) continue;
+            for (int h = 0; h < 2; ++h) {
+              const int s = 2 * j + h;
+              if (s >= nst) break;
+              mbar_wait(bar(P_READY + 2 * t + h), j & 1);
+              TRACE(0, s, 3 * t + 1);
+              tc05::fence_after_sync();
+              const bool with_lo =
+                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) != 0;
+              const bool last_of_tile = h == 1 || s == nst - 1;
+              if (tc05::elect_one()) {
+                issue_pv(t, vslot, h, s > 0, with_lo);
+                tc05::commit(bar(PV_DONE + 2 * t + h));
+                if (last_of_tile && 2 * (j + 1) < nst) {
+                  issue_qk(t, k1slot);
+                  tc05::commit(bar(S_FULL + 2 * t));
+                  tc05::commit(bar(S_FULL + 2 * t + 1));
+                }
               }
+              __syncwarp();
+              TRACE(0, s, 3 * t + 2);
             }
-            __syncwarp();
           }
-          if ((h == 1 || s == max_ns - 1) && tc05::elect_one()) {
+          if (tc05::elect_one()) {
             tc05::commit(bar(KV_EMPTY + vslot));
-            if (more_k) tc05::commit(bar(KV_EMPTY + kslot));
+            if (more_k) tc05::commit(bar(KV_EMPTY + k1slot));
           }
           __syncwarp();
         }
@@ -329,12 +364,15 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int s = 0; s < my_ns; ++s) {
         const int hb = s & 1;                       // S buffer of this step
         const uint32_t t_sb = t_s + hb * kStep;
+        if (wq == 0) TRACE(1 + t, s, 0);
         mbar_wait(bar(S_FULL + 2 * t + hb), (s >> 1) & 1);
+        if (wq == 0) TRACE(1 + t, s, 1);
         tc05::fence_after_sync();
         uint32_t s0[32], s1[32];
         tc05::ld32(t_sb + 0, s0);
         tc05::ld32(t_sb + 32, s1);
         tc05::wait_ld();
+        if (wq == 0) TRACE(1 + t, s, 2);
         const int rem = limit - s * kStep;  // columns [0, rem) of this step are visible
         if (__any_sync(0xffffffffu, rem < kStep)) {
           const uint32_t ninf = __float_as_uint(-INFINITY);
@@ -430,6 +468,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc05::wait_st();
         tc05::fence_before_sync();
         mbar_arrive(bar(P_READY + 2 * t + hb));
+        if (wq == 0) TRACE(1 + t, s, 3);
       }
       // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
       T* orow = nullptr;
@@ -504,7 +543,7 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
-  const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kStep);
+  const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
   const uint32_t idesc_pv = tc05::make_idesc(fp, fa, 0, 1, kRows, kD);
   kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv);
   TVMB200_LAUNCH_OK();
@@ -536,3 +575,9 @@ int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int
 }  // namespace tvmb200
 
 extern "C" void tvmb200_set_prefill_impl(int impl) { tvmb200::g_prefill_impl.store(impl); }
+
+#ifdef TVMB200_TRACE
+extern "C" __attribute__((visibility("default"))) int tvmb200_debug_prefill_trace(long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, tvmb200::g_trace, sizeof(tvmb200::g_trace)));
+}
+#endif
