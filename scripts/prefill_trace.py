@@ -26,6 +26,11 @@ buf = (ctypes.c_longlong * (3 * 64 * 8))()
 rc = L.tvmb200_debug_prefill_trace(buf)
 assert rc == 0, rc
 tr = np.frombuffer(buf, dtype=np.int64).reshape(3, 64, 8)
+lo_used = tr[0, :, [0, 3]].copy()  # with_lo flags of the MMA warp, not time stamps
+tr[0, :, 0] = 0
+tr[0, :, 3] = 0
+print("P_lo pass used per step (tile 0):", lo_used[0][:32].tolist())
+print("P_lo pass used per step (tile 1):", lo_used[1][:32].tolist())
 t0 = tr[tr > 0].min()
 rel = np.where(tr > 0, tr - t0, -1)
 mode = sys.argv[2] if len(sys.argv) > 2 else "tile"
@@ -39,7 +44,9 @@ if mode == "tile":
         if a[3] < 0 and b[3] < 0:
             break
         print(f"{s:3d} | {a[1]-a[0]:6d} {a[2]-a[1]:5d} {a[3]-a[2]:5d} {a[3]:8d} | {b[1]-b[0]:6d} {b[2]-b[1]:5d} {b[3]-b[2]:5d} {b[3]:8d} |"
-              f" {m[1]:7d} {m[2]:7d} ({m[2]-m[1]:4d}) | {m[4]:7d} {m[5]:7d} ({m[5]-m[4]:4d})")
+              f" {m[1]:7d} {m[2]:7d} ({m[2]-m[1]:4d}) | {m[4]:7d} {m[5]:7d} ({m[5]-m[4]:4d})"
+              f" || T0 phases: max {a[4]-a[2]:4d} exp {a[5]-a[4]:4d} st+lo {a[6]-a[5]:4d} wait_st+arrive {a[3]-a[6]:4d}"
+              f" | T1: max {b[4]-b[2]:4d} exp {b[5]-b[4]:4d} st+lo {b[6]-b[5]:4d} wait_st+arrive {b[3]-b[6]:4d}")
 else:
     print("role 0 (MMA warp) index s = 2j+h: [3t+1] P ready seen, [3t+2] PV(+QK) issued;  roles 1/2 (softmax warpgroup 0/1)")
     print("index 2j+t: [0] wait S, [1] S ready, [2] ld done, [3] P arrive.   all times in clk from the first stamp")

@@ -99,17 +99,6 @@ __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
 
 }  // namespace
 
-__device__ __forceinline__ bool wg_any(bool pred, int barrier_id) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %1, 0;\n\t"
-      "bar.red.or.pred pout, %2, 128, pin;\n\tselp.u32 %0, 1, 0, pout;\n\t}"
-      : "=r"(out)
-      : "r"(static_cast<uint32_t>(pred)), "r"(barrier_id)
-      : "memory");
-  return out != 0;
-}
-
 template <typename T, typename PT, bool PAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -189,6 +178,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_init(bar(PV_DONE + 2 * t + h), 1);
       }
     }
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * i) = 0;
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -262,15 +252,17 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
           const uint32_t p0 = tmem + t * 128 + half * kStep;
           const uint32_t d = tmem + 256 + t * 128;
+          // second trip = the P_lo residual pass.  A real loop on purpose: ptxas predicates an `if (with_lo)` body,
+          // and a predicated-off UTCHMMA still costs the issuing thread a full MMA slot (measured: +300 clk per group)
+          const int passes = with_lo ? 2 : 1;
+#pragma unroll 1
+          for (int ps = 0; ps < passes; ++ps) {
 #pragma unroll
-          for (int s = 0; s < kStep / 16; ++s) {
-            // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
-            tc05::mma_ts_w(d, p0 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv, (acc || s > 0) ? 1u : 0u);
-          }
-          if (with_lo) {
-#pragma unroll
-            for (int s = 0; s < kStep / 16; ++s)
-              tc05::mma_ts_w(d, p0 + 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv, 1u);
+            for (int s = 0; s < kStep / 16; ++s) {
+              // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
+              tc05::mma_ts_w(d, p0 + ps * 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv,
+                             (acc || s > 0 || ps > 0) ? 1u : 0u);
+            }
           }
         };
         mbar_wait(bar(Q_FULL), 0);
@@ -320,7 +312,10 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               TRACE(0, s, 3 * t + 1);
               tc05::fence_after_sync();
               const bool with_lo =
-                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) != 0;
+                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) == s + 1;
+#ifdef TVMB200_TRACE
+              if (blockIdx.x == TVMB200_TRACE && lane == 0 && s < 64) g_trace[0][s][3 * t] = with_lo ? 1 : 0;
+#endif
               const bool last_of_tile = h == 1 || s == nst - 1;
               if (tc05::elect_one()) {
                 issue_pv(t, vslot, h, s > 0, with_lo);
@@ -392,6 +387,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mx3 = tc05::fmax3(mx3, __uint_as_float(s1[c + 2]), __uint_as_float(s1[c + 3]));
         }
         const float mx = fmaxf(tc05::fmax3(mx0, mx1, mx2), mx3);
+        if (wq == 0) TRACE(1 + t, s, 4);
         const float m_new = fmaxf(m_used, mx * sc);
         // lazy rescale: keep the old reference max while the true max is within 2^8 of it
         const bool grow = m_new - m_used > kRescaleThreshold;
@@ -443,13 +439,17 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         };
         exp_pack(s0, 0);
         exp_pack(s1, 1);
+        if (wq == 0) TRACE(1 + t, s, 5);
         tc05::st32(t_sb, pk);
         sum_a = tc05::fadd2(sum_a, sum_b);
         l += sum_a.x + sum_a.y;
         if (kLoPass) {
-          // largest weight of this row in this step vs. the running denominator
+          // largest weight of this row in this step vs. the running denominator.  The decision is per WARP (no
+          // warpgroup barrier): a warp with such a row stores P_lo for its 32 rows and stamps the tile's flag with
+          // this step's id; every other warp stores zeros, so a PV_lo pass triggered by another warp adds nothing
+          // for its rows.  The MMA warp runs the second pass iff the flag carries the id of the step it issues.
           const float p_max = fast_exp2(fmaf(mx, sc, mneg));
-          const bool need_lo = wg_any(p_max > kLoTau * l, 1 + t);
+          const bool need_lo = __any_sync(0xffffffffu, p_max > kLoTau * l);
           if (need_lo) {
             auto lo_pack = [&](const uint32_t (&sr)[32], int chunk) {
 #pragma unroll
@@ -461,10 +461,14 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             };
             lo_pack(s0, 0);
             lo_pack(s1, 1);
-            tc05::st32(t_sb + 32, pk);
+            if (lane == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = s + 1;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) pk[c] = 0u;
           }
-          if (r == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = need_lo ? 1 : 0;
+          tc05::st32(t_sb + 32, pk);
         }
+        if (wq == 0) TRACE(1 + t, s, 6);
         tc05::wait_st();
         tc05::fence_before_sync();
         mbar_arrive(bar(P_READY + 2 * t + hb));
