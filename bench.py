@@ -35,6 +35,10 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant kernel on the named workload,
+# from the committed `ncu --set full` captures under profiles/ (a profiler number: reported next to the algorithmic
+# bytes, never used for timing)
+NCU_DRAM_BYTES = {"decode_c2": 1074441000 + 6551808, "prefill_c3": 402782208 + 221668096}
 
 
 def measured_peaks():
@@ -297,14 +301,15 @@ def run_own(args):
                    "l2": "KV working set 1 GiB/GPU > 126 MB L2 (no flush needed)"},
         "tok_s_layer": round(world * w.B / (ms_per_step * 1e-3), 1),
         "roofline": {"bound": "hbm", "kernel": "decode_kernel(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
-                     "peak": hbm_peak, "unit": "GB/s", "frac": round(dec_gbs / hbm_peak, 4), "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": round(dec_gbs / hbm_peak, 4), "traffic": NCU_DRAM_BYTES["decode_c2"],
+                     "traffic_source": "profiles/r1_decode_v2_ncu.md: dram read+write of one launch, ncu --set full",
                      "peak_source": f"of {peak_src}", "algorithmic_bytes": w.decode_bytes(),
                      "kernel_ms": round(decode_ms, 5), "frac_of_spec_8000": round(dec_gbs / 8000.0, 4)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
     try:
-        e2e = run_e2e(args, w, world, dist)
+        e2e = {"value": None, "skipped": "--no-e2e"} if args.no_e2e else run_e2e(args, w, world, dist)
     except Exception as e:  # pragma: no cover
         e2e = {"value": None, "error": repr(e)[:300]}
     if rank == 0:
@@ -416,7 +421,11 @@ def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
            "config": {"workload": "C3 ragged causal prefill 16x2048, 32q/8kv heads, D128, bf16", "l2": "q/k/v/o "
                       "0.67 GB > L2"},
            "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(tf / peak, 4), "traffic": None, "peak_source": f"of {peak_src}",
+                        "frac": round(tf / peak, 4), "traffic": NCU_DRAM_BYTES["prefill_c3"],
+                        "traffic_source": "profiles/r1_prefill_tc05_v3_ncu.md: dram read+write of one launch (bytes)",
+                        "peak_source": f"of {peak_src} (burst; sustained " + str(peaks.get("bf16_tflops_sustained")) + ")",
+                        "frac_of_sustained": (round(tf / float(peaks["bf16_tflops_sustained"]), 4)
+                                              if peaks.get("bf16_tflops_sustained") else None),
                         "algorithmic_flops": w.flops()},
            "gpu_launches": int(capi.launch_count() - n0), "clocks": clk.summary()}
     if rank == 0:
@@ -513,6 +522,7 @@ def main():
     ap.add_argument("--workload", default="decode", choices=["decode", "prefill", "c4"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs: launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

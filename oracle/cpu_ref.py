@@ -75,40 +75,61 @@ def _one_step_ref(mod, t, Hq, Hkv, D, theta=5e5):
                                      t["kofs"], t["qpos"], t["o"], t["lse"], 0, 1.0, theta, D ** -0.5)
 
 
-def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128, budget_s=60.0):
-    """One step = split_rotary + append + decode of one layer on a B-sequence slice of C2."""
+def time_decode_steps(steps=3, warmup=1, B=1, L=4096, Hq=32, Hkv=8, D=128, budget_s=60.0, threads=None):
+    """One step = split_rotary + append + decode of one layer on a slice of C2.  The reference's CPU PrimFuncs are
+    serial, so the slice is `threads` independent B-sequence sub-batches (own pages / page tables), one per host
+    thread (tvm-ffi releases the GIL during a call): all host cores work, each on the reference's own code."""
+    import threading
+
     dtype = "float16"  # the reference's CPU path is tested in fp16/fp32 only (no bf16 CPU codegen)
-    inp = _decode_inputs(B, L, Hq, Hkv, D, dtype)
-    nnz = inp["page_values"].size
     mod = _ref_module(dtype, Hq, Hkv, D)
     kind = "reference" if mod is not None else "port"
+    ncpu = os.cpu_count() or 1
+    T = max(1, min(int(threads or ncpu), 64 // B)) if kind == "reference" else 1
+    inps = [_decode_inputs(B, L, Hq, Hkv, D, dtype, seed=i) for i in range(T)]
+    nnz = inps[0]["page_values"].size
     if mod is not None:
         import torch
 
-        t = {k_: torch.from_numpy(v_.astype(np.float16) if v_.dtype == np.float32 else v_) for k_, v_ in inp.items()}
-        t["q"] = torch.zeros((B, Hq, D), dtype=torch.float16)
-        t["k"] = torch.zeros((B, Hkv, D), dtype=torch.float16)
-        t["v"] = torch.zeros((B, Hkv, D), dtype=torch.float16)
-        t["o"] = torch.zeros((B, Hq, D), dtype=torch.float16)
-        t["lse"] = torch.zeros((B, Hq), dtype=torch.float32)
-        run = lambda: _one_step_ref(mod, t, Hq, Hkv, D)  # noqa: E731
+        def tensors(inp):
+            t = {k_: torch.from_numpy(v_.astype(np.float16) if v_.dtype == np.float32 else v_) for k_, v_ in inp.items()}
+            t["q"] = torch.zeros((B, Hq, D), dtype=torch.float16)
+            t["k"] = torch.zeros((B, Hkv, D), dtype=torch.float16)
+            t["v"] = torch.zeros((B, Hkv, D), dtype=torch.float16)
+            t["o"] = torch.zeros((B, Hq, D), dtype=torch.float16)
+            t["lse"] = torch.zeros((B, Hq), dtype=torch.float32)
+            return t
+
+        ts = [tensors(inp) for inp in inps]
+        one = lambda i: _one_step_ref(mod, ts[i], Hq, Hkv, D)  # noqa: E731
     else:
-        run = lambda: _one_step_port(inp, Hq, Hkv, D, dtype)  # noqa: E731
-    t0 = time.perf_counter()
-    for _ in range(max(warmup, 1)):
-        run()
-    t_one = (time.perf_counter() - t0) / max(warmup, 1)
+        one = lambda i: _one_step_port(inps[i], Hq, Hkv, D, dtype)  # noqa: E731
+
+    def run(n):
+        """n steps on every sub-batch, the sub-batches in parallel; returns seconds"""
+        def work(i):
+            for _ in range(n):
+                one(i)
+        t0 = time.perf_counter()
+        if T == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(i,)) for i in range(T)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        return time.perf_counter() - t0
+
+    t_one = run(max(warmup, 1)) / max(warmup, 1)
     steps = max(1, min(steps, int(budget_s / max(t_one, 1e-6))))  # bounded: the whole run ends within ~budget_s
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        run()
-    dt = (time.perf_counter() - t0) / steps
-    bytes_ = _step_bytes(B, L, Hq, Hkv, D, nnz)
+    dt = run(steps) / steps
+    bytes_ = T * _step_bytes(B, L, Hq, Hkv, D, nnz)
     return {"value": round(bytes_ / dt / 1e9, 4), "unit": "GB/s", "ms_per_step": round(dt * 1e3, 3), "steps": steps,
-            "warmup": warmup, "cores": 1 if kind == "reference" else int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "warmup": warmup, "cores": T if kind == "reference" else int(os.environ.get("OMP_NUM_THREADS", ncpu)),
             "kind": kind, "dtype": "f16",
-            "sample": f"{B}/64 of the C2 batch ({B} seq x {L} ctx, {Hq}q/{Hkv}kv, D{D}, fp16), {steps} steps; "
-                      f"host has {os.cpu_count()} cores"}
+            "sample": f"{T * B}/64 of the C2 batch ({T} threads x {B} seq x {L} ctx, {Hq}q/{Hkv}kv, D{D}, fp16), "
+                      f"{steps} steps; host has {ncpu} cores"}
 
 
 def time_decode(B=1, L=4096, Hq=32, Hkv=8, D=128, repeats=20):

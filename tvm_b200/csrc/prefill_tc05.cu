@@ -57,10 +57,15 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
 #define TVMB200_LO_TAU_INV 8
 #endif
 constexpr float kLoTau = 1.0f / TVMB200_LO_TAU_INV;
-#ifndef TVMB200_POLY_PAIRS
-#define TVMB200_POLY_PAIRS 4
+// of every 16 column pairs, how many take 2^x on the FMA pipe instead of the MUFU (swept on C3: 2 is best for bf16,
+// 4 for fp16 -- the bf16 step carries the extra P_lo work on the FMA / ALU pipes)
+#ifdef TVMB200_POLY_PAIRS
+template <typename PT>
+constexpr int kPolyPairsOf = TVMB200_POLY_PAIRS;
+#else
+template <typename PT>
+constexpr int kPolyPairsOf = std::is_same<PT, __nv_bfloat16>::value ? 2 : 4;
 #endif
-constexpr int kPolyPairs = TVMB200_POLY_PAIRS;  // of every 16 column pairs, how many take the FMA-pipe exp2
 
 struct SmemLayout {
   static constexpr int q = 0;
@@ -422,6 +427,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             const int pi = c >> 1;
+            constexpr int kPolyPairs = kPolyPairsOf<PT>;
             const bool poly = ((pi + 1) * kPolyPairs) / 16 != (pi * kPolyPairs) / 16;
             const float2 x = tc05::ffma2(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, mneg2);
             float2 a;
