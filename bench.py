@@ -109,8 +109,8 @@ class DecodeWorkload:
         return self.decode_bytes() + self.append_bytes() + self.rotary_bytes()
 
     def run_rotary_append(self, capi):
-        capi.split_rotary(self.qkv, self.q_rope_position, self.q, self.k, self.v, 1, self.rope_scale, self.rope_theta)
-        capi.transpose_append(self.pages, self.k, self.v, self.append_position)
+        capi.split_rotary_append(self.qkv, self.q_rope_position, self.append_position, self.q, self.k, self.v,
+                                 self.pages, 1, self.rope_scale, self.rope_theta)
 
     def run_decode(self, capi):
         capi.attention_decode(self.q, self.pages, self.page_indptr, self.page_values, self.length_info,

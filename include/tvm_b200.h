@@ -120,6 +120,19 @@ TVMB200_API int tvmb200_split_rotary(const void* qkv, const int32_t* position_ma
                          float rope_theta, int dtype, tvmb200_stream_t stream);
 
 /*!
+ * \brief f_split_rotary immediately followed by f_transpose_append, in ONE launch (SURVEY 8(f) "next": fused
+ *  rotary + append).  Replaces the back-to-back callback pair of AttentionWithFusedQKV when the append precedes
+ *  the attention (paged_kv_cache.cc:1360 then :1371): q, k, v are written exactly as tvmb200_split_rotary writes
+ *  them and the same k / v registers are scattered to slot append_position_map[t] (page = slot / page_size) of
+ *  `pages` when it is >= 0, so pages, q, k, v are bit-identical to the two-call sequence.
+ */
+TVMB200_API int tvmb200_split_rotary_append(const void* qkv, const int32_t* q_rope_position_map,
+                                const int32_t* append_position_map, void* q, void* k, void* v, void* pages,
+                                int64_t ntoken, int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                int32_t page_size, int32_t head_dim, int32_t rotary_dim, int64_t apply_rope,
+                                float rope_scale, float rope_theta, int dtype, tvmb200_stream_t stream);
+
+/*!
  * \brief f_merge_inplace  (ctor arg 23; _decode_kernels.py:414-526; called paged_kv_cache.cc:2292,2329,1557)
  *  (V,S) <- merge((V,S),(V',S')) with base-2 LSE.  v, v_other: [N,H,D]; s, s_other: [N,H] float32.
  */

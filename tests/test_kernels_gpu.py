@@ -115,6 +115,42 @@ def test_split_rotary(capi, dtype, apply_rope, theta):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("apply_rope", [0, 1])
+def test_split_rotary_append_fused(capi, dtype, apply_rope):
+    """The one-launch f_split_rotary + f_transpose_append must leave q, k, v AND the pages bit-identical to the
+    two-call sequence (and to the oracle's append of the oracle-rotated... of the GPU-rotated k / v), skipped
+    slots (-1) included."""
+    import torch
+
+    rng = np.random.default_rng(4)
+    n, hq, hkv, d, npages = 37, 32, 8, 128, 9
+    qkv = to_dev(rand16(rng, (n, hq + 2 * hkv, d), dtype), dtype)
+    pos = _i32(rng.integers(0, 4096, n).astype(np.int32))
+    slots = rng.permutation(npages * 16)[:n].astype(np.int32)
+    slots[[3, 11]] = -1
+    pages0 = rand16(rng, (npages, 2, hkv, 16, d), dtype)
+    tdt = qkv.dtype
+    outs = []
+    for fused in (False, True):
+        q = torch.empty((n, hq, d), dtype=tdt, device="cuda")
+        k = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+        v = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+        pages = to_dev(pages0, dtype)
+        if fused:
+            capi.split_rotary_append(qkv, pos, _i32(slots), q, k, v, pages, apply_rope, 1.0, 5e5)
+        else:
+            capi.split_rotary(qkv, pos, q, k, v, apply_rope, 1.0, 5e5)
+            capi.transpose_append(pages, k, v, _i32(slots))
+        torch.cuda.synchronize()
+        outs.append((q, k, v, pages))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    want = pages0.copy()
+    ok.transpose_append(want, to_np(outs[1][1]), to_np(outs[1][2]), slots)
+    assert np.array_equal(to_np(outs[1][3]), want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_merge_state_inplace(capi, dtype):
     import torch
 

@@ -56,6 +56,7 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_copy_single_page.argtypes = [P, I64, I64, I64, I64, I32, I32, I32, c_int, P]
     L.tvmb200_compact_kv_copy.argtypes = [P, P, P, I32, I32, I64, I32, I32, I32, c_int, P]
     L.tvmb200_split_rotary.argtypes = [P, P, P, P, P, I64, I32, I32, I32, I32, I64, F, F, c_int, P]
+    L.tvmb200_split_rotary_append.argtypes = [P, P, P, P, P, P, P, I64, I64, I32, I32, I32, I32, I32, I64, F, F, c_int, P]
     L.tvmb200_merge_state_inplace.argtypes = [P, P, P, P, I64, I32, I32, c_int, P]
     L.tvmb200_attention_decode.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
                                            c_int, c_int, F, F, F, c_int, P]
@@ -139,6 +140,15 @@ def split_rotary(qkv, position_map, q, k, v, apply_rope, rope_scale, rope_theta,
     _check(lib().tvmb200_split_rotary(_p(qkv), _p(position_map), _p(q), _p(k), _p(v), qkv.shape[0], q.shape[1],
                                       k.shape[1], qkv.shape[2], rotary_dim, apply_rope, rope_scale, rope_theta,
                                       _dt(qkv), _stream(qkv)))
+
+
+def split_rotary_append(qkv, q_rope_position, append_position, q, k, v, pages, apply_rope, rope_scale, rope_theta,
+                        rotary_dim=0):
+    """f_split_rotary + f_transpose_append in one launch (bit-identical to the two calls)."""
+    P, _, Hkv, page, D = pages.shape
+    _check(lib().tvmb200_split_rotary_append(_p(qkv), _p(q_rope_position), _p(append_position), _p(q), _p(k), _p(v),
+                                             _p(pages), qkv.shape[0], P, q.shape[1], Hkv, page, D, rotary_dim,
+                                             apply_rope, rope_scale, rope_theta, _dt(qkv), _stream(qkv)))
 
 
 def merge_state_inplace(v, s, v_other, s_other):

@@ -149,6 +149,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// ---- programmatic dependent launch (griddepcontrol): no-ops unless the launch carries the attribute --------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // non-suspending poll (try_wait may park the thread for a HW time slice; pollers that watch several barriers use this)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;

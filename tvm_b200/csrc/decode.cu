@@ -94,6 +94,10 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
     for (int i = 0; i < NW * NSTAGE; ++i) mbar_init(bars_base + i * 8, 1);
     mbar_fence_init();
   }
+  // Programmatic dependent launch: when launched with the stream-serialization attribute this grid may start while
+  // the previous kernel of the stream (the fused rotary + append) drains; nothing it produced -- or that it still
+  // reads -- is touched above this line.  Without the attribute the wait returns at once.
+  pdl_wait();
   const int B = p.batch;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int np = p.page_indptr[b + 1] - p.page_indptr[b];
@@ -433,6 +437,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
     }
     __syncthreads();  // scratch (= stage memory) is reused by the next item's TMA
   }
+  pdl_launch_dependents();  // the merge kernel's blocks may be scheduled; they still wait for this grid's completion
 }
 
 // reduce the partial (O, LSE) of sequences that were split into > 1 chunks.  grid = (B, Hq), D threads.
@@ -442,14 +447,37 @@ decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ 
                     const int32_t* __restrict__ chunk_off, T* __restrict__ output,
                     float* __restrict__ lse, int num_qo_heads) {
   const int b = blockIdx.x, hq = blockIdx.y, dd = threadIdx.x;
+  pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
   const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
   if (c1 - c0 <= 1) return;
+  // The kernel is pure latency (a few KiB per block): keep the loads independent -- the chunk LSEs go to shared
+  // memory in one parallel sweep, the partial outputs are read four at a time -- instead of two serial chains.
+  __shared__ float s_lse[D];
+  const int nc = c1 - c0;
+  const bool staged = nc <= D;
+  if (staged) {
+    if (dd < nc) s_lse[dd] = part_lse[static_cast<int64_t>(c0 + dd) * num_qo_heads + hq];
+    __syncthreads();
+  }
+  auto lse_of = [&](int c) { return staged ? s_lse[c] : part_lse[static_cast<int64_t>(c0 + c) * num_qo_heads + hq]; };
   float mm = kNegInit;
-  for (int c = c0; c < c1; ++c) mm = fmaxf(mm, part_lse[static_cast<int64_t>(c) * num_qo_heads + hq]);
+  for (int c = 0; c < nc; ++c) mm = fmaxf(mm, lse_of(c));
+  const float* po = part_o + (static_cast<int64_t>(c0) * num_qo_heads + hq) * D + dd;
+  const int64_t cs = static_cast<int64_t>(num_qo_heads) * D;
   float acc = 0.f, den = 0.f;
-  for (int c = c0; c < c1; ++c) {
-    const float w = exp2f(part_lse[static_cast<int64_t>(c) * num_qo_heads + hq] - mm);
-    acc += w * part_o[(static_cast<int64_t>(c) * num_qo_heads + hq) * D + dd];
+  int c = 0;
+  for (; c + 4 <= nc; c += 4) {
+    const float v0 = po[(c + 0) * cs], v1 = po[(c + 1) * cs], v2 = po[(c + 2) * cs], v3 = po[(c + 3) * cs];
+    const float w0 = exp2f(lse_of(c + 0) - mm), w1 = exp2f(lse_of(c + 1) - mm);
+    const float w2 = exp2f(lse_of(c + 2) - mm), w3 = exp2f(lse_of(c + 3) - mm);
+    acc += w0 * v0; den += w0;
+    acc += w1 * v1; den += w1;
+    acc += w2 * v2; den += w2;
+    acc += w3 * v3; den += w3;
+  }
+  for (; c < nc; ++c) {
+    const float w = exp2f(lse_of(c) - mm);
+    acc += w * po[c * cs];
     den += w;
   }
   output[(static_cast<int64_t>(b) * num_qo_heads + hq) * D + dd] = DT<T>::from_f(acc / den);
@@ -559,11 +587,25 @@ static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, in
                       8 * D * sizeof(T);
   auto kern = decode_kernel<T, D, NW, NSTAGE, ROPE>;
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<grid, NW * 32, smem, st>>>(tmap, p);
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = pdl;
+  cfg.numAttrs = 1;
+  TVMB200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, p));
   TVMB200_LAUNCH_OK();
   if (need_merge) {
-    decode_merge_kernel<T, D><<<dim3(p.batch, p.num_qo_heads), D, 0, st>>>(
-        p.part_o, p.part_lse, p.chunk_off, static_cast<T*>(p.output), p.lse, p.num_qo_heads);
+    cfg.gridDim = dim3(p.batch, p.num_qo_heads);
+    cfg.blockDim = dim3(D);
+    cfg.dynamicSmemBytes = 0;
+    TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_kernel<T, D>, static_cast<const float*>(p.part_o),
+                                    static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
+                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads));
     TVMB200_LAUNCH_OK();
   }
   return 0;

@@ -1011,14 +1011,24 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   // Part 2: split fused qkv (+ RoPE when the mode is "normal")
   const int64_t apply_rope = rope_mode_ == TVMB200_ROPE_NORMAL;
   TRACE("split_rotary", {TF({n, hq + 2 * hkv, d}), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hkv, d}), TF({n, hkv, d}), SI(apply_rope)});
-  if (!plan)
-    Rc(tvmb200_split_rotary(qkv, dev(v_q_rope_pos_), tmp_q_, tmp_k_, tmp_v_, n, hq, hkv, d, 0, apply_rope,
-                            static_cast<float>(rotary_scale_), static_cast<float>(rotary_theta_), dtype_, st));
-  auto append = [&]() {
+  auto trace_append = [&]() {
     TRACE("transpose_append", {TF({num_total_pages_, 2, hkv, ps, d}), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_append_pos_)});
+  };
+  auto append = [&]() {
+    trace_append();
     if (!plan) Rc(tvmb200_transpose_append(pages, tmp_k_, tmp_v_, dev(v_append_pos_), n, num_total_pages_, hkv, ps, d, dtype_, st));
   };
-  if (append_before_attn_) append();
+  if (append_before_attn_) {
+    // the reference's f_split_rotary -> f_transpose_append pair (paged_kv_cache.cc:1360, :1371) as one launch
+    trace_append();
+    if (!plan)
+      Rc(tvmb200_split_rotary_append(qkv, dev(v_q_rope_pos_), dev(v_append_pos_), tmp_q_, tmp_k_, tmp_v_, pages, n,
+                                     num_total_pages_, hq, hkv, ps, d, 0, apply_rope, static_cast<float>(rotary_scale_),
+                                     static_cast<float>(rotary_theta_), dtype_, st));
+  } else if (!plan) {
+    Rc(tvmb200_split_rotary(qkv, dev(v_q_rope_pos_), tmp_q_, tmp_k_, tmp_v_, n, hq, hkv, d, 0, apply_rope,
+                            static_cast<float>(rotary_scale_), static_cast<float>(rotary_theta_), dtype_, st));
+  }
 
   // Part 5: attention
   bool is_first = true;

@@ -107,13 +107,18 @@ compact_kv_copy_kernel(uint4* __restrict__ pages, const int32_t* __restrict__ in
 // computed ONCE into shared memory (the reference recomputes powf/cosf/sinf per element), then
 // every (head, 8-element vector pair) is rotated with 128-bit loads/stores.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// APPEND = true additionally scatters the (rotated) k and v rows of token t into the paged cache at slot
+// append_pos[t] (>= 0), i.e. f_split_rotary followed by f_transpose_append in one launch; the values written to
+// the pages are the very registers written to k / v, so the result is bit-identical to the two-kernel sequence.
+template <typename T, bool APPEND>
 __global__ void __launch_bounds__(256)
 split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ position_map,
                     uint4* __restrict__ q, uint4* __restrict__ k, uint4* __restrict__ v,
                     int num_qo_heads, int num_kv_heads, int head_dim, int rotary_dim,
-                    int apply_rope, float rope_scale, float rope_theta) {
+                    int apply_rope, float rope_scale, float rope_theta, uint4* __restrict__ pages,
+                    const int32_t* __restrict__ append_pos, int page_size) {
   extern __shared__ float2 cs[];  // [rotary_dim/2] (cos, sin)
+  pdl_launch_dependents();  // a dependent launched programmatically (the decode kernel) may start its prologue now
   const int64_t t = blockIdx.x;
   const int row_vecs = head_dim / 8;
   const int half_vecs = rotary_dim / 16;  // vectors in one rotary half
@@ -134,12 +139,20 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
     const int h = w / row_vecs;
     const int j = w - h * row_vecs;
     uint4* dst;
+    uint4* dst_page = nullptr;
     if (h < num_qo_heads) {
       dst = q + (t * num_qo_heads + h) * row_vecs + j;
-    } else if (h < num_qo_heads + num_kv_heads) {
-      dst = k + (t * num_kv_heads + (h - num_qo_heads)) * row_vecs + j;
     } else {
-      dst = v + (t * num_kv_heads + (h - num_qo_heads - num_kv_heads)) * row_vecs + j;
+      const int is_v = h >= num_qo_heads + num_kv_heads;
+      const int hh = h - num_qo_heads - is_v * num_kv_heads;
+      dst = (is_v ? v : k) + (t * num_kv_heads + hh) * row_vecs + j;
+      if (APPEND) {
+        const int32_t slot = append_pos[t];
+        if (slot >= 0) {
+          const int64_t pg = slot / page_size, off = slot - pg * page_size;
+          dst_page = pages + (((pg * 2 + is_v) * num_kv_heads + hh) * page_size + off) * row_vecs + j;
+        }
+      }
     }
     uint4 x = ldg_nc_v4(src + w);
     const bool rot = apply_rope > 0 && h < num_qo_heads + num_kv_heads && j < 2 * half_vecs;
@@ -161,6 +174,7 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
       x = o;
     }
     *dst = x;
+    if (APPEND && dst_page != nullptr) *dst_page = x;
   }
 }
 
@@ -292,13 +306,45 @@ extern "C" int tvmb200_split_rotary(const void* qkv, const int32_t* position_map
   const int apply = apply_rope > 0 ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == TVMB200_F16) {
-    split_rotary_kernel<__half><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+    split_rotary_kernel<__half, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
-        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta);
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
+        nullptr, nullptr, 16);
   } else {
-    split_rotary_kernel<__nv_bfloat16><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+    split_rotary_kernel<__nv_bfloat16, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
-        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta);
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
+        nullptr, nullptr, 16);
+  }
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int tvmb200_split_rotary_append(const void* qkv, const int32_t* q_rope_position_map,
+                                           const int32_t* append_position_map, void* q, void* k, void* v,
+                                           void* pages, int64_t ntoken, int64_t num_pages, int32_t num_qo_heads,
+                                           int32_t num_kv_heads, int32_t page_size, int32_t head_dim,
+                                           int32_t rotary_dim, int64_t apply_rope, float rope_scale,
+                                           float rope_theta, int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "split_rotary_append: unsupported dtype %d", dtype);
+  if (rotary_dim <= 0) rotary_dim = head_dim;
+  TVMB200_CHECK(head_dim % 8 == 0 && rotary_dim % 16 == 0 && rotary_dim <= head_dim,
+                "split_rotary_append: head_dim %d / rotary_dim %d unsupported (need D %% 8 == 0, rd %% 16 == 0)", head_dim, rotary_dim);
+  TVMB200_CHECK(page_size > 0 && num_pages >= 0, "split_rotary_append: bad page geometry (%d slots, %ld pages)", page_size, (long)num_pages);
+  if (ntoken == 0) return 0;
+  const size_t smem = static_cast<size_t>(rotary_dim / 2) * sizeof(float2);
+  const int apply = apply_rope > 0 ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TVMB200_F16) {
+    split_rotary_kernel<__half, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), q_rope_position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
+        static_cast<uint4*>(pages), append_position_map, page_size);
+  } else {
+    split_rotary_kernel<__nv_bfloat16, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), q_rope_position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
+        static_cast<uint4*>(pages), append_position_map, page_size);
   }
   TVMB200_LAUNCH_OK();
   return 0;
