@@ -33,6 +33,7 @@
 #include "prefill.cuh"
 #include "tc05.cuh"
 
+#include <mutex>
 #include <type_traits>
 
 namespace tvmb200 {
@@ -70,19 +71,22 @@ constexpr int kPolyPairsOf = std::is_same<PT, __nv_bfloat16>::value ? 2 : 4;
 struct SmemLayout {
   static constexpr int q = 0;
   static constexpr int kv = q + 2 * kTileBytes;
-  static constexpr int bars = kv + kSlots * kTileBytes;
-  static constexpr int tmem_ptr = bars + 192;
-  static constexpr int lo_flag = bars + 208;  // int[2][2]: P of (tile t, S buffer h) has a P_lo part
-  static constexpr int xch = bars + 256;        // float[2 parities][2 warpgroups][128 rows]: row max / row sum exchange
-  static constexpr int scan = xch + 2 * 2 * kRows * 4;
+  static constexpr int bars = kv + kSlots * kTileBytes;   // 26 mbarriers
+  static constexpr int tmem_ptr = bars + 224;
+  static constexpr int lo_flag = bars + 232;  // int[2][2]: id of the step whose P of (tile t, S half h) has a P_lo part
+  static constexpr int item = bars + 248;     // int[2]: work-item ring filled by the producer warp
+  static constexpr int scan = bars + 256;
 };
-// S_FULL / P_READY / PV_DONE: one barrier per (tile, S buffer) = index 2 t + h.  A waiter may only ever be one phase
-// behind its barrier (parity waits alias after two); with QK(s+2) queued behind PV(s) the softmax can finish step s
-// while PV(s-1) is still running, so PV_DONE must be per buffer as well.
-enum Bar { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, NUM_BARS = 21 };
+// S_FULL / P_READY / PV_DONE: one barrier per (tile, S half) = index 2 t + h.  The kernel is persistent, so every
+// barrier is used across work items: each role keeps running use counts and waits for parity (count & 1).
+enum Bar {
+  Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, Q_EMPTY = 21, ITEM_FULL = 22,
+  ITEM_EMPTY = 24, NUM_BARS = 26
+};
 
 #ifdef TVMB200_TRACE
-// tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot]
+// tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot];
+// with the persistent kernel the stamps are those of the LAST work item CTA number TVMB200_TRACE processed
 __device__ long long g_trace[3][64][8];
 #define TRACE(role, step, slot)                                                             \
   do {                                                                                      \
@@ -93,22 +97,72 @@ __device__ long long g_trace[3][64][8];
 #define TRACE(role, step, slot)
 #endif
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 template <typename PT>
 __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
   return DT<PT>::pack(lo, hi);
 }
 
+// one work item = 256 GQA-folded query rows of one sequence x one KV head
+struct Item {
+  int h, q_beg, qo_len, row0, tok0, nqt, kv_len, kv_beg, pg_beg, n_pages, ns0, ns1, n_kv;
+};
+
+template <bool PAGED>
+__device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s_tiles, int id, int n_items) {
+  Item it;
+  const int B = p.batch, g = p.group;
+  const int ritem = n_items - 1 - id;  // late (= long-KV under a causal mask) tiles first
+  const int tg = ritem / p.num_kv_heads;
+  it.h = ritem - tg * p.num_kv_heads;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_tiles[mid] <= tg) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int pair = tg - s_tiles[b];
+  it.q_beg = p.q_indptr[b];
+  it.qo_len = p.q_indptr[b + 1] - it.q_beg;
+  it.row0 = pair * 2 * kRows;            // first folded row of the item
+  it.tok0 = it.row0 / g;                 // first query token (relative to the sequence)
+  const int tok_per_tile = kRows / g;
+  it.nqt = (it.qo_len * g - it.row0 > kRows) ? 2 : 1;  // second tile entirely outside the sequence?
+  it.kv_beg = 0;
+  it.pg_beg = 0;
+  it.n_pages = 0;
+  if (PAGED) {
+    it.pg_beg = p.page_indptr[b];
+    it.n_pages = p.page_indptr[b + 1] - it.pg_beg;
+    it.kv_len = it.n_pages > 0 ? (it.n_pages - 1) * 16 + p.length_info[b] : 0;
+  } else {
+    it.kv_beg = p.kv_indptr[b];
+    it.kv_len = p.kv_indptr[b + 1] - it.kv_beg;
+  }
+  const bool causal = p.mask_mode == kMaskCausal;
+  // visible KV extent of each tile's last valid token bounds that tile's step count
+  auto steps_of = [&](int t) {
+    const int tok_last = min(it.qo_len, it.tok0 + (t + 1) * tok_per_tile) - 1;
+    const int kv_end = causal ? max(0, min(it.kv_len, it.kv_len - it.qo_len + tok_last + 1)) : it.kv_len;
+    return (t < it.nqt) ? (kv_end + kStep - 1) / kStep : 0;
+  };
+  it.ns0 = steps_of(0);
+  it.ns1 = steps_of(1);
+  it.n_kv = (max(it.ns0, it.ns1) + 1) >> 1;  // 128-row K / V tiles to load
+  return it;
+}
+
 }  // namespace
 
+// Persistent: one CTA per SM walks a device-wide work queue (an atomic counter; long items first).  The producer warp
+// fetches the next item id and publishes it through a two-entry shared-memory ring, so the next item's Q and first
+// K / V tiles are in flight -- and its first QK^T issued -- while the softmax warpgroups still normalise and store the
+// previous item's O: TMEM allocation, barrier setup, the Q load from HBM and the O store no longer sit between two
+// tiles' tensor work (they cost ~12 % with one CTA per tile).
 template <typename T, typename PT, bool PAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p, const uint32_t idesc_qk,
-                    const uint32_t idesc_pv) {
+                    const uint32_t idesc_pv, int* __restrict__ work_counter) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -117,9 +171,10 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   constexpr bool kLoPass = std::is_same<PT, __nv_bfloat16>::value;
   int* s_tiles = reinterpret_cast<int*>(sgen + SmemLayout::scan);
   int* s_tmp = s_tiles + B + 1;
+  volatile int* s_item = reinterpret_cast<volatile int*>(sgen + SmemLayout::item);
   auto bar = [&](int i) -> uint32_t { return sbase + SmemLayout::bars + i * 8; };
 
-  // ---- which (sequence, 256-row tile pair, kv head) is this CTA? --------------------------------------------
+  // ---- work enumeration: 256-row tile pairs per sequence ---------------------------------------------------------
   for (int b = tid; b < B; b += kThreads) {
     const int rows = (p.q_indptr[b + 1] - p.q_indptr[b]) * g;
     s_tiles[b] = (rows + 2 * kRows - 1) / (2 * kRows);
@@ -127,44 +182,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   __syncthreads();
   block_exclusive_scan(s_tiles, B, s_tmp);
   const int n_items = s_tiles[B] * p.num_kv_heads;
-  if (static_cast<int>(blockIdx.x) >= n_items) return;
-  const int ritem = n_items - 1 - blockIdx.x;  // late (= long-KV under a causal mask) tiles first
-  const int tg = ritem / p.num_kv_heads;
-  const int h = ritem - tg * p.num_kv_heads;
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (s_tiles[mid] <= tg) lo = mid; else hi = mid;
-  }
-  const int b = lo;
-  const int pair = tg - s_tiles[b];
-  const int q_beg = p.q_indptr[b];
-  const int qo_len = p.q_indptr[b + 1] - q_beg;
-  const int row0 = pair * 2 * kRows;            // first folded row of the CTA
-  const int tok0 = row0 / g;                    // first query token (relative to the sequence)
-  const int tok_per_tile = kRows / g;
-  const int nqt = (qo_len * g - row0 > kRows) ? 2 : 1;  // second tile entirely outside the sequence?
-
-  int kv_len, kv_beg = 0, pg_beg = 0, n_pages = 0;
-  if (PAGED) {
-    pg_beg = p.page_indptr[b];
-    n_pages = p.page_indptr[b + 1] - pg_beg;
-    kv_len = n_pages > 0 ? (n_pages - 1) * 16 + p.length_info[b] : 0;
-  } else {
-    kv_beg = p.kv_indptr[b];
-    kv_len = p.kv_indptr[b + 1] - kv_beg;
-  }
   const bool causal = p.mask_mode == kMaskCausal;
-  // visible KV extent of each tile's last valid token bounds that tile's step count
-  auto steps_of = [&](int t) {
-    const int tok_last = min(qo_len, tok0 + (t + 1) * tok_per_tile) - 1;
-    const int kv_end = causal ? max(0, min(kv_len, kv_len - qo_len + tok_last + 1)) : kv_len;
-    return (t < nqt) ? (kv_end + kStep - 1) / kStep : 0;
-  };
-  const int ns0 = steps_of(0), ns1 = steps_of(1);
-  auto ns = [&](int t) { return t ? ns1 : ns0; };
-  const int max_ns = max(ns0, ns1);
-  const int n_kv = (max_ns + 1) >> 1;  // 128-row K / V tiles to load
+  const int tok_per_tile = kRows / g;
 
   // ---- one-time setup ------------------------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -172,6 +191,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_k);
     if (!PAGED) tma_prefetch_desc(&tm_v);
     mbar_init(bar(Q_FULL), 1);
+    mbar_init(bar(Q_EMPTY), 1);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(bar(KV_FULL + i), 1);
       mbar_init(bar(KV_EMPTY + i), 1);
@@ -182,6 +202,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_init(bar(P_READY + 2 * t + h), kRows);
         mbar_init(bar(PV_DONE + 2 * t + h), 1);
       }
+      mbar_init(bar(ITEM_FULL + t), 1);
+      mbar_init(bar(ITEM_EMPTY + t), 9);  // the MMA warp + the eight softmax warps
     }
     for (int i = 0; i < 4; ++i) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * i) = 0;
     mbar_fence_init();
@@ -199,25 +221,42 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp < 4) {
     tc05::setmaxnreg_dec<64>();
     if (warp == 0) {
-      // =========================== TMA producer ===========================
-      if (n_kv > 0) {
+      // =========================== TMA producer + work fetch ===========================
+      uint32_t fill = 0;   // K / V tiles loaded so far (all items): ring slot = fill & 3
+      uint32_t n_q = 0;    // Q loads so far
+      for (int k = 0;; ++k) {
+        const int islot = k & 1;
+        int id = 0;
         if (lane == 0) {
-          mbar_expect_tx(bar(Q_FULL), nqt * kTileBytes);
-          for (int t = 0; t < nqt; ++t)
-            for (int hf = 0; hf < 2; ++hf)
-              tc05::tma_load_3d(sq + t * kTileBytes + hf * kHalfBytes, &tm_q, hf * 64, h * g,
-                                q_beg + tok0 + t * tok_per_tile, bar(Q_FULL), kEvictFirst);
+          mbar_wait(bar(ITEM_EMPTY + islot), ((k >> 1) & 1) ^ 1);
+          id = atomicAdd(work_counter, 1);
+          if (id == n_items + static_cast<int>(gridDim.x) - 1) *work_counter = 0;  // the very last fetch of the launch
+          s_item[islot] = id;
+          mbar_arrive(bar(ITEM_FULL + islot));
         }
-        for (int f = 0; f < 2 * n_kv; ++f) {
-          const int j = f >> 1, is_v = f & 1, slot = f & (kSlots - 1);
-          mbar_wait(bar(KV_EMPTY + slot), ((f / kSlots) & 1) ^ 1);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= n_items) break;
+        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        if (it.n_kv == 0) continue;
+        if (lane == 0) {
+          mbar_wait(bar(Q_EMPTY), (n_q & 1) ^ 1);  // every QK^T of the previous item has read Q
+          mbar_expect_tx(bar(Q_FULL), it.nqt * kTileBytes);
+          for (int t = 0; t < it.nqt; ++t)
+            for (int hf = 0; hf < 2; ++hf)
+              tc05::tma_load_3d(sq + t * kTileBytes + hf * kHalfBytes, &tm_q, hf * 64, it.h * g,
+                                it.q_beg + it.tok0 + t * tok_per_tile, bar(Q_FULL), kEvictFirst);
+        }
+        ++n_q;
+        for (int fl = 0; fl < 2 * it.n_kv; ++fl, ++fill) {
+          const int j = fl >> 1, is_v = fl & 1, slot = fill & (kSlots - 1);
+          mbar_wait(bar(KV_EMPTY + slot), ((fill / kSlots) & 1) ^ 1);
           const uint32_t dst = skv + slot * kTileBytes;
           if (!PAGED) {
             if (lane == 0) {
               mbar_expect_tx(bar(KV_FULL + slot), kTileBytes);
               const CUtensorMap* tm = is_v ? &tm_v : &tm_k;
               for (int hf = 0; hf < 2; ++hf)
-                tc05::tma_load_3d(dst + hf * kHalfBytes, tm, hf * 64, h, kv_beg + j * kKV, bar(KV_FULL + slot),
+                tc05::tma_load_3d(dst + hf * kHalfBytes, tm, hf * 64, it.h, it.kv_beg + j * kKV, bar(KV_FULL + slot),
                                   kEvictLast);
             }
           } else {
@@ -225,9 +264,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             __syncwarp();
             if (lane < 16) {
               const int i = lane >> 1, hf = lane & 1;
-              const int pi = min(j * 8 + i, n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
-              const int pid = __ldg(p.page_values + pg_beg + pi);
-              const int row = ((pid * 2 + is_v) * p.num_kv_heads + h) * 16;
+              const int pi = min(j * 8 + i, it.n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
+              const int pid = __ldg(p.page_values + it.pg_beg + pi);
+              const int row = ((pid * 2 + is_v) * p.num_kv_heads + it.h) * 16;
               tma_load_2d(dst + hf * kHalfBytes + i * 16 * 128, &tm_k, hf * 64, row, bar(KV_FULL + slot), kEvictLast);
             }
           }
@@ -235,70 +274,83 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     } else if (warp == 1) {
       // =========================== MMA issuer ===========================
-      if (max_ns > 0) {
-        // descriptors: high words are constant per operand kind, low words = (address >> 4) | LBO field
-        const uint64_t dkm = tc05::make_smem_desc(0, 16, 1024);          // K-major operands (Q, K)
-        const uint64_t dmn = tc05::make_smem_desc(0, kHalfBytes, 1024);  // MN-major operand (V)
-        const uint32_t kmaj_hi = static_cast<uint32_t>(dkm >> 32), kmaj_lo = static_cast<uint32_t>(dkm);
-        const uint32_t mnmaj_hi = static_cast<uint32_t>(dmn >> 32), mnmaj_lo = static_cast<uint32_t>(dmn);
-        const uint32_t q_lo = kmaj_lo + (sq >> 4), k_lo = kmaj_lo + (skv >> 4), v_lo = mnmaj_lo + (skv >> 4);
-        // S_t[0:128) = Q_t x (K tile in `kslot`)^T, one N = 128 MMA per 16-wide slice of the head dim
-        auto issue_qk = [&](int t, uint32_t kslot) {
-          const uint32_t a0 = q_lo + ((t * kTileBytes) >> 4);
-          const uint32_t b0 = k_lo + ((kslot * kTileBytes) >> 4);
-          const uint32_t d = tmem + t * 128;
+      // descriptors: high words are constant per operand kind, low words = (address >> 4) | LBO field
+      const uint64_t dkm = tc05::make_smem_desc(0, 16, 1024);          // K-major operands (Q, K)
+      const uint64_t dmn = tc05::make_smem_desc(0, kHalfBytes, 1024);  // MN-major operand (V)
+      const uint32_t kmaj_hi = static_cast<uint32_t>(dkm >> 32), kmaj_lo = static_cast<uint32_t>(dkm);
+      const uint32_t mnmaj_hi = static_cast<uint32_t>(dmn >> 32), mnmaj_lo = static_cast<uint32_t>(dmn);
+      const uint32_t q_lo = kmaj_lo + (sq >> 4), k_lo = kmaj_lo + (skv >> 4), v_lo = mnmaj_lo + (skv >> 4);
+      // S_t[0:128) = Q_t x (K tile in `kslot`)^T, one N = 128 MMA per 16-wide slice of the head dim
+      auto issue_qk = [&](int t, uint32_t kslot) {
+        const uint32_t a0 = q_lo + ((t * kTileBytes) >> 4);
+        const uint32_t b0 = k_lo + ((kslot * kTileBytes) >> 4);
+        const uint32_t d = tmem + t * 128;
 #pragma unroll
-          for (int s = 0; s < kD / 16; ++s) {
-            const uint32_t off = ((s >> 2) * kHalfBytes + (s & 3) * 32) >> 4;
-            tc05::mma_ss_w(d, a0 + off, kmaj_hi, b0 + off, kmaj_hi, idesc_qk, s > 0);
-          }
-        };
-        auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc, bool with_lo) {
-          const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
-          const uint32_t p0 = tmem + t * 128 + half * kStep;
-          const uint32_t d = tmem + 256 + t * 128;
-          // second trip = the P_lo residual pass.  A real loop on purpose: ptxas predicates an `if (with_lo)` body,
-          // and a predicated-off UTCHMMA still costs the issuing thread a full MMA slot (measured: +300 clk per group)
-          const int passes = with_lo ? 2 : 1;
+        for (int s = 0; s < kD / 16; ++s) {
+          const uint32_t off = ((s >> 2) * kHalfBytes + (s & 3) * 32) >> 4;
+          tc05::mma_ss_w(d, a0 + off, kmaj_hi, b0 + off, kmaj_hi, idesc_qk, s > 0);
+        }
+      };
+      auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc, bool with_lo) {
+        const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
+        const uint32_t p0 = tmem + t * 128 + half * kStep;
+        const uint32_t d = tmem + 256 + t * 128;
+        // second trip = the P_lo residual pass.  A real loop on purpose: ptxas predicates an `if (with_lo)` body,
+        // and a predicated-off UTCHMMA still costs the issuing thread a full MMA slot (measured: +300 clk per group)
+        const int passes = with_lo ? 2 : 1;
 #pragma unroll 1
-          for (int ps = 0; ps < passes; ++ps) {
+        for (int ps = 0; ps < passes; ++ps) {
 #pragma unroll
-            for (int s = 0; s < kStep / 16; ++s) {
-              // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
-              tc05::mma_ts_w(d, p0 + ps * 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv,
-                             (acc || s > 0 || ps > 0) ? 1u : 0u);
-            }
+          for (int s = 0; s < kStep / 16; ++s) {
+            // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
+            tc05::mma_ts_w(d, p0 + ps * 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv,
+                           (acc || s > 0 || ps > 0) ? 1u : 0u);
           }
-        };
-        mbar_wait(bar(Q_FULL), 0);
-        mbar_wait(bar(KV_FULL + 0), 0);  // K_0
+        }
+      };
+      uint32_t fill = 0, n_q = 0;
+      uint32_t n_p[2][2] = {{0, 0}, {0, 0}};  // real (tile, half) steps issued so far = completions of P_READY waited
+      for (int k = 0;; ++k) {
+        const int islot = k & 1;
+        mbar_wait(bar(ITEM_FULL + islot), (k >> 1) & 1);
+        const int id = s_item[islot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
+        if (id >= n_items) break;
+        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        const int n_kv = it.n_kv;
+        if (n_kv == 0) continue;
+        auto ns = [&](int t) { return t ? it.ns1 : it.ns0; };
+        mbar_wait(bar(Q_FULL), n_q & 1);
+        ++n_q;
+        mbar_wait(bar(KV_FULL + (fill & (kSlots - 1))), (fill / kSlots) & 1);  // K_0
         tc05::fence_after_sync();
         if (tc05::elect_one()) {
           for (int t = 0; t < 2; ++t)
             if (ns(t) > 0) {
-              issue_qk(t, 0);
+              issue_qk(t, fill & (kSlots - 1));
               tc05::commit(bar(S_FULL + 2 * t));
               tc05::commit(bar(S_FULL + 2 * t + 1));
             }
-          tc05::commit(bar(KV_EMPTY + 0));
+          tc05::commit(bar(KV_EMPTY + (fill & (kSlots - 1))));
+          if (n_kv == 1) tc05::commit(bar(Q_EMPTY));  // no further QK^T in this item
         }
         __syncwarp();
-        // The softmax warpgroups walk (KV tile j, Q tile t) in j-major order, both on the same Q tile at a time,
-        // so P arrives in a fixed order: (t0, lower half), (t0, upper half), (t1, lower), (t1, upper), next j.
-        // Behind the upper half of a tile go its QK for KV tile j+1, i.e. one Q tile's PV + QK occupy the tensor
-        // pipe exactly while both warpgroups run the other Q tile's softmax.
+        // The softmax warpgroups hand P over in a fixed order: (t0, lower half), (t0, upper half), (t1, lower),
+        // (t1, upper), next KV tile.  Behind the upper half of a tile goes its QK for KV tile j+1, i.e. one Q tile's
+        // PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
         for (int j = 0; j < n_kv; ++j) {
-          const int fv = 2 * j + 1, fk1 = 2 * j + 2;
+          const uint32_t fv = fill + 2 * j + 1, fk1 = fill + 2 * j + 2;
           const int vslot = fv & (kSlots - 1), k1slot = fk1 & (kSlots - 1);
           const bool more_k = j + 1 < n_kv;
           mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
           if (PAGED && j == n_kv - 1) {
             // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
             // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-            const int valid = kv_len - j * kKV;
+            const int valid = it.kv_len - j * kKV;
             if (valid < kKV) {
-              for (int it = lane; it < (kKV - valid) * 16; it += 32) {
-                const int r = valid + (it >> 4), c = it & 15;
+              for (int e = lane; e < (kKV - valid) * 16; e += 32) {
+                const int r = valid + (e >> 4), c = e & 15;
                 const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
                 asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
               }
@@ -313,14 +365,14 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             for (int h = 0; h < 2; ++h) {
               const int s = 2 * j + h;
               if (s >= nst) break;
-              mbar_wait(bar(P_READY + 2 * t + h), j & 1);
+              mbar_wait(bar(P_READY + 2 * t + h), n_p[t][h] & 1);
+              ++n_p[t][h];
               TRACE(0, s, 3 * t + 1);
               tc05::fence_after_sync();
+              // the P_lo stamp of this (tile, half) use: the softmax warps count their steps the same way
+              const int lo_id = static_cast<int>(n_p[t][h]);
               const bool with_lo =
-                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) == s + 1;
-#ifdef TVMB200_TRACE
-              if (blockIdx.x == TVMB200_TRACE && lane == 0 && s < 64) g_trace[0][s][3 * t] = with_lo ? 1 : 0;
-#endif
+                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) == lo_id;
               const bool last_of_tile = h == 1 || s == nst - 1;
               if (tc05::elect_one()) {
                 issue_pv(t, vslot, h, s > 0, with_lo);
@@ -338,9 +390,11 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (tc05::elect_one()) {
             tc05::commit(bar(KV_EMPTY + vslot));
             if (more_k) tc05::commit(bar(KV_EMPTY + k1slot));
+            if (j + 2 == n_kv) tc05::commit(bar(Q_EMPTY));  // the item's last QK^T (of KV tile n_kv-1) is issued
           }
           __syncwarp();
         }
+        fill += 2 * n_kv;
       }
     }
   } else {
@@ -349,25 +403,38 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int t = (warp - 4) >> 2;          // which Q tile
     const int wq = warp & 3;                // TMEM lane quarter of this warp
     const int r = wq * 32 + lane;           // row within the tile
-    const int R = row0 + t * kRows + r;     // folded row within the sequence
-    const int tok = R / g;
-    const bool valid = t < nqt && tok < qo_len;
-    const int limit = causal ? max(0, min(kv_len, kv_len - qo_len + tok + 1)) : kv_len;  // visible columns [0, limit)
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t t_s = tmem + lane_addr + t * 128;
     const uint32_t t_o = tmem + lane_addr + 256 + t * 128;
-    float m_used = kNegInit, l = 0.f;
     const float sc = p.scale_log2;
-
-    const int my_ns = ns(t);
-    if (t < nqt) {
+    uint32_t n_s = 0;             // KV tiles (= QK^T results) of my Q tile consumed so far, all items
+    uint32_t n_p[2] = {0, 0};     // my steps so far per S half = my arrivals on P_READY(t, half)
+    for (int k = 0;; ++k) {
+      const int islot = k & 1;
+      mbar_wait(bar(ITEM_FULL + islot), (k >> 1) & 1);
+      const int id = s_item[islot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
+      if (id >= n_items) break;
+      const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+      const int h = it.h, q_beg = it.q_beg, qo_len = it.qo_len, kv_len = it.kv_len, nqt = it.nqt;
+      const int R = it.row0 + t * kRows + r;     // folded row within the sequence
+      const int tok = R / g;
+      const bool valid = t < nqt && tok < qo_len;
+      const int limit = causal ? max(0, min(kv_len, kv_len - qo_len + tok + 1)) : kv_len;  // visible columns [0, limit)
+      float m_used = kNegInit, l = 0.f;
+      const int my_ns = t ? it.ns1 : it.ns0;
+      if (t >= nqt) continue;
       for (int s = 0; s < my_ns; ++s) {
-        const int hb = s & 1;                       // S buffer of this step
+        const int hb = s & 1;                       // S half of this step
         const uint32_t t_sb = t_s + hb * kStep;
         if (wq == 0) TRACE(1 + t, s, 0);
-        mbar_wait(bar(S_FULL + 2 * t + hb), (s >> 1) & 1);
+        mbar_wait(bar(S_FULL + 2 * t + hb), n_s & 1);
+        if (hb == 1 || s == my_ns - 1) ++n_s;       // this KV tile's S is consumed with this step
         if (wq == 0) TRACE(1 + t, s, 1);
         tc05::fence_after_sync();
+        ++n_p[hb];
+        const int lo_id = static_cast<int>(n_p[hb]);
         uint32_t s0[32], s1[32];
         tc05::ld32(t_sb + 0, s0);
         tc05::ld32(t_sb + 32, s1);
@@ -403,7 +470,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             l *= alpha;
           }
           if (s > 0) {
-            mbar_wait(bar(PV_DONE + 2 * t + ((s - 1) & 1)), ((s - 1) >> 1) & 1);  // O_t must be complete before it is rescaled
+            mbar_wait(bar(PV_DONE + 2 * t + ((s - 1) & 1)), (n_p[(s - 1) & 1] - 1) & 1);  // O_t must be complete before it is rescaled
             tc05::fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -467,7 +534,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             };
             lo_pack(s0, 0);
             lo_pack(s1, 1);
-            if (lane == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = s + 1;
+            if (lane == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = lo_id;
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c) pk[c] = 0u;
@@ -488,7 +555,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         p.lse[static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq] = l > 0.f ? m_used + log2f(l) : kNegInit;
       }
       if (my_ns > 0) {
-        mbar_wait(bar(PV_DONE + 2 * t + ((my_ns - 1) & 1)), ((my_ns - 1) >> 1) & 1);
+        const int hl = (my_ns - 1) & 1;
+        mbar_wait(bar(PV_DONE + 2 * t + hl), (n_p[hl] - 1) & 1);
         tc05::fence_after_sync();
         const float inv = l > 0.f ? 1.0f / l : 0.f;
 #pragma unroll
@@ -508,6 +576,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
           }
         }
+        // O_t is free for the next item's first PV: that PV waits for this warpgroup's next P_READY, which these
+        // very threads only signal after the loads above
+        tc05::fence_before_sync();
       } else if (valid) {
         // no visible KV at all: O = 0, LSE = -5e4 (the reference's empty result)
 #pragma unroll
@@ -543,11 +614,28 @@ bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head
   return static_cast<int64_t>(total_q_len) * g >= 2048;
 }
 
+// device-wide work counter of the persistent kernel (one int per device; the kernel leaves it at zero)
+static int get_work_counter(int** out) {
+  static int* counters[64];
+  static std::mutex mu;
+  int dev = 0;
+  TVMB200_CUDA(cudaGetDevice(&dev));
+  TVMB200_CHECK(dev >= 0 && dev < 64, "device id %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!counters[dev]) {
+    TVMB200_CUDA(cudaMalloc(&counters[dev], 256));
+    TVMB200_CUDA(cudaMemset(counters[dev], 0, 256));
+  }
+  *out = counters[dev];
+  return 0;
+}
+
 template <typename T, typename PT, bool PAGED>
 static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          int total_q_len, cudaStream_t st) {
   const int64_t max_pairs = (static_cast<int64_t>(total_q_len) * p.group + 2 * kRows - 1) / (2 * kRows) + p.batch;
-  const int64_t grid = max_pairs * p.num_kv_heads;
+  const int64_t max_items = max_pairs * p.num_kv_heads;
+  const int grid = static_cast<int>(max_items < num_sms() ? max_items : num_sms());  // persistent: one CTA per SM
   const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
   auto kern = prefill_tc05_kernel<T, PT, PAGED>;
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -555,7 +643,11 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
   const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
   const uint32_t idesc_pv = tc05::make_idesc(fp, fa, 0, 1, kRows, kD);
-  kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv);
+  int* counter = nullptr;
+  if (int rc = get_work_counter(&counter)) return rc;
+  // the kernel resets the counter with its last fetch; the memset only matters after an aborted launch
+  TVMB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv, counter);
   TVMB200_LAUNCH_OK();
   return 0;
 }
