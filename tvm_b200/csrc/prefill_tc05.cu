@@ -86,11 +86,11 @@ enum Bar {
 
 #ifdef TVMB200_TRACE
 // tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot];
-// with the persistent kernel the stamps are those of the LAST work item CTA number TVMB200_TRACE processed
+// the stamps are those of work item number TVMB200_TRACE (whichever CTA fetched it)
 __device__ long long g_trace[3][64][8];
 #define TRACE(role, step, slot)                                                             \
   do {                                                                                      \
-    if (blockIdx.x == TVMB200_TRACE && (threadIdx.x & 31) == 0 && (step) < 64)              \
+    if (trace_item == TVMB200_TRACE && (threadIdx.x & 31) == 0 && (step) < 64)              \
       g_trace[role][step][slot] = clock64();                                                \
   } while (0)
 #else
@@ -317,6 +317,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
         if (id >= n_items) break;
+        const int trace_item = id;
+        (void)trace_item;
         const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
         const int n_kv = it.n_kv;
         if (n_kv == 0) continue;
@@ -416,6 +418,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
       if (id >= n_items) break;
+      const int trace_item = id;
+      (void)trace_item;
       const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
       const int h = it.h, q_beg = it.q_beg, qo_len = it.qo_len, kv_len = it.kv_len, nqt = it.nqt;
       const int R = it.row0 + t * kRows + r;     // folded row within the sequence
