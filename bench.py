@@ -112,6 +112,12 @@ class DecodeWorkload:
         capi.split_rotary_append(self.qkv, self.q_rope_position, self.append_position, self.q, self.k, self.v,
                                  self.pages, 1, self.rope_scale, self.rope_theta)
 
+    def run_decode_gather(self, capi, gather):
+        """decode of this rank's KV-head shard; the kernel stores its heads into every rank's gathered buffer"""
+        return gather.decode(capi, self.q, self.pages, self.page_indptr, self.page_values, self.length_info,
+                             self.k_rope_pos_offset, self.q_rope_position, self.o, self.lse, 0, self.rope_scale,
+                             self.rope_theta, self.sm_scale)
+
     def run_decode(self, capi):
         capi.attention_decode(self.q, self.pages, self.page_indptr, self.page_values, self.length_info,
                               self.k_rope_pos_offset, self.q_rope_position, self.o, self.lse, 0, self.rope_scale,
@@ -245,17 +251,16 @@ def run_own(args):
         return run_c4(args, capi, rank, world, dev, peaks, peak_src)
     w = DecodeWorkload(seed=rank, device=dev)
     dist = None
-    gathered = None
     if world > 1:
         import torch.distributed as dist  # noqa: F811
 
-        gathered = torch.empty((world * w.B, w.Hq, w.D), device=dev, dtype=torch.bfloat16)
-
+    # Batch split (weak scaling): every rank owns 64 whole sequences -- page table, KV pages, queries and outputs -- so
+    # the path has NO exchange step (a sequence's attention output feeds that rank's own next layer); NCCL is only
+    # used for the barrier / max-over-ranks timing.  The head-sharded mode (--workload c4) is the one with a real
+    # exchange (per-head outputs are re-assembled) and keeps its all-gather inside the timed step.
     def step():
         w.run_rotary_append(capi)
         w.run_decode(capi)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, w.o)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -274,8 +279,6 @@ def run_own(args):
             ev[2 * i + 1].record()
             w.run_decode(capi)
             ev[2 * i + 2].record()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, w.o)
         ev_end.record()
         torch.cuda.synchronize()
     launches = capi.launch_count() - n0
@@ -297,7 +300,7 @@ def run_own(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C2 Llama-3-8B decode: batch 64/GPU x 4096 ctx, 32q/8kv heads, D128, page16, bf16 "
                                "paged KV; step = split_rotary+append+decode of one layer",
-                   "global_batch": w.B * world, "seq_len": w.L, "parallelism": f"batch-split x{world}",
+                   "global_batch": w.B * world, "seq_len": w.L, "parallelism": f"batch-split x{world} (no data-path collective)",
                    "l2": "KV working set 1 GiB/GPU > 126 MB L2 (no flush needed)"},
         "tok_s_layer": round(world * w.B / (ms_per_step * 1e-3), 1),
         "roofline": {"bound": "hbm", "kernel": "decode_kernel(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
@@ -359,14 +362,11 @@ def run_e2e(args, w, world, dist=None):
     seq_ids, ones = list(range(B)), [1] * B
     d_qkv = torch.empty_like(w.qkv)
     h_out = torch.empty(w.o.shape, dtype=torch.bfloat16).pin_memory()
-    gathered = torch.empty((world * B, Hq, D), device=dev, dtype=torch.bfloat16) if world > 1 else None
 
     def step():
         cache.begin_forward(seq_ids, ones)
         d_qkv.copy_(w.h_qkv, non_blocking=True)
         cache.attention_with_fused_qkv(0, w.sm_scale, d_qkv, w.o)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, w.o)
         h_out.copy_(w.o, non_blocking=True)
         cache.end_forward()
 
@@ -442,11 +442,31 @@ def run_c4(args, capi, rank, world, dev, peaks, peak_src):
     Hq, Hkv, B, L = 64, 8, 256, 8192
     q0, q1, k0, k1 = sharding.head_shard(Hq, Hkv, world, rank)
     w = DecodeWorkload(B=B, L=L, Hq=q1 - q0, Hkv=k1 - k0, seed=0, device=dev)  # same page table on every rank
+    gather, gather_kind = None, "none"
     if world > 1:
         import torch.distributed as dist
 
+        gather_kind = args.gather
+        if gather_kind == "p2p":
+            try:
+                gather = sharding.PeerHeadGather(B, Hq, w.D, torch.bfloat16, dev)
+            except Exception as e:  # symmetric memory unavailable on this box: the NCCL all-gather still works
+                if rank == 0:
+                    print(f"[bench] peer gather unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+                gather_kind = "nccl"
+        if gather is not None:
+            # parity of the fused path against decode + NCCL all-gather on the same inputs, once, before timing
+            w.run_rotary_append(capi)
+            got = w.run_decode_gather(capi, gather).clone()
+            w.run_decode(capi)
+            want = sharding.all_gather_heads(w.o)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), "peer-gathered heads differ from decode + NCCL all-gather"
+
     def step():
         w.run_rotary_append(capi)
+        if gather is not None:
+            return w.run_decode_gather(capi, gather)
         w.run_decode(capi)
         if world > 1:
             return sharding.all_gather_heads(w.o)
@@ -478,7 +498,9 @@ def run_c4(args, capi, rank, world, dev, peaks, peak_src):
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": {"workload": "C4 Llama-3-70B GQA decode: batch 256 x 8192 ctx, 64q/8kv heads sharded by KV-head group, "
-                                  "D128, page16, bf16; step = split_rotary+append+decode (+all-gather of O)",
+                                  "D128, page16, bf16; step = split_rotary+append+decode+re-assembly of the per-head O on every rank",
+                      "head_gather": {"p2p": "in-kernel NVLink peer stores + flags (tvmb200_attention_decode_gather)",
+                                      "nccl": "ncclAllGather behind the kernel", "none": "single GPU"}[gather_kind],
                       "global_batch": B, "seq_len": L, "parallelism": f"tp{world} (KV-head groups)",
                       "l2": "KV working set >= 1 GiB/GPU > 126 MB L2"},
            "tok_s_layer": round(B / (ms * 1e-3), 1),
@@ -522,6 +544,8 @@ def main():
     ap.add_argument("--workload", default="decode", choices=["decode", "prefill", "c4"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p",
+                    help="c4 workload: how the per-head outputs are re-assembled across ranks")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs: launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":

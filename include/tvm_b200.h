@@ -120,6 +120,31 @@ TVMB200_API int tvmb200_split_rotary(const void* qkv, const int32_t* position_ma
                          float rope_theta, int dtype, tvmb200_stream_t stream);
 
 /*!
+ * \brief f_attention_decode for a KV-head shard of one multi-GPU box, fused with the re-assembly of the per-head
+ *  outputs.  The reference shards this path with Disco tensor parallelism and gathers the heads with
+ *  `runtime.disco.allgather` -> ncclAllGather behind the kernel (src/runtime/extra/disco/nccl/nccl.cc:136-144;
+ *  sharded attention: tests/python/disco/test_ccl.py:557-700).  Here the kernel that produces O stores this rank's
+ *  `num_qo_heads` heads into EVERY rank's gathered buffer `peer_outputs[i]` ([batch, world*num_qo_heads, D], heads
+ *  [rank*num_qo_heads, (rank+1)*num_qo_heads)) through NVLink peer pointers, then writes `epoch` to
+ *  `peer_flags[i][rank]` with release semantics at system scope.  `output` / `lse` still receive the local result.
+ *  A consumer on rank i calls tvmb200_wait_peer_flags(peer_flags[i], world, epoch) before it reads its gathered buffer.
+ *  Epochs must increase by one per call (wrap-around safe); pointers are peer-mapped device pointers of one process
+ *  per GPU (e.g. torch.distributed._symmetric_memory buffer_ptrs).  world == 1 degenerates to a local copy.
+ */
+TVMB200_API int tvmb200_attention_decode_gather(const void* q, const void* pages, const int32_t* page_indptr,
+                                    const int32_t* page_values, const int32_t* length_info,
+                                    const int32_t* k_rope_pos_offset, const int32_t* q_rope_position,
+                                    void* output, float* lse, int32_t batch_size, int32_t nnz_pages,
+                                    int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                    int32_t page_size, int32_t head_dim, int sliding_window, int rotary_mode,
+                                    float rope_scale, float rope_theta, float sm_scale, int dtype,
+                                    void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
+                                    int32_t rank, uint32_t epoch, tvmb200_stream_t stream);
+
+/*! \brief Block the stream until flags[r] has reached `epoch` for every r < world (see tvmb200_attention_decode_gather). */
+TVMB200_API int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream);
+
+/*!
  * \brief f_split_rotary immediately followed by f_transpose_append, in ONE launch (SURVEY 8(f) "next": fused
  *  rotary + append).  Replaces the back-to-back callback pair of AttentionWithFusedQKV when the append precedes
  *  the attention (paged_kv_cache.cc:1360 then :1371): q, k, v are written exactly as tvmb200_split_rotary writes

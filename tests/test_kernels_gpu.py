@@ -219,6 +219,38 @@ def test_decode_batch64(capi, dtype):
     _run_decode(capi, rng, list(rng.integers(1, 700, 64)), 32, 8, 128, dtype)
 
 
+@pytest.mark.parametrize("kv_lens", [[11, 70, 300, 0, 16], [8192, 3, 4097]])
+def test_decode_gather_single_rank(capi, kv_lens):
+    """tvmb200_attention_decode_gather with world = 1 (this rank is its own peer): the gathered buffer, the local
+    output and the LSE must be bit-identical to plain attention_decode, whether or not the sequences are split, and the
+    rank's flag must carry the epoch afterwards (two consecutive epochs: the block counter resets itself)."""
+    import torch
+
+    rng = np.random.default_rng(16)
+    dtype, hq, hkv, d = "bfloat16", 32, 8, 128
+    B = len(kv_lens)
+    c = make_paged_cache(rng, kv_lens, hkv, d, dtype)
+    q = to_dev(rand16(rng, (B, hq, d), dtype), dtype)
+    pages = to_dev(c["pages"], dtype)
+    kpos = _i32(np.zeros(B, np.int32))
+    qpos = _i32(np.maximum(np.array(kv_lens) - 1, 0).astype(np.int32))
+    args = (q, pages, _i32(c["page_indptr"]), _i32(c["page_values"]), _i32(c["length_info"]), kpos, qpos)
+    o = torch.empty((B, hq, d), dtype=q.dtype, device="cuda")
+    lse = torch.empty((B, hq), dtype=torch.float32, device="cuda")
+    capi.attention_decode(*args, o, lse, 0, 1.0, 1e4, d ** -0.5)
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    for epoch in (1, 2):
+        gathered = torch.full((B, hq, d), float("nan"), dtype=q.dtype, device="cuda")
+        o2 = torch.full_like(o, float("nan"))
+        lse2 = torch.full_like(lse, float("nan"))
+        capi.attention_decode_gather(*args, o2, lse2, 0, 1.0, 1e4, d ** -0.5, [gathered.data_ptr()], [flags.data_ptr()],
+                                     0, epoch)
+        capi.wait_peer_flags(flags, 1, epoch)
+        torch.cuda.synchronize()
+        assert torch.equal(o2, o) and torch.equal(lse2, lse) and torch.equal(gathered, o)
+        assert int(flags[0]) == epoch
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_decode_sliding_window(capi, dtype):
     rng = np.random.default_rng(14)

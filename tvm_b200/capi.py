@@ -60,6 +60,9 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_merge_state_inplace.argtypes = [P, P, P, P, I64, I32, I32, c_int, P]
     L.tvmb200_attention_decode.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
                                            c_int, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_decode_gather.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
+                                                  c_int, c_int, F, F, F, c_int, P, P, I32, I32, ctypes.c_uint32, P]
+    L.tvmb200_wait_peer_flags.argtypes = [P, I32, ctypes.c_uint32, P]
     L.tvmb200_attention_prefill_paged.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I64, I32, I32,
                                                   I32, I32, c_int, I32, c_int, c_int, F, F, F, c_int, P]
     L.tvmb200_attention_prefill_ragged.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32,
@@ -163,6 +166,26 @@ def attention_decode(q, pages, page_indptr, page_values, length_info, k_rope_pos
         _p(q), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
         _p(q_rope_position), _p(output), _p(lse), q.shape[0], page_values.shape[0], P, q.shape[1], Hkv, page, D,
         1 if length_info.dim() == 2 else 0, rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages), _stream(q)))
+
+
+def attention_decode_gather(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output,
+                            lse, rotary_mode, rope_scale, rope_theta, sm_scale, peer_output_ptrs, peer_flag_ptrs, rank,
+                            epoch):
+    """attention_decode of this rank's KV-head shard + peer stores of its heads into every rank's gathered buffer.
+    peer_output_ptrs / peer_flag_ptrs: lists of `world` integer device addresses (peer-mapped)."""
+    P, _, Hkv, page, D = pages.shape
+    world = len(peer_output_ptrs)
+    outs = (c_void_p * world)(*[int(x) for x in peer_output_ptrs])
+    flags = (c_void_p * world)(*[int(x) for x in peer_flag_ptrs])
+    _check(lib().tvmb200_attention_decode_gather(
+        _p(q), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
+        _p(q_rope_position), _p(output), _p(lse), q.shape[0], page_values.shape[0], P, q.shape[1], Hkv, page, D,
+        1 if length_info.dim() == 2 else 0, rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages),
+        ctypes.cast(outs, c_void_p), ctypes.cast(flags, c_void_p), world, rank, epoch & 0xFFFFFFFF, _stream(q)))
+
+
+def wait_peer_flags(flags, world, epoch):
+    _check(lib().tvmb200_wait_peer_flags(_p(flags), world, epoch & 0xFFFFFFFF, _stream(flags)))
 
 
 def attention_prefill_paged(q, q_indptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset,

@@ -48,6 +48,7 @@ struct DecodeParams {
   int num_kv_heads;
   int group;  // Hq / Hkv
   int chunk_pages;
+  int always_partial;  // every item writes fp32 partials, the merge kernel produces all outputs (peer-gather mode)
   int sliding;  // length_info is [3,B]
   int rotary_mode;
   float rope_scale;
@@ -426,7 +427,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
         const bool empty = den == 0.f;
         const float outv = empty ? 0.f : acc / den;
         const float lsev = empty ? kNegInit : mm + log2f(den);
-        if (n_chunks_b == 1) {
+        if (n_chunks_b == 1 && !p.always_partial) {
           static_cast<T*>(p.output)[(static_cast<int64_t>(b) * p.num_qo_heads + hq) * D + dd] = DT<T>::from_f(outv);
           if (dd == 0) p.lse[static_cast<int64_t>(b) * p.num_qo_heads + hq] = lsev;
         } else {
@@ -440,16 +441,32 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   pdl_launch_dependents();  // the merge kernel's blocks may be scheduled; they still wait for this grid's completion
 }
 
+// Head-sharded multi-GPU decode (north_star: KV-head groups across one 8 x B200 box; reference: Disco tensor
+// parallelism + ncclAllGather of the per-head outputs, src/runtime/extra/disco/nccl/nccl.cc:136-144).  Instead of a
+// collective behind the kernel, the merge kernel itself stores this rank's heads into EVERY rank's gathered
+// [n, total_heads, D] buffer through NVLink peer pointers, and the last block to finish raises this rank's flag in
+// every peer's flag array (release at system scope); a consumer waits until all `n` flags carry the step's epoch.
+struct PeerGather {
+  void* out[8];        // gathered output buffer of rank i (peer-mapped device pointer)
+  uint32_t* flags[8];  // flag array of rank i: flags[i][r] = last epoch rank r has completely written into rank i
+  int n;               // number of ranks (0 = no gather)
+  int rank;
+  int head_offset;     // first gathered head of this rank
+  int total_heads;
+  uint32_t epoch;
+  int32_t* done;       // block counter (zero between launches)
+};
+
 // reduce the partial (O, LSE) of sequences that were split into > 1 chunks.  grid = (B, Hq), D threads.
 template <typename T, int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
                     const int32_t* __restrict__ chunk_off, T* __restrict__ output,
-                    float* __restrict__ lse, int num_qo_heads) {
+                    float* __restrict__ lse, int num_qo_heads, const PeerGather pg) {
   const int b = blockIdx.x, hq = blockIdx.y, dd = threadIdx.x;
   pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
   const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
-  if (c1 - c0 <= 1) return;
+  if (pg.n == 0 && c1 - c0 <= 1) return;
   // The kernel is pure latency (a few KiB per block): keep the loads independent -- the chunk LSEs go to shared
   // memory in one parallel sweep, the partial outputs are read four at a time -- instead of two serial chains.
   __shared__ float s_lse[D];
@@ -480,8 +497,37 @@ decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ 
     acc += w * po[c * cs];
     den += w;
   }
-  output[(static_cast<int64_t>(b) * num_qo_heads + hq) * D + dd] = DT<T>::from_f(acc / den);
+  const T outv = DT<T>::from_f(acc / den);
+  output[(static_cast<int64_t>(b) * num_qo_heads + hq) * D + dd] = outv;
   if (dd == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = mm + log2f(den);
+  if (pg.n > 0) {
+    const int64_t at = (static_cast<int64_t>(b) * pg.total_heads + pg.head_offset + hq) * D + dd;
+    for (int i = 0; i < pg.n; ++i) static_cast<T*>(pg.out[i])[at] = outv;
+    // completion: the block's peer stores are ordered (barrier, then ONE system-scope fence by thread 0 -- fences are
+    // cumulative over what the barrier made visible to it) before its ticket; the last block signals every peer
+    __syncthreads();
+    if (dd == 0) {
+      __threadfence_system();
+      const int total = static_cast<int>(gridDim.x * gridDim.y);
+      if (atomicAdd(pg.done, 1) == total - 1) {
+        *pg.done = 0;
+        __threadfence_system();
+        for (int i = 0; i < pg.n; ++i)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pg.flags[i] + pg.rank), "r"(pg.epoch) : "memory");
+      }
+    }
+  }
+}
+
+// wait until every rank's flag in this rank's flag array carries `epoch` (one thread per rank)
+__global__ void wait_peer_flags_kernel(const uint32_t* __restrict__ flags, int n, uint32_t epoch) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    } while (static_cast<int32_t>(v - epoch) < 0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -580,7 +626,7 @@ int get_tmap_2d_cached(CUtensorMap* out, const void* base, int dtype, uint64_t r
 
 template <typename T, int D, int NW, int NSTAGE, bool ROPE>
 static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
-                         cudaStream_t st) {
+                         cudaStream_t st, const PeerGather& pg) {
   using Cfg = DecodeCfg<D>;
   const size_t smem = 1024 + static_cast<size_t>(NW) * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8 +
                       (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int) + 16 + (D / 2) * sizeof(float) +
@@ -605,7 +651,7 @@ static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, in
     cfg.dynamicSmemBytes = 0;
     TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_kernel<T, D>, static_cast<const float*>(p.part_o),
                                     static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
-                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads));
+                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads, pg));
     TVMB200_LAUNCH_OK();
   }
   return 0;
@@ -613,25 +659,23 @@ static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, in
 
 template <typename T, int D, int NW, int NSTAGE>
 static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
-                         cudaStream_t st) {
+                         cudaStream_t st, const PeerGather& pg) {
   // inline RoPE is a separate instantiation so the default (pre-rotated K) path keeps its register budget
-  return p.rotary_mode == 1 ? launch_decode_impl<T, D, NW, NSTAGE, true>(tmap, p, grid, need_merge, st)
-                            : launch_decode_impl<T, D, NW, NSTAGE, false>(tmap, p, grid, need_merge, st);
+  return p.rotary_mode == 1 ? launch_decode_impl<T, D, NW, NSTAGE, true>(tmap, p, grid, need_merge, st, pg)
+                            : launch_decode_impl<T, D, NW, NSTAGE, false>(tmap, p, grid, need_merge, st, pg);
 }
 
 }  // namespace tvmb200
 
 using namespace tvmb200;
 
-extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const int32_t* page_indptr,
-                                        const int32_t* page_values, const int32_t* length_info,
-                                        const int32_t* k_rope_pos_offset,
-                                        const int32_t* q_rope_position, void* output, float* lse,
-                                        int32_t batch_size, int32_t nnz_pages, int64_t num_pages,
-                                        int32_t num_qo_heads, int32_t num_kv_heads,
-                                        int32_t page_size, int32_t head_dim, int sliding_window,
-                                        int rotary_mode, float rope_scale, float rope_theta,
-                                        float sm_scale, int dtype, tvmb200_stream_t stream) {
+static int decode_entry(const void* q, const void* pages, const int32_t* page_indptr,
+                        const int32_t* page_values, const int32_t* length_info,
+                        const int32_t* k_rope_pos_offset, const int32_t* q_rope_position, void* output, float* lse,
+                        int32_t batch_size, int32_t nnz_pages, int64_t num_pages, int32_t num_qo_heads,
+                        int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int sliding_window,
+                        int rotary_mode, float rope_scale, float rope_theta, float sm_scale, int dtype,
+                        tvmb200_stream_t stream, const PeerGather& pg) {
   TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "attention_decode: unsupported dtype %d", dtype);
   TVMB200_CHECK(page_size == 16, "attention_decode: page_size %d unsupported (the B200 path is built for 16-slot pages)", page_size);
   TVMB200_CHECK(head_dim == 128 || head_dim == 64, "attention_decode: head_dim %d unsupported (64 or 128)", head_dim);
@@ -652,7 +696,8 @@ extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const 
   int chunk_pages = static_cast<int>((work + static_cast<int64_t>(grid_max) * 8 - 1) / (static_cast<int64_t>(grid_max) * 8));
   chunk_pages = ((chunk_pages + NW - 1) / NW) * NW;
   if (chunk_pages < 8) chunk_pages = 8;
-  const bool need_merge = chunk_pages < nnz_pages;  // otherwise every sequence is a single chunk
+  // otherwise every sequence is a single chunk; the peer-gather mode always goes through the merge kernel
+  const bool need_merge = chunk_pages < nnz_pages || pg.n > 0;
   const int64_t max_chunks = static_cast<int64_t>(nnz_pages) / chunk_pages + batch_size;
   const int64_t n_items_max = max_chunks * num_kv_heads;
   const int grid = static_cast<int>(n_items_max < grid_max ? n_items_max : grid_max);
@@ -681,6 +726,7 @@ extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const 
   p.num_kv_heads = num_kv_heads;
   p.group = group;
   p.chunk_pages = chunk_pages;
+  p.always_partial = pg.n > 0 ? 1 : 0;
   p.sliding = sliding_window ? 1 : 0;
   p.rotary_mode = rotary_mode;
   p.rope_scale = rope_scale;
@@ -692,10 +738,76 @@ extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const 
   if (int rc = get_tmap_2d_cached(&tmap, pages, dtype, rows, head_dim, 16)) return rc;
 
   if (dtype == TVMB200_F16) {
-    if (head_dim == 128) return launch_decode<__half, 128, NW, 3>(tmap, p, grid, need_merge, st);
-    return launch_decode<__half, 64, NW, 6>(tmap, p, grid, need_merge, st);
+    if (head_dim == 128) return launch_decode<__half, 128, NW, 3>(tmap, p, grid, need_merge, st, pg);
+    return launch_decode<__half, 64, NW, 6>(tmap, p, grid, need_merge, st, pg);
   } else {
-    if (head_dim == 128) return launch_decode<__nv_bfloat16, 128, NW, 3>(tmap, p, grid, need_merge, st);
-    return launch_decode<__nv_bfloat16, 64, NW, 6>(tmap, p, grid, need_merge, st);
+    if (head_dim == 128) return launch_decode<__nv_bfloat16, 128, NW, 3>(tmap, p, grid, need_merge, st, pg);
+    return launch_decode<__nv_bfloat16, 64, NW, 6>(tmap, p, grid, need_merge, st, pg);
   }
+}
+
+extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const int32_t* page_indptr,
+                                        const int32_t* page_values, const int32_t* length_info,
+                                        const int32_t* k_rope_pos_offset,
+                                        const int32_t* q_rope_position, void* output, float* lse,
+                                        int32_t batch_size, int32_t nnz_pages, int64_t num_pages,
+                                        int32_t num_qo_heads, int32_t num_kv_heads,
+                                        int32_t page_size, int32_t head_dim, int sliding_window,
+                                        int rotary_mode, float rope_scale, float rope_theta,
+                                        float sm_scale, int dtype, tvmb200_stream_t stream) {
+  PeerGather pg = {};
+  return decode_entry(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
+                      batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window,
+                      rotary_mode, rope_scale, rope_theta, sm_scale, dtype, stream, pg);
+}
+
+static int get_done_counter(int32_t** out) {
+  static int32_t* counters[64];
+  static std::mutex mu;
+  int dev = 0;
+  TVMB200_CUDA(cudaGetDevice(&dev));
+  TVMB200_CHECK(dev >= 0 && dev < 64, "device id %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!counters[dev]) {
+    TVMB200_CUDA(cudaMalloc(&counters[dev], 256));
+    TVMB200_CUDA(cudaMemset(counters[dev], 0, 256));
+  }
+  *out = counters[dev];
+  return 0;
+}
+
+extern "C" int tvmb200_attention_decode_gather(const void* q, const void* pages, const int32_t* page_indptr,
+                                               const int32_t* page_values, const int32_t* length_info,
+                                               const int32_t* k_rope_pos_offset, const int32_t* q_rope_position,
+                                               void* output, float* lse, int32_t batch_size, int32_t nnz_pages,
+                                               int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                               int32_t page_size, int32_t head_dim, int sliding_window, int rotary_mode,
+                                               float rope_scale, float rope_theta, float sm_scale, int dtype,
+                                               void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
+                                               int32_t rank, uint32_t epoch, tvmb200_stream_t stream) {
+  TVMB200_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "attention_decode_gather: world %d / rank %d (1..8 ranks of one box)", world, rank);
+  TVMB200_CHECK(peer_outputs != nullptr && peer_flags != nullptr, "attention_decode_gather: peer pointer arrays are null");
+  PeerGather pg = {};
+  pg.n = world;
+  pg.rank = rank;
+  pg.head_offset = rank * num_qo_heads;
+  pg.total_heads = world * num_qo_heads;
+  pg.epoch = epoch;
+  for (int i = 0; i < world; ++i) {
+    TVMB200_CHECK(peer_outputs[i] != nullptr && peer_flags[i] != nullptr, "attention_decode_gather: peer %d pointer is null", i);
+    pg.out[i] = peer_outputs[i];
+    pg.flags[i] = peer_flags[i];
+  }
+  if (int rc = get_done_counter(&pg.done)) return rc;
+  if (batch_size <= 0) return 0;
+  return decode_entry(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
+                      batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window,
+                      rotary_mode, rope_scale, rope_theta, sm_scale, dtype, stream, pg);
+}
+
+extern "C" int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream) {
+  TVMB200_CHECK(flags != nullptr && world >= 1 && world <= 8, "wait_peer_flags: bad arguments");
+  wait_peer_flags_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, world, epoch);
+  TVMB200_LAUNCH_OK();
+  return 0;
 }

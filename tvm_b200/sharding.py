@@ -56,3 +56,44 @@ def all_gather_batch(o_local, group=None):
     out = torch.empty((world * o_local.shape[0],) + tuple(o_local.shape[1:]), dtype=o_local.dtype, device=o_local.device)
     dist.all_gather_into_tensor(out, o_local.contiguous(), group=group)
     return out
+
+
+class PeerHeadGather:
+    """Re-assembly of the per-head decode outputs over NVLink peer memory, done BY the attention kernel
+    (capi.attention_decode_gather) instead of an NCCL all-gather behind it.  One process per GPU; the gathered
+    [n, Hq, D] buffer and a small flag array of every rank are allocated as torch symmetric memory so that each rank
+    holds peer-mapped pointers to all of them.  `gathered` is double-buffered by epoch parity so a rank that runs ahead
+    into step e+1 never overwrites a buffer a slower rank still reads for step e.  (The reference: Disco allgather ->
+    ncclAllGather, src/runtime/extra/disco/nccl/nccl.cc:136-144.)"""
+
+    def __init__(self, n, num_qo_heads_total, head_dim, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.bufs, self.buf_ptrs = [], []
+        for _ in range(2):
+            t = symm_mem.empty((n, num_qo_heads_total, head_dim), dtype=dtype, device=device)
+            h = symm_mem.rendezvous(t, group)
+            self.bufs.append(t)
+            self.buf_ptrs.append(list(h.buffer_ptrs))
+        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        hf = symm_mem.rendezvous(self.flags, group)
+        self.flag_ptrs = list(hf.buffer_ptrs)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def decode(self, capi, q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output,
+               lse, rotary_mode, rope_scale, rope_theta, sm_scale):
+        """-> the gathered [n, Hq_total, D] tensor of this step (valid once the returned stream work has run)"""
+        self.epoch += 1
+        par = self.epoch & 1
+        capi.attention_decode_gather(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset,
+                                     q_rope_position, output, lse, rotary_mode, rope_scale, rope_theta, sm_scale,
+                                     self.buf_ptrs[par], self.flag_ptrs, self.rank, self.epoch)
+        capi.wait_peer_flags(self.flags, self.world, self.epoch)
+        return self.bufs[par]
