@@ -219,7 +219,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t sq = sbase + SmemLayout::q, skv = sbase + SmemLayout::kv;
 
   if (warp < 4) {
-    tc05::setmaxnreg_dec<64>();
+    tc05::setmaxnreg_dec<72>();
     if (warp == 0) {
       // =========================== TMA producer + work fetch ===========================
       uint32_t fill = 0;   // K / V tiles loaded so far (all items): ring slot = fill & 3
@@ -429,43 +429,33 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       float m_used = kNegInit, l = 0.f;
       const int my_ns = t ? it.ns1 : it.ns0;
       if (t >= nqt) continue;
-      for (int s = 0; s < my_ns; ++s) {
-        const int hb = s & 1;                       // S half of this step
-        const uint32_t t_sb = t_s + hb * kStep;
-        if (wq == 0) TRACE(1 + t, s, 0);
-        mbar_wait(bar(S_FULL + 2 * t + hb), n_s & 1);
-        if (hb == 1 || s == my_ns - 1) ++n_s;       // this KV tile's S is consumed with this step
-        if (wq == 0) TRACE(1 + t, s, 1);
-        tc05::fence_after_sync();
-        ++n_p[hb];
-        const int lo_id = static_cast<int>(n_p[hb]);
-        uint32_t s0[32], s1[32];
-        tc05::ld32(t_sb + 0, s0);
-        tc05::ld32(t_sb + 32, s1);
-        tc05::wait_ld();
-        if (wq == 0) TRACE(1 + t, s, 2);
-        const int rem = limit - s * kStep;  // columns [0, rem) of this step are visible
+      const uint32_t ninf = __float_as_uint(-INFINITY);
+      // columns [0, rem) of a 64-column half are visible
+      auto mask_half = [&](uint32_t (&x0)[32], uint32_t (&x1)[32], int rem) {
         if (__any_sync(0xffffffffu, rem < kStep)) {
-          const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            if (c >= rem) s0[c] = ninf;
-            if (c + 32 >= rem) s1[c] = ninf;
+            if (c >= rem) x0[c] = ninf;
+            if (c + 32 >= rem) x1[c] = ninf;
           }
         }
-        // four independent FMNMX3 chains, 8 deep each
+      };
+      // four independent FMNMX3 chains per half
+      auto half_max = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32]) {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          mx0 = tc05::fmax3(mx0, __uint_as_float(s0[c]), __uint_as_float(s0[c + 1]));
-          mx1 = tc05::fmax3(mx1, __uint_as_float(s0[c + 2]), __uint_as_float(s0[c + 3]));
-          mx2 = tc05::fmax3(mx2, __uint_as_float(s1[c]), __uint_as_float(s1[c + 1]));
-          mx3 = tc05::fmax3(mx3, __uint_as_float(s1[c + 2]), __uint_as_float(s1[c + 3]));
+          mx0 = tc05::fmax3(mx0, __uint_as_float(x0[c]), __uint_as_float(x0[c + 1]));
+          mx1 = tc05::fmax3(mx1, __uint_as_float(x0[c + 2]), __uint_as_float(x0[c + 3]));
+          mx2 = tc05::fmax3(mx2, __uint_as_float(x1[c]), __uint_as_float(x1[c + 1]));
+          mx3 = tc05::fmax3(mx3, __uint_as_float(x1[c + 2]), __uint_as_float(x1[c + 3]));
         }
-        const float mx = fmaxf(tc05::fmax3(mx0, mx1, mx2), mx3);
-        if (wq == 0) TRACE(1 + t, s, 4);
+        return fmaxf(tc05::fmax3(mx0, mx1, mx2), mx3);
+      };
+      // lazy rescale: keep the old reference max while the true max is within 2^8 of it.  `prev_half` >= 0 names the
+      // S half whose PV was issued last: O_t must be complete before it is rescaled.
+      auto rescale = [&](float mx, int prev_half) {
         const float m_new = fmaxf(m_used, mx * sc);
-        // lazy rescale: keep the old reference max while the true max is within 2^8 of it
         const bool grow = m_new - m_used > kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
@@ -473,8 +463,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             m_used = m_new;
             l *= alpha;
           }
-          if (s > 0) {
-            mbar_wait(bar(PV_DONE + 2 * t + ((s - 1) & 1)), (n_p[(s - 1) & 1] - 1) & 1);  // O_t must be complete before it is rescaled
+          if (prev_half >= 0) {
+            mbar_wait(bar(PV_DONE + 2 * t + prev_half), (n_p[prev_half] - 1) & 1);
             tc05::fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -487,69 +477,135 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
           }
         }
+      };
+      // exp2, pack, store P (and P_lo) of one 64-column half, hand it to the MMA warp.  Scale/subtract and the row sum
+      // run as packed FFMA2 / FADD2; kPolyPairs of every 16 pairs take 2^x on the FMA pipe instead of the MUFU unit.
+      auto do_half = [&](uint32_t (&x0)[32], uint32_t (&x1)[32], int hb, float mx_half, int si) {
         const float mneg = -m_used;
         const float2 sc2 = make_float2(sc, sc), mneg2 = make_float2(mneg, mneg);
+        const uint32_t t_sb = t_s + hb * kStep;
+        ++n_p[hb];
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-        // p in place (s regs), P_hi packed into 32 columns.  Scale/subtract and the row sum run as packed
-        // FFMA2 / FADD2; kPolyPairs of every 16 pairs take 2^x on the FMA pipe instead of the MUFU unit
-        // (the MUFU needs as many cycles per tile as the tensor core: 128x128 ex2 at 16/clk/SM = 1024 clk).
-        uint32_t pk[32];
-        auto exp_pack = [&](uint32_t (&sr)[32], int chunk) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const int pi = c >> 1;
-            constexpr int kPolyPairs = kPolyPairsOf<PT>;
-            const bool poly = ((pi + 1) * kPolyPairs) / 16 != (pi * kPolyPairs) / 16;
-            const float2 x = tc05::ffma2(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, mneg2);
-            float2 a;
-            if (poly) {
-              a = tc05::exp2_poly2(x);
-            } else {
-              a.x = fast_exp2(x.x);
-              a.y = fast_exp2(x.y);
-            }
-            if (pi & 1) sum_b = tc05::fadd2(sum_b, a); else sum_a = tc05::fadd2(sum_a, a);
-            sr[c] = __float_as_uint(a.x);
-            sr[c + 1] = __float_as_uint(a.y);
-            pk[chunk * 16 + pi] = pack_p<PT>(a.x, a.y);
+        // 2^(s*scale - m) of column pair `pi` of a 32-column chunk (pi is a compile-time index once unrolled)
+        auto exp_pair = [&](uint32_t u0, uint32_t u1, int pi) {
+          constexpr int kPolyPairs = kPolyPairsOf<PT>;
+          const bool poly = ((pi + 1) * kPolyPairs) / 16 != (pi * kPolyPairs) / 16;
+          const float2 x = tc05::ffma2(make_float2(__uint_as_float(u0), __uint_as_float(u1)), sc2, mneg2);
+          float2 a;
+          if (poly) {
+            a = tc05::exp2_poly2(x);
+          } else {
+            a.x = fast_exp2(x.x);
+            a.y = fast_exp2(x.y);
           }
+          if (pi & 1) sum_b = tc05::fadd2(sum_b, a); else sum_a = tc05::fadd2(sum_a, a);
+          return a;
         };
-        exp_pack(s0, 0);
-        exp_pack(s1, 1);
-        if (wq == 0) TRACE(1 + t, s, 5);
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float2 a = exp_pair(x0[c], x0[c + 1], c >> 1);
+          pk[c >> 1] = pack_p<PT>(a.x, a.y);
+          if (kLoPass) {  // keep the fp32 weights (in place of S) for a possible P_lo residual
+            x0[c] = __float_as_uint(a.x);
+            x0[c + 1] = __float_as_uint(a.y);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float2 a = exp_pair(x1[c], x1[c + 1], c >> 1);
+          pk[16 + (c >> 1)] = pack_p<PT>(a.x, a.y);
+          if (kLoPass) {
+            x1[c] = __float_as_uint(a.x);
+            x1[c + 1] = __float_as_uint(a.y);
+          }
+        }
         tc05::st32(t_sb, pk);
         sum_a = tc05::fadd2(sum_a, sum_b);
         l += sum_a.x + sum_a.y;
         if (kLoPass) {
-          // largest weight of this row in this step vs. the running denominator.  The decision is per WARP (no
-          // warpgroup barrier): a warp with such a row stores P_lo for its 32 rows and stamps the tile's flag with
-          // this step's id; every other warp stores zeros, so a PV_lo pass triggered by another warp adds nothing
-          // for its rows.  The MMA warp runs the second pass iff the flag carries the id of the step it issues.
-          const float p_max = fast_exp2(fmaf(mx, sc, mneg));
-          const bool need_lo = __any_sync(0xffffffffu, p_max > kLoTau * l);
-          if (need_lo) {
-            auto lo_pack = [&](const uint32_t (&sr)[32], int chunk) {
+          // bf16 only: does some row of this warp have a weight above kLoTau of its running denominator?  The decision
+          // is per WARP (no warpgroup barrier): a warp with such a row stores the residual P_lo = P - bf16(P) of its 32
+          // rows and stamps the tile's flag with this step's id; every other warp stores zeros, so a PV_lo pass
+          // triggered by another warp adds nothing for its rows.  The MMA warp runs the second pass iff the flag
+          // carries the id of the step it issues.
+          const float p_max = fast_exp2(fmaf(mx_half, sc, mneg));
+          if (__any_sync(0xffffffffu, p_max > kLoTau * l)) {
 #pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                const float a0 = __uint_as_float(sr[c]), a1 = __uint_as_float(sr[c + 1]);
-                const float2 hi2 = DT<PT>::to_f2(pk[chunk * 16 + (c >> 1)]);
-                pk[chunk * 16 + (c >> 1)] = pack_p<PT>(a0 - hi2.x, a1 - hi2.y);
-              }
-            };
-            lo_pack(s0, 0);
-            lo_pack(s1, 1);
-            if (lane == 0) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = lo_id;
+            for (int c = 0; c < 32; c += 2) {
+              const float2 h0 = DT<PT>::to_f2(pk[c >> 1]), h1 = DT<PT>::to_f2(pk[16 + (c >> 1)]);
+              pk[c >> 1] = pack_p<PT>(__uint_as_float(x0[c]) - h0.x, __uint_as_float(x0[c + 1]) - h0.y);
+              pk[16 + (c >> 1)] = pack_p<PT>(__uint_as_float(x1[c]) - h1.x, __uint_as_float(x1[c + 1]) - h1.y);
+            }
+            if (lane == 0)
+              *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = static_cast<int>(n_p[hb]);
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c) pk[c] = 0u;
           }
           tc05::st32(t_sb + 32, pk);
         }
-        if (wq == 0) TRACE(1 + t, s, 6);
+        if (wq == 0) TRACE(1 + t, si, 5);
         tc05::wait_st();
         tc05::fence_before_sync();
         mbar_arrive(bar(P_READY + 2 * t + hb));
-        if (wq == 0) TRACE(1 + t, s, 3);
+        if (wq == 0) TRACE(1 + t, si, 3);
+      };
+      if constexpr (!kLoPass) {
+        // fp16: one iteration = one KV tile (128 columns): all S values are loaded and reduced to ONE row maximum /
+        // rescale decision, then the two 64-column halves are exponentiated, packed and handed over one after the
+        // other, so PV of the lower half runs while the upper half is still in the exp2 phase (-4 % time).
+        const int my_tiles = (my_ns + 1) >> 1;
+        for (int j = 0; j < my_tiles; ++j) {
+          const bool has_b = 2 * j + 1 < my_ns;       // upper half visible to some row of the tile (CTA-uniform)
+          if (wq == 0) TRACE(1 + t, 2 * j, 0);
+          mbar_wait(bar(S_FULL + 2 * t), n_s & 1);
+          if (has_b) mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);
+          ++n_s;
+          if (wq == 0) TRACE(1 + t, 2 * j, 1);
+          tc05::fence_after_sync();
+          uint32_t sa0[32], sa1[32], sb0[32], sb1[32];
+          tc05::ld32(t_s + 0, sa0);
+          tc05::ld32(t_s + 32, sa1);
+          if (has_b) {
+            tc05::ld32(t_s + 64, sb0);
+            tc05::ld32(t_s + 96, sb1);
+          }
+          tc05::wait_ld();
+          if (wq == 0) TRACE(1 + t, 2 * j, 2);
+          const int rem_a = limit - 2 * j * kStep;
+          mask_half(sa0, sa1, rem_a);
+          const float mx_a = half_max(sa0, sa1);
+          float mx_b = -INFINITY;
+          if (has_b) {
+            mask_half(sb0, sb1, rem_a - kStep);
+            mx_b = half_max(sb0, sb1);
+          }
+          if (wq == 0) TRACE(1 + t, 2 * j, 4);
+          rescale(fmaxf(mx_a, mx_b), j > 0 ? 1 : -1);  // the last PV of KV tile j-1 is its upper half
+          do_half(sa0, sa1, 0, mx_a, 2 * j);
+          if (has_b) do_half(sb0, sb1, 1, mx_b, 2 * j + 1);
+        }
+      } else {
+        // bf16: 64-column steps (the wide iteration plus the P_lo words does not fit the register budget: 953 -> 913)
+        for (int s = 0; s < my_ns; ++s) {
+          const int hb = s & 1;                       // S half of this step
+          if (wq == 0) TRACE(1 + t, s, 0);
+          mbar_wait(bar(S_FULL + 2 * t + hb), n_s & 1);
+          if (hb == 1 || s == my_ns - 1) ++n_s;       // this KV tile's S is consumed with this step
+          if (wq == 0) TRACE(1 + t, s, 1);
+          tc05::fence_after_sync();
+          uint32_t s0[32], s1[32];
+          tc05::ld32(t_s + hb * kStep, s0);
+          tc05::ld32(t_s + hb * kStep + 32, s1);
+          tc05::wait_ld();
+          if (wq == 0) TRACE(1 + t, s, 2);
+          mask_half(s0, s1, limit - s * kStep);
+          const float mx = half_max(s0, s1);
+          if (wq == 0) TRACE(1 + t, s, 4);
+          rescale(mx, s > 0 ? ((s - 1) & 1) : -1);
+          do_half(s0, s1, hb, mx, s);
+        }
       }
       // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
       T* orow = nullptr;
