@@ -26,11 +26,6 @@ buf = (ctypes.c_longlong * (3 * 64 * 8))()
 rc = L.tvmb200_debug_prefill_trace(buf)
 assert rc == 0, rc
 tr = np.frombuffer(buf, dtype=np.int64).reshape(3, 64, 8)
-lo_used = tr[0, :, [0, 3]].copy()  # with_lo flags of the MMA warp, not time stamps
-tr[0, :, 0] = 0
-tr[0, :, 3] = 0
-print("P_lo pass used per step (tile 0):", lo_used[0][:32].tolist())
-print("P_lo pass used per step (tile 1):", lo_used[1][:32].tolist())
 t0 = tr[tr > 0].min()
 rel = np.where(tr > 0, tr - t0, -1)
 mode = sys.argv[2] if len(sys.argv) > 2 else "tile"

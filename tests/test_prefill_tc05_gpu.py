@@ -42,8 +42,9 @@ def test_tc05_ragged_long(tc05, dtype):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("q_scale,v_scale", [(2.0, 1.0), (4.0, 2.0), (8.0, 1.0)])
 def test_tc05_peaked(tc05, dtype, q_scale, v_scale):
-    """A few keys dominate every row (scores with std 2..8) and V is larger: the case the bf16 P_lo pass exists for
-    (P rounded to 8 bits without it); must stay inside the 2e-3 / 1e-2 bar at every element."""
+    """A few keys dominate every row (scores with std 2..8) and V is larger: the case where the precision of P shows
+    (bf16 P would lose it: the kernel keeps P in fp16 and converts bf16 V tiles to fp16 in shared memory); must stay
+    inside the 2e-3 / 1e-2 bar at every element."""
     rng = np.random.default_rng(46)
     _run_ragged(tc05, rng, [300, 77, 513], [300, 400, 600], 32, 8, 128, dtype, causal=1, q_scale=q_scale,
                 v_scale=v_scale)

@@ -6,11 +6,13 @@
 // Reference semantics: python/tvm/relax/frontend/nn/llm/_prefill_kernels.py:217-391 (paged), :795-923
 // (ragged); numerics per _kernel_common.py:222-334 (base-2 online softmax, fp32 accumulate, LSE = m + log2 d).
 //
-// Design (one CTA = 256 GQA-folded query rows of one sequence x one KV head = two 128-row UMMA tiles):
-//   warp 0      TMA producer: Q tiles (3-D box: 64 cols x g heads x 128/g tokens = the reference's row fold
-//               row = token*g + head, _prefill_kernels.py:318-324) once, then K_j / V_j tiles of 128 KV rows
-//               through a 4-slot shared-memory ring (ragged: one 3-D box per 64-col half; paged: eight
-//               16-row page boxes per half, page ids looked up by the producer lanes).
+// Design (persistent: one CTA per SM pulls work items = 256 GQA-folded query rows of one sequence x one KV head = two
+// 128-row UMMA tiles from a device-wide queue, long items first):
+//   warp 0      work fetch (atomic counter -> 2-entry item ring in shared memory) + TMA producer: Q tiles (3-D box:
+//               64 cols x g heads x 128/g tokens = the reference's row fold row = token*g + head,
+//               _prefill_kernels.py:318-324) once per item, K_j / V_j tiles of 128 KV rows through a 4-slot ring
+//               (ragged: one 3-D box per 64-col half; paged: eight 16-row page boxes per half, page ids looked up by
+//               the producer lanes).  The next item's Q / K / V loads start while the current item finishes.
 //   warp 1      MMA issuer (one elected thread).  Per Q tile t and KV tile j: S_t = Q_t K_j^T as eight N = 128 SS
 //               MMAs (K-major operands) into the tile's 128-column S region, and O_t += P_t V_j as two groups of
 //               four TS MMAs (P read from TMEM, V an MN-major shared-memory operand), one group per 64-column half
@@ -19,17 +21,18 @@
 //               steps run the tensor pipe at half rate.  P arrives in a fixed order -- (t0, lower half), (t0, upper),
 //               (t1, lower), (t1, upper) -- and QK_t(j+1) is issued right behind the upper-half PV of tile t, so one
 //               Q tile's PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
-//   warp 2      TMEM allocator (512 columns: S_0, S_1 of 128 columns each, O_0, O_1 of 128; P aliases the S half it
-//               was computed from: P_hi in its first 32 columns, P_lo in the last 32).
-//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row, 64 columns (= one half of
-//               the S region) per step; tcgen05.ld the 64 S values,
-//               mask (diagonal / tail steps only), running max with LAZY rescale (O in TMEM is only rescaled
-//               when the max grows by more than 2^8), exp2, pack to 16-bit, tcgen05.st P, arrive.
-//               Each tile stops at its own last visible step under a causal mask.
-//               The same threads normalise and store O / LSE at the end.
+//   warps 2, 3  TMEM allocation (512 columns: S_0, S_1 of 128 columns each, O_0, O_1 of 128; P aliases the first 32
+//               columns of the S half it was computed from) and, for bf16 inputs, conversion of every V tile to fp16 in
+//               shared memory, so that P can be fp16 (kind::f16 wants one format for A and B).
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; per KV tile: tcgen05.ld the 128
+//               S values, mask (diagonal / tail tiles only), ONE row maximum and LAZY rescale decision (O in TMEM is
+//               only rescaled when the max grows by more than 2^8), then per 64-column half exp2 (4 of 16 pairs on
+//               the FMA pipe), pack to fp16, tcgen05.st P, arrive.  Each tile stops at its own last visible step
+//               under a causal mask.  The same threads normalise and store O / LSE at the end of an item.
 // Measured (scripts/softmax_bench.cu, scripts/prefill_trace.py): the kernel is bound by the softmax instruction
-// stream (~850 clk per 128 x 64 step of one warpgroup), not by the tensor pipe (59 % busy) nor by the MUFU.
-// All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); no __syncthreads in the loop.
+// stream, not by the tensor pipe (~55 % busy) nor by the MUFU.
+// All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives), reused across items with running
+// use counts for the wait parity; no __syncthreads in the loop.
 #include "prefill.cuh"
 #include "tc05.cuh"
 
@@ -49,39 +52,32 @@ constexpr int kTileBytes = 2 * kHalfBytes; // 32 KiB
 constexpr int kSlots = 4;                  // K/V ring
 constexpr int kThreads = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
-// bf16 keeps 8 mantissa bits of P (the reference keeps P in fp32).  When a row of a tile has a weight
-// p > kLoTau * l (a few keys dominate: short rows, peaked attention) the tile gets a second PV pass with the
-// rounding residual P_lo = P - bf16(P) (stored next to P_hi in TMEM), which restores ~16 bits.  Flat tiles
-// (the common case at long context) keep the single pass: a weight below l/8 contributes at most
-// 2^-9 / 8 * |v| = 2.4e-4 |v| of rounding error, << the 2e-3 parity bar (tests: test_tc05_bf16_peaked).
-#ifndef TVMB200_LO_TAU_INV
-#define TVMB200_LO_TAU_INV 8
-#endif
-constexpr float kLoTau = 1.0f / TVMB200_LO_TAU_INV;
-// of every 16 column pairs, how many take 2^x on the FMA pipe instead of the MUFU (swept on C3: 2 is best for bf16,
-// 4 for fp16 -- the bf16 step carries the extra P_lo work on the FMA / ALU pipes)
+// P is always fp16 (11 bits; the reference keeps P in fp32): kind::f16 UMMA needs A and B in one format, so for bf16
+// inputs the V tile is converted to fp16 in shared memory by two otherwise idle warps (exact for |v| in [2^-14, 65504],
+// saturating above).  The first tcgen05 versions kept P in bf16 and added a second PV pass with the rounding residual
+// P_lo = P - bf16(P) for steps with dominant weights: slower (956 vs 976 TFLOP/s) and much more code.
+// of every 16 column pairs, how many take 2^x on the FMA pipe instead of the MUFU (swept on C3: 4)
 #ifdef TVMB200_POLY_PAIRS
 template <typename PT>
 constexpr int kPolyPairsOf = TVMB200_POLY_PAIRS;
 #else
 template <typename PT>
-constexpr int kPolyPairsOf = std::is_same<PT, __nv_bfloat16>::value ? 2 : 4;
+constexpr int kPolyPairsOf = 4;
 #endif
 
 struct SmemLayout {
   static constexpr int q = 0;
   static constexpr int kv = q + 2 * kTileBytes;
-  static constexpr int bars = kv + kSlots * kTileBytes;   // 26 mbarriers
-  static constexpr int tmem_ptr = bars + 224;
-  static constexpr int lo_flag = bars + 232;  // int[2][2]: id of the step whose P of (tile t, S half h) has a P_lo part
-  static constexpr int item = bars + 248;     // int[2]: work-item ring filled by the producer warp
-  static constexpr int scan = bars + 256;
+  static constexpr int bars = kv + kSlots * kTileBytes;   // 30 mbarriers
+  static constexpr int tmem_ptr = bars + 256;
+  static constexpr int item = bars + 280;     // int[2]: work-item ring filled by the producer warp
+  static constexpr int scan = bars + 288;
 };
 // S_FULL / P_READY / PV_DONE: one barrier per (tile, S half) = index 2 t + h.  The kernel is persistent, so every
 // barrier is used across work items: each role keeps running use counts and waits for parity (count & 1).
 enum Bar {
   Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, Q_EMPTY = 21, ITEM_FULL = 22,
-  ITEM_EMPTY = 24, NUM_BARS = 26
+  ITEM_EMPTY = 24, V_CONV = 26, NUM_BARS = 30
 };
 
 #ifdef TVMB200_TRACE
@@ -168,7 +164,10 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int B = p.batch, g = p.group;
-  constexpr bool kLoPass = std::is_same<PT, __nv_bfloat16>::value;
+  static_assert(std::is_same<PT, __half>::value, "P is fp16: bf16 inputs convert V in shared memory");
+  // bf16 inputs with fp16 P: warps 2 and 3 convert every V tile to fp16 in shared memory (exact for |v| in
+  // [2^-14, 65504], saturating above), so P keeps 11 bits without a residual pass and PV is an f16 x f16 MMA
+  constexpr bool kConvertV = !std::is_same<T, PT>::value;
   int* s_tiles = reinterpret_cast<int*>(sgen + SmemLayout::scan);
   int* s_tmp = s_tiles + B + 1;
   volatile int* s_item = reinterpret_cast<volatile int*>(sgen + SmemLayout::item);
@@ -195,6 +194,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(bar(KV_FULL + i), 1);
       mbar_init(bar(KV_EMPTY + i), 1);
+      mbar_init(bar(V_CONV + i), 2);
     }
     for (int t = 0; t < 2; ++t) {
       for (int h = 0; h < 2; ++h) {
@@ -203,9 +203,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_init(bar(PV_DONE + 2 * t + h), 1);
       }
       mbar_init(bar(ITEM_FULL + t), 1);
-      mbar_init(bar(ITEM_EMPTY + t), 9);  // the MMA warp + the eight softmax warps
+      mbar_init(bar(ITEM_EMPTY + t), kConvertV ? 11 : 9);  // the MMA warp + the eight softmax warps (+ two V converters)
     }
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * i) = 0;
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -291,21 +290,14 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc05::mma_ss_w(d, a0 + off, kmaj_hi, b0 + off, kmaj_hi, idesc_qk, s > 0);
         }
       };
-      auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc, bool with_lo) {
+      auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc) {
         const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
         const uint32_t p0 = tmem + t * 128 + half * kStep;
         const uint32_t d = tmem + 256 + t * 128;
-        // second trip = the P_lo residual pass.  A real loop on purpose: ptxas predicates an `if (with_lo)` body,
-        // and a predicated-off UTCHMMA still costs the issuing thread a full MMA slot (measured: +300 clk per group)
-        const int passes = with_lo ? 2 : 1;
-#pragma unroll 1
-        for (int ps = 0; ps < passes; ++ps) {
 #pragma unroll
-          for (int s = 0; s < kStep / 16; ++s) {
-            // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
-            tc05::mma_ts_w(d, p0 + ps * 32 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv,
-                           (acc || s > 0 || ps > 0) ? 1u : 0u);
-          }
+        for (int s = 0; s < kStep / 16; ++s) {
+          // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
+          tc05::mma_ts_w(d, p0 + s * 8, b0 + ((s * 16 * 128) >> 4), mnmaj_hi, idesc_pv, (acc || s > 0) ? 1u : 0u);
         }
       };
       uint32_t fill = 0, n_q = 0;
@@ -345,8 +337,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const uint32_t fv = fill + 2 * j + 1, fk1 = fill + 2 * j + 2;
           const int vslot = fv & (kSlots - 1), k1slot = fk1 & (kSlots - 1);
           const bool more_k = j + 1 < n_kv;
-          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
-          if (PAGED && j == n_kv - 1) {
+          mbar_wait(bar((kConvertV ? V_CONV : KV_FULL) + vslot), (fv / kSlots) & 1);
+          if (kConvertV) tc05::fence_after_sync();
+          if (PAGED && !kConvertV && j == n_kv - 1) {
             // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
             // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
             const int valid = it.kv_len - j * kKV;
@@ -371,13 +364,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               ++n_p[t][h];
               TRACE(0, s, 3 * t + 1);
               tc05::fence_after_sync();
-              // the P_lo stamp of this (tile, half) use: the softmax warps count their steps the same way
-              const int lo_id = static_cast<int>(n_p[t][h]);
-              const bool with_lo =
-                  kLoPass && *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + h)) == lo_id;
               const bool last_of_tile = h == 1 || s == nst - 1;
               if (tc05::elect_one()) {
-                issue_pv(t, vslot, h, s > 0, with_lo);
+                issue_pv(t, vslot, h, s > 0);
                 tc05::commit(bar(PV_DONE + 2 * t + h));
                 if (last_of_tile && 2 * (j + 1) < nst) {
                   issue_qk(t, k1slot);
@@ -397,6 +386,45 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           __syncwarp();
         }
         fill += 2 * n_kv;
+      }
+    } else if (kConvertV) {
+      // =========================== V converters (warps 2 and 3): bf16 -> fp16 in place ===========================
+      uint32_t fill = 0;
+      for (int k = 0;; ++k) {
+        const int islot = k & 1;
+        mbar_wait(bar(ITEM_FULL + islot), (k >> 1) & 1);
+        const int id = s_item[islot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
+        if (id >= n_items) break;
+        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        for (int j = 0; j < it.n_kv; ++j) {
+          const uint32_t fv = fill + 2 * j + 1;
+          const int vslot = fv & (kSlots - 1);
+          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
+          // warp 2 owns the first 64-column half of the tile (16 KiB), warp 3 the second; the element-wise
+          // conversion does not care about the 128B swizzle.  Rows past kv_len of a paged tile (whatever the page
+          // holds, maybe NaN bit patterns) become zeros: P is exactly 0 there but 0 * NaN = NaN.
+          uint4* half = reinterpret_cast<uint4*>(sgen + SmemLayout::kv + vslot * kTileBytes + (warp - 2) * kHalfBytes);
+          const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - j * kKV : kKV;
+#pragma unroll 4
+          for (int e = lane; e < kHalfBytes / 16; e += 32) {
+            uint4 v = half[e];
+            if ((e >> 3) < valid) {  // 8 x 16 B per 128-byte row of the half
+              v.x = tc05::bf16x2_to_f16x2_sat(v.x);
+              v.y = tc05::bf16x2_to_f16x2_sat(v.y);
+              v.z = tc05::bf16x2_to_f16x2_sat(v.z);
+              v.w = tc05::bf16x2_to_f16x2_sat(v.w);
+            } else {
+              v = make_uint4(0u, 0u, 0u, 0u);
+            }
+            half[e] = v;
+          }
+          fence_proxy_async();  // generic-proxy writes before the tensor core (async proxy) reads the tile
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(V_CONV + vslot));
+        }
+        fill += 2 * it.n_kv;
       }
     }
   } else {
@@ -478,9 +506,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
       };
-      // exp2, pack, store P (and P_lo) of one 64-column half, hand it to the MMA warp.  Scale/subtract and the row sum
+      // exp2, pack, store P of one 64-column half, hand it to the MMA warp.  Scale/subtract and the row sum
       // run as packed FFMA2 / FADD2; kPolyPairs of every 16 pairs take 2^x on the FMA pipe instead of the MUFU unit.
-      auto do_half = [&](uint32_t (&x0)[32], uint32_t (&x1)[32], int hb, float mx_half, int si) {
+      auto do_half = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32], int hb, int si) {
         const float mneg = -m_used;
         const float2 sc2 = make_float2(sc, sc), mneg2 = make_float2(mneg, mneg);
         const uint32_t t_sb = t_s + hb * kStep;
@@ -506,106 +534,54 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int c = 0; c < 32; c += 2) {
           const float2 a = exp_pair(x0[c], x0[c + 1], c >> 1);
           pk[c >> 1] = pack_p<PT>(a.x, a.y);
-          if (kLoPass) {  // keep the fp32 weights (in place of S) for a possible P_lo residual
-            x0[c] = __float_as_uint(a.x);
-            x0[c + 1] = __float_as_uint(a.y);
-          }
         }
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const float2 a = exp_pair(x1[c], x1[c + 1], c >> 1);
           pk[16 + (c >> 1)] = pack_p<PT>(a.x, a.y);
-          if (kLoPass) {
-            x1[c] = __float_as_uint(a.x);
-            x1[c + 1] = __float_as_uint(a.y);
-          }
         }
         tc05::st32(t_sb, pk);
         sum_a = tc05::fadd2(sum_a, sum_b);
         l += sum_a.x + sum_a.y;
-        if (kLoPass) {
-          // bf16 only: does some row of this warp have a weight above kLoTau of its running denominator?  The decision
-          // is per WARP (no warpgroup barrier): a warp with such a row stores the residual P_lo = P - bf16(P) of its 32
-          // rows and stamps the tile's flag with this step's id; every other warp stores zeros, so a PV_lo pass
-          // triggered by another warp adds nothing for its rows.  The MMA warp runs the second pass iff the flag
-          // carries the id of the step it issues.
-          const float p_max = fast_exp2(fmaf(mx_half, sc, mneg));
-          if (__any_sync(0xffffffffu, p_max > kLoTau * l)) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float2 h0 = DT<PT>::to_f2(pk[c >> 1]), h1 = DT<PT>::to_f2(pk[16 + (c >> 1)]);
-              pk[c >> 1] = pack_p<PT>(__uint_as_float(x0[c]) - h0.x, __uint_as_float(x0[c + 1]) - h0.y);
-              pk[16 + (c >> 1)] = pack_p<PT>(__uint_as_float(x1[c]) - h1.x, __uint_as_float(x1[c + 1]) - h1.y);
-            }
-            if (lane == 0)
-              *reinterpret_cast<volatile int*>(sgen + SmemLayout::lo_flag + 4 * (2 * t + hb)) = static_cast<int>(n_p[hb]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) pk[c] = 0u;
-          }
-          tc05::st32(t_sb + 32, pk);
-        }
         if (wq == 0) TRACE(1 + t, si, 5);
         tc05::wait_st();
         tc05::fence_before_sync();
         mbar_arrive(bar(P_READY + 2 * t + hb));
         if (wq == 0) TRACE(1 + t, si, 3);
       };
-      if constexpr (!kLoPass) {
-        // fp16: one iteration = one KV tile (128 columns): all S values are loaded and reduced to ONE row maximum /
-        // rescale decision, then the two 64-column halves are exponentiated, packed and handed over one after the
-        // other, so PV of the lower half runs while the upper half is still in the exp2 phase (-4 % time).
-        const int my_tiles = (my_ns + 1) >> 1;
-        for (int j = 0; j < my_tiles; ++j) {
-          const bool has_b = 2 * j + 1 < my_ns;       // upper half visible to some row of the tile (CTA-uniform)
-          if (wq == 0) TRACE(1 + t, 2 * j, 0);
-          mbar_wait(bar(S_FULL + 2 * t), n_s & 1);
-          if (has_b) mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);
-          ++n_s;
-          if (wq == 0) TRACE(1 + t, 2 * j, 1);
-          tc05::fence_after_sync();
-          uint32_t sa0[32], sa1[32], sb0[32], sb1[32];
-          tc05::ld32(t_s + 0, sa0);
-          tc05::ld32(t_s + 32, sa1);
-          if (has_b) {
-            tc05::ld32(t_s + 64, sb0);
-            tc05::ld32(t_s + 96, sb1);
-          }
-          tc05::wait_ld();
-          if (wq == 0) TRACE(1 + t, 2 * j, 2);
-          const int rem_a = limit - 2 * j * kStep;
-          mask_half(sa0, sa1, rem_a);
-          const float mx_a = half_max(sa0, sa1);
-          float mx_b = -INFINITY;
-          if (has_b) {
-            mask_half(sb0, sb1, rem_a - kStep);
-            mx_b = half_max(sb0, sb1);
-          }
-          if (wq == 0) TRACE(1 + t, 2 * j, 4);
-          rescale(fmaxf(mx_a, mx_b), j > 0 ? 1 : -1);  // the last PV of KV tile j-1 is its upper half
-          do_half(sa0, sa1, 0, mx_a, 2 * j);
-          if (has_b) do_half(sb0, sb1, 1, mx_b, 2 * j + 1);
+      // One iteration = one KV tile (128 columns): all S values are loaded and reduced to ONE row maximum /
+      // rescale decision, then the two 64-column halves are exponentiated, packed and handed over one after the
+      // other, so PV of the lower half runs while the upper half is still in the exp2 phase (-4 % time).
+      const int my_tiles = (my_ns + 1) >> 1;
+      for (int j = 0; j < my_tiles; ++j) {
+        const bool has_b = 2 * j + 1 < my_ns;       // upper half visible to some row of the tile (CTA-uniform)
+        if (wq == 0) TRACE(1 + t, 2 * j, 0);
+        mbar_wait(bar(S_FULL + 2 * t), n_s & 1);
+        if (has_b) mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);
+        ++n_s;
+        if (wq == 0) TRACE(1 + t, 2 * j, 1);
+        tc05::fence_after_sync();
+        uint32_t sa0[32], sa1[32], sb0[32], sb1[32];
+        tc05::ld32(t_s + 0, sa0);
+        tc05::ld32(t_s + 32, sa1);
+        if (has_b) {
+          tc05::ld32(t_s + 64, sb0);
+          tc05::ld32(t_s + 96, sb1);
         }
-      } else {
-        // bf16: 64-column steps (the wide iteration plus the P_lo words does not fit the register budget: 953 -> 913)
-        for (int s = 0; s < my_ns; ++s) {
-          const int hb = s & 1;                       // S half of this step
-          if (wq == 0) TRACE(1 + t, s, 0);
-          mbar_wait(bar(S_FULL + 2 * t + hb), n_s & 1);
-          if (hb == 1 || s == my_ns - 1) ++n_s;       // this KV tile's S is consumed with this step
-          if (wq == 0) TRACE(1 + t, s, 1);
-          tc05::fence_after_sync();
-          uint32_t s0[32], s1[32];
-          tc05::ld32(t_s + hb * kStep, s0);
-          tc05::ld32(t_s + hb * kStep + 32, s1);
-          tc05::wait_ld();
-          if (wq == 0) TRACE(1 + t, s, 2);
-          mask_half(s0, s1, limit - s * kStep);
-          const float mx = half_max(s0, s1);
-          if (wq == 0) TRACE(1 + t, s, 4);
-          rescale(mx, s > 0 ? ((s - 1) & 1) : -1);
-          do_half(s0, s1, hb, mx, s);
+        tc05::wait_ld();
+        if (wq == 0) TRACE(1 + t, 2 * j, 2);
+        const int rem_a = limit - 2 * j * kStep;
+        mask_half(sa0, sa1, rem_a);
+        const float mx_a = half_max(sa0, sa1);
+        float mx_b = -INFINITY;
+        if (has_b) {
+          mask_half(sb0, sb1, rem_a - kStep);
+          mx_b = half_max(sb0, sb1);
         }
+        if (wq == 0) TRACE(1 + t, 2 * j, 4);
+        rescale(fmaxf(mx_a, mx_b), j > 0 ? 1 : -1);  // the last PV of KV tile j-1 is its upper half
+        do_half(sa0, sa1, 0, 2 * j);
+        if (has_b) do_half(sb0, sb1, 1, 2 * j + 1);
       }
       // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
       T* orow = nullptr;
@@ -702,7 +678,8 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
   const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
-  const uint32_t idesc_pv = tc05::make_idesc(fp, fa, 0, 1, kRows, kD);
+  // V is converted to the P format in shared memory when the two differ (bf16 inputs, fp16 P)
+  const uint32_t idesc_pv = tc05::make_idesc(fp, fp, 0, 1, kRows, kD);
   int* counter = nullptr;
   if (int rc = get_work_counter(&counter)) return rc;
   // the kernel resets the counter with its last fetch; the memset only matters after an aborted launch
@@ -730,8 +707,8 @@ int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int
   if (dtype == TVMB200_F16)
     return paged ? launch_tc05_t<__half, __half, true>(p, tq, tk, tv, total_q_len, st)
                  : launch_tc05_t<__half, __half, false>(p, tq, tk, tv, total_q_len, st);
-  return paged ? launch_tc05_t<__nv_bfloat16, __nv_bfloat16, true>(p, tq, tk, tv, total_q_len, st)
-               : launch_tc05_t<__nv_bfloat16, __nv_bfloat16, false>(p, tq, tk, tv, total_q_len, st);
+  return paged ? launch_tc05_t<__nv_bfloat16, __half, true>(p, tq, tk, tv, total_q_len, st)
+               : launch_tc05_t<__nv_bfloat16, __half, false>(p, tq, tk, tv, total_q_len, st);
 }
 
 }  // namespace tvmb200

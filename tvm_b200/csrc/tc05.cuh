@@ -190,6 +190,13 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
+// two bf16 (one 32-bit word) -> two fp16, round to nearest, saturating to +-65504 (bf16 has the wider exponent range)
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2_sat(uint32_t u) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(u & 0xffff0000u)), "f"(__uint_as_float(u << 16)));
+  return d;
+}
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
