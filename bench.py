@@ -38,7 +38,7 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant kernel on the named workload,
 # from the committed `ncu --set full` captures under profiles/ (a profiler number: reported next to the algorithmic
 # bytes, never used for timing)
-NCU_DRAM_BYTES = {"decode_c2": 1074441000 + 6551808, "prefill_c3": 402782208 + 221668096}
+NCU_DRAM_BYTES = {"decode_c2": 1074441000 + 6551808, "prefill_c3": 402785280 + 220196864}
 
 
 def measured_peaks():
@@ -422,7 +422,7 @@ def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
                       "0.67 GB > L2"},
            "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(tf / peak, 4), "traffic": NCU_DRAM_BYTES["prefill_c3"],
-                        "traffic_source": "profiles/r1_prefill_tc05_v3_ncu.md: dram read+write of one launch (bytes)",
+                        "traffic_source": "profiles/r1_prefill_tc05_v6_ncu.md: dram read+write of one launch (bytes)",
                         "peak_source": f"of {peak_src} (burst; sustained " + str(peaks.get("bf16_tflops_sustained")) + ")",
                         "frac_of_sustained": (round(tf / float(peaks["bf16_tflops_sustained"]), 4)
                                               if peaks.get("bf16_tflops_sustained") else None),

@@ -59,6 +59,57 @@ def test_tc05_paged(tc05, dtype, causal):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("causal", [1, 0])
+def test_tc05_work_queue_many_ragged_items(tc05, dtype, causal):
+    """The persistent kernel walks a device-wide work queue with barriers reused across items: far more items than
+    SMs, of wildly different lengths, including empty sequences, sequences without any visible KV tile and items whose
+    second Q tile is absent -- every row against the oracle."""
+    rng = np.random.default_rng(47)
+    B = 150
+    q_lens = [int(x) for x in rng.integers(0, 200, B)]
+    q_lens[3] = 0
+    q_lens[10] = 1
+    q_lens[20] = 64
+    q_lens[21] = 65
+    kv_lens = [q + int(rng.integers(0, 300)) for q in q_lens]
+    if not causal:
+        kv_lens[5] = 0          # no KV at all: O = 0, LSE = -5e4
+    _run_ragged(tc05, rng, q_lens, kv_lens, 8, 2, 128, dtype, causal=causal)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tc05_work_queue_paged_many_items(tc05, dtype):
+    rng = np.random.default_rng(48)
+    B = 100
+    q_lens = [int(x) for x in rng.integers(1, 150, B)]
+    kv_lens = [int(x) for x in rng.integers(0, 400, B)]
+    _run_paged_prefill(tc05, rng, q_lens, kv_lens, 8, 2, 128, dtype, causal=0)
+
+
+def test_tc05_back_to_back_launches_reuse_the_work_counter(tc05):
+    """The kernel must leave its work counter at zero: 20 launches in a row (no host sync in between) all agree."""
+    import torch
+
+    torch.manual_seed(1)
+    n, hq, hkv, d = 3000, 8, 2, 128
+    q = torch.randn(n, hq, d, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(n, hkv, d, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(n, hkv, d, device="cuda", dtype=torch.bfloat16)
+    ip = torch.tensor([0, 700, 701, 2000, 3000], dtype=torch.int32, device="cuda")
+    qpos = torch.zeros(n, dtype=torch.int32, device="cuda")
+    kofs = torch.zeros(4, dtype=torch.int32, device="cuda")
+    outs = []
+    for _ in range(20):
+        o = torch.empty_like(q)
+        lse = torch.empty(n, hq, device="cuda", dtype=torch.float32)
+        tc05.attention_prefill_ragged(q, ip, k, v, ip, qpos, kofs, o, lse, 1, 0, 1.0, 1e4, d ** -0.5)
+        outs.append((o, lse))
+    torch.cuda.synchronize()
+    for o, lse in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(lse, outs[0][1])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_tc05_paged_uninitialised_tail(tc05, dtype):
     """Slots past kv_len in the last page hold NaN bit patterns (torch.empty-like pools): output must stay finite."""
     rng = np.random.default_rng(45)
