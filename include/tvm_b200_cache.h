@@ -90,6 +90,16 @@ TVMB200_API int tvmb200_cache_attention_with_fused_qkv(tvmb200_cache_t c, int64_
 TVMB200_API int tvmb200_cache_debug_get_kv(tvmb200_cache_t c, int64_t seq_id, int64_t start_pos, int64_t end_pos,
                                            void* k_out, void* v_out, tvmb200_stream_t stream);
 
+/*!
+ * \brief Register the cache under the Relax VM's global function names (`vm.builtin.paged_attention_kv_cache_create`,
+ *  `vm.builtin.kv_state_*`, `vm.builtin.attention_kv_cache_*`: src/runtime/vm/kv_state.cc:33-116,
+ *  paged_kv_cache.cc:2535-2639) in the tvm-ffi global table of this process, so that a compiled Relax / MLC model,
+ *  which calls them by name, runs on tvm_b200's cache and kernels unmodified.  allow_override != 0 replaces the
+ *  reference's own registrations when libtvm_runtime is loaded too.  Returns the number of names registered, < 0 on
+ *  error (libtvm_ffi.so not loaded, or a name exists and allow_override == 0).
+ */
+TVMB200_API int tvmb200_register_vm_builtins(int allow_override);
+
 /* ---- introspection (parity tests, integration glue) ---- */
 /*! \brief device pointer of pages_[local_layer]: [num_total_pages, 2, Hkv, page, D]. */
 TVMB200_API int tvmb200_cache_pages(tvmb200_cache_t c, int64_t local_layer, void** dev_ptr, int64_t* num_total_pages);

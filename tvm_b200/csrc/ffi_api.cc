@@ -18,8 +18,10 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/tvm_b200.h"
+#include "../../include/tvm_b200_cache.h"
 
 namespace tvmb200 {
 int32_t layer_sliding_window_size();
@@ -598,6 +600,351 @@ int impl_launch_count(const TVMFFIAny*, int32_t, TVMFFIAny* result) {
   return 0;
 }
 
+
+// =====================================================================================================
+// the host cache under the Relax VM's own global names.  A compiled model calls
+// `vm.builtin.paged_attention_kv_cache_create` and the `vm.builtin.kv_state_*` / `attention_kv_cache_*` functions BY
+// NAME (src/runtime/vm/kv_state.cc:33-116, paged_kv_cache.cc:2535-2639; callers python/tvm/relax/frontend/nn/llm/
+// kv_cache.py:124-351); register_vm_builtins() re-registers those names onto tvm_b200's cache (kv_cache_host.cc), so the
+// unmodified model runs on the sm_100a kernels.  The cache travels through the VM registers as an opaque pointer; the
+// callback arguments of the constructor (13..27) are accepted and ignored.  Unsupported entries (MLA, disaggregation,
+// cross / shared-KV attention) are registered too and raise.
+// =====================================================================================================
+tvmb200_cache_t arg_cache(const TVMFFIAny* args, int i, const char* fn) {
+  if (args[i].type_index != kTVMFFIOpaquePtr || args[i].v_ptr == nullptr)
+    throw Err{"TypeError", fmt("%s: argument %d must be the cache returned by vm.builtin.paged_attention_kv_cache_create "
+                               "of tvm_b200 (got type index %d)", fn, i, args[i].type_index)};
+  return static_cast<tvmb200_cache_t>(args[i].v_ptr);
+}
+
+struct ShapeView {
+  const int64_t* data = nullptr;
+  int64_t size = 0;
+  int64_t operator[](int64_t i) const { return data[i]; }
+};
+
+ShapeView arg_shape(const TVMFFIAny* args, int i, const char* fn, const char* name) {
+  if (args[i].type_index != kTVMFFIShape)
+    throw Err{"TypeError", fmt("%s: argument %d (%s) must be a Shape, got type index %d", fn, i, name, args[i].type_index)};
+  const TVMFFIShapeCell* c = TVMFFIShapeGetCellPtr(args[i].v_obj);
+  return ShapeView{c->data, static_cast<int64_t>(c->size)};
+}
+
+void cache_rc(int rc) {
+  if (rc != 0) throw Err{"RuntimeError", tvmb200_last_error()};
+}
+
+void ret_int(TVMFFIAny* result, int64_t v) {
+  result->type_index = kTVMFFIInt;
+  result->zero_padding = 0;
+  result->v_int64 = v;
+}
+
+#define TVMB200_VM_BEGIN() try {
+#define TVMB200_VM_END()                       \
+    return 0;                                  \
+  } catch (const Err& e) {                     \
+    return raise(e.kind.c_str(), e.msg);       \
+  } catch (const std::exception& e) {          \
+    return raise("RuntimeError", e.what());    \
+  }
+#define TVMB200_VM_NONE() do { result->type_index = kTVMFFINone; result->zero_padding = 0; result->v_int64 = 0; } while (0)
+
+int vm_create(void*, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.paged_attention_kv_cache_create";
+  TVMB200_VM_BEGIN();
+  if (n != 28 && n != 29) throw Err{"TypeError", fmt("%s expects 28 or 29 arguments, got %d", fn, n)};
+  const ShapeView cfg = arg_shape(args, 0, fn, "cache_config"), li = arg_shape(args, 1, fn, "layer_indptr");
+  if (cfg.size != 5 && cfg.size != 6) throw Err{"ValueError", fmt("%s: cache_config must have 5 or 6 entries", fn)};
+  if (li.size < 2) throw Err{"ValueError", fmt("%s: layer_indptr needs at least two entries", fn)};
+  const int64_t hq = arg_int(args, 2, fn, "num_qo_heads"), hkv = arg_int(args, 3, fn, "num_kv_heads");
+  const int64_t d_qk = arg_int(args, 4, fn, "qk_head_dim"), d_v = arg_int(args, 5, fn, "v_head_dim");
+  if (d_qk != d_v) throw Err{"ValueError", fmt("%s: qk_head_dim %ld != v_head_dim %ld (MLA is outside this hot path)", fn, (long)d_qk, (long)d_v)};
+  const ShapeView kinds = arg_shape(args, 6, fn, "attn_kinds");
+  if (arg_int(args, 7, fn, "enable_kv_transfer") != 0)
+    throw Err{"ValueError", fmt("%s: enable_kv_transfer (NVSHMEM disaggregation) is not supported", fn)};
+  if (args[11].type_index != kTVMFFINone)
+    throw Err{"ValueError", fmt("%s: rope_ext_factors (longrope) is not supported", fn)};
+  const Tensor init = arg_tensor(args, 12, fn, "init");
+  if (init.t->device.device_type != kDLCUDA) throw Err{"ValueError", fmt("%s: the cache lives on a CUDA device; there is no CPU fallback", fn)};
+  std::vector<int32_t> kinds32(kinds.size);
+  for (int64_t i = 0; i < kinds.size; ++i) kinds32[i] = static_cast<int32_t>(kinds[i]);
+  tvmb200_cache_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.reserved_num_seqs = cfg[0];
+  c.total_token_capacity = cfg[1];
+  c.prefill_chunk_size = cfg[2];
+  c.page_size = cfg[3];
+  c.support_sliding_window = static_cast<int32_t>(cfg[4]);
+  c.layer_sliding_window_size = cfg.size == 6 ? cfg[5] : 0;
+  c.layer_id_begin_offset = li[0];  // worker group 0 (single pipeline stage)
+  c.num_layers = li[1] - li[0];
+  c.num_qo_heads = hq;
+  c.num_kv_heads = hkv;
+  c.head_dim = d_qk;
+  c.attn_kinds = kinds32.empty() ? nullptr : kinds32.data();
+  c.rope_mode = static_cast<int32_t>(arg_int(args, 8, fn, "rope_mode"));
+  c.rotary_scale = arg_float(args, 9, fn, "rotary_scale");
+  c.rotary_theta = arg_float(args, 10, fn, "rotary_theta");
+  c.dtype = kv_dtype(init, fn, "init");
+  c.device_id = init.t->device.device_id;
+  tvmb200_cache_t cache = nullptr;
+  cache_rc(tvmb200_cache_create(&c, &cache));
+  result->type_index = kTVMFFIOpaquePtr;
+  result->zero_padding = 0;
+  result->v_ptr = cache;
+  TVMB200_VM_END();
+}
+
+int vm_clear(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_clear";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  cache_rc(tvmb200_cache_clear(arg_cache(a, 0, fn)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_add_sequence(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_add_sequence";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 2, fn);
+  cache_rc(tvmb200_cache_add_sequence(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id")));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_remove_sequence(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_remove_sequence";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 2, fn);
+  cache_rc(tvmb200_cache_remove_sequence(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id")));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_fork_sequence(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_fork_sequence";
+  TVMB200_VM_BEGIN();
+  if (n != 3 && n != 4) throw Err{"TypeError", fmt("%s expects (cache, parent, child[, fork_pos])", fn)};
+  cache_rc(tvmb200_cache_fork_sequence(arg_cache(a, 0, fn), arg_int(a, 1, fn, "parent_seq_id"),
+                                       arg_int(a, 2, fn, "child_seq_id"), n == 4 ? arg_int(a, 3, fn, "fork_pos") : -1));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_popn(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_popn";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 3, fn);
+  cache_rc(tvmb200_cache_popn(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id"), static_cast<int32_t>(arg_int(a, 2, fn, "n"))));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_begin_forward(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_begin_forward";
+  TVMB200_VM_BEGIN();
+  if (n != 3 && n != 4) throw Err{"TypeError", "KVState BeginForward only accepts 3 or 4 arguments"};
+  const ShapeView ids = arg_shape(a, 1, fn, "seq_ids"), lens = arg_shape(a, 2, fn, "append_lengths");
+  if (ids.size != lens.size) throw Err{"ValueError", fmt("%s: seq_ids and append_lengths differ in length", fn)};
+  ShapeView tree;
+  if (n == 4 && a[3].type_index != kTVMFFINone) tree = arg_shape(a, 3, fn, "token_tree_parent_ptr");
+  cache_rc(tvmb200_cache_begin_forward(arg_cache(a, 0, fn), ids.data, lens.data, static_cast<int32_t>(ids.size),
+                                       tree.data, static_cast<int32_t>(tree.size)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_end_forward(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_state_end_forward";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  cache_rc(tvmb200_cache_end_forward(arg_cache(a, 0, fn)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_enable_sliding_window(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_enable_sliding_window_for_seq";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 4, fn);
+  cache_rc(tvmb200_cache_enable_sliding_window_for_seq(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id"),
+                                                       static_cast<int32_t>(arg_int(a, 2, fn, "sliding_window_size")),
+                                                       static_cast<int32_t>(arg_int(a, 3, fn, "attn_sink_size"))));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_commit_tree_nodes(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_commit_accepted_token_tree_nodes";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 3, fn);
+  const ShapeView ids = arg_shape(a, 1, fn, "seq_ids"), leaves = arg_shape(a, 2, fn, "leaf_indices");
+  if (ids.size != leaves.size) throw Err{"ValueError", fmt("%s: seq_ids and leaf_indices differ in length", fn)};
+  cache_rc(tvmb200_cache_commit_accepted_token_tree_nodes(arg_cache(a, 0, fn), ids.data, leaves.data, static_cast<int32_t>(ids.size)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_empty(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_empty";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  int32_t v = 0;
+  cache_rc(tvmb200_cache_empty(arg_cache(a, 0, fn), &v));
+  result->type_index = kTVMFFIBool;
+  result->zero_padding = 0;
+  result->v_int64 = v != 0;
+  TVMB200_VM_END();
+}
+int vm_num_available_pages(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_get_num_available_pages";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  int32_t v = 0;
+  cache_rc(tvmb200_cache_get_num_available_pages(arg_cache(a, 0, fn), &v));
+  ret_int(result, v);
+  TVMB200_VM_END();
+}
+int vm_total_sequence_length(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_get_total_sequence_length";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  int32_t v = 0;
+  cache_rc(tvmb200_cache_get_total_sequence_length(arg_cache(a, 0, fn), &v));
+  ret_int(result, v);
+  TVMB200_VM_END();
+}
+
+// a Tensor view of q_rope_position_map (valid until the next begin_forward), as GetQueryPositions returns
+struct PosView {
+  DLManagedTensor m;
+  int64_t shape[1];
+};
+void pos_view_deleter(DLManagedTensor* m) { delete reinterpret_cast<PosView*>(m->manager_ctx); }
+
+int vm_query_positions(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_get_query_positions";
+  typedef int (*PFN_FromDLPack)(DLManagedTensor*, int32_t, int32_t, TVMFFIObjectHandle*);
+  static PFN_FromDLPack from_dlpack = reinterpret_cast<PFN_FromDLPack>(ffi_sym("TVMFFITensorFromDLPack"));
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 1, fn);
+  if (!from_dlpack) throw Err{"RuntimeError", "libtvm_ffi.so (TVMFFITensorFromDLPack) is not loaded"};
+  tvmb200_cache_t c = arg_cache(a, 0, fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int32_t* ptr = nullptr;
+  int64_t len = 0;
+  cache_rc(tvmb200_cache_get_query_positions(c, &ptr, &len, env_stream(dev)));
+  PosView* v = new PosView();
+  v->shape[0] = len;
+  v->m.dl_tensor.data = const_cast<int32_t*>(ptr);
+  v->m.dl_tensor.device = DLDevice{kDLCUDA, dev};
+  v->m.dl_tensor.ndim = 1;
+  v->m.dl_tensor.dtype = DLDataType{kDLInt, 32, 1};
+  v->m.dl_tensor.shape = v->shape;
+  v->m.dl_tensor.strides = nullptr;
+  v->m.dl_tensor.byte_offset = 0;
+  v->m.manager_ctx = v;
+  v->m.deleter = pos_view_deleter;
+  TVMFFIObjectHandle h = nullptr;
+  if (from_dlpack(&v->m, 0, 0, &h) != 0) return -1;  // error already raised by tvm-ffi
+  result->type_index = kTVMFFITensor;
+  result->zero_padding = 0;
+  result->v_obj = static_cast<TVMFFIObject*>(h);
+  TVMB200_VM_END();
+}
+int vm_debug_get_kv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_debug_get_kv";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 6, fn);
+  const Tensor k = arg_tensor(a, 4, fn, "k_data"), v = arg_tensor(a, 5, fn, "v_data");
+  cache_rc(tvmb200_cache_debug_get_kv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id"), arg_int(a, 2, fn, "start_pos"),
+                                      arg_int(a, 3, fn, "end_pos"), k.data, v.data, env_stream(k.t->device.device_id)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_attention_with_fused_qkv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_attention_with_fused_qkv";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 5, fn);
+  const Tensor qkv = arg_tensor(a, 3, fn, "qkv_data"), o = arg_tensor(a, 4, fn, "o_data");
+  if (qkv.t->device.device_type != kDLCUDA || o.t->device.device_type != kDLCUDA)
+    throw Err{"ValueError", fmt("%s: qkv_data / o_data must be CUDA tensors (there is no CPU fallback)", fn)};
+  if (qkv.ndim() != 3 || o.ndim() != 3) throw Err{"ValueError", fmt("%s: qkv_data and o_data must be 3-D", fn)};
+  (void)kv_dtype(qkv, fn, "qkv_data");
+  cache_rc(tvmb200_cache_attention_with_fused_qkv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+                                                  qkv.data, o.data, qkv.shape(0), env_stream(qkv.t->device.device_id)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_unsupported(void*, const TVMFFIAny*, int32_t, TVMFFIAny*) {
+  return raise("RuntimeError", "tvm_b200: this vm.builtin KV-cache entry (MLA / disaggregation / cross or shared-KV attention) is "
+                               "outside the PagedKVCache MHA hot path and is not implemented");
+}
+
+struct VmBuiltin {
+  const char* name;
+  TVMFFISafeCallType fn;
+};
+const VmBuiltin kVmBuiltins[] = {
+    {"vm.builtin.paged_attention_kv_cache_create", vm_create},
+    {"vm.builtin.kv_state_clear", vm_clear},
+    {"vm.builtin.kv_state_add_sequence", vm_add_sequence},
+    {"vm.builtin.kv_state_remove_sequence", vm_remove_sequence},
+    {"vm.builtin.kv_state_fork_sequence", vm_fork_sequence},
+    {"vm.builtin.kv_state_popn", vm_popn},
+    {"vm.builtin.kv_state_begin_forward", vm_begin_forward},
+    {"vm.builtin.kv_state_end_forward", vm_end_forward},
+    {"vm.builtin.attention_kv_cache_enable_sliding_window_for_seq", vm_enable_sliding_window},
+    {"vm.builtin.attention_kv_cache_commit_accepted_token_tree_nodes", vm_commit_tree_nodes},
+    {"vm.builtin.attention_kv_cache_empty", vm_empty},
+    {"vm.builtin.attention_kv_cache_get_num_available_pages", vm_num_available_pages},
+    {"vm.builtin.attention_kv_cache_get_total_sequence_length", vm_total_sequence_length},
+    {"vm.builtin.attention_kv_cache_get_query_positions", vm_query_positions},
+    {"vm.builtin.attention_kv_cache_debug_get_kv", vm_debug_get_kv},
+    {"vm.builtin.attention_kv_cache_attention_with_fused_qkv", vm_attention_with_fused_qkv},
+    {"vm.builtin.kv_cache_disagg_prepare_recv", vm_unsupported},
+    {"vm.builtin.kv_cache_disagg_mark_send", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_debug_get_kv_mla", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_self_attention", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_cross_attention", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_attention_with_shared_kv", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_append_mla_kv", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_merge_attn_output_inplace", vm_unsupported},
+};
+
+// (allow_override) -> number of names registered
+int impl_register_vm_builtins(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "register_vm_builtins";
+  TVMB200_VM_BEGIN();
+  if (n > 1) throw Err{"TypeError", "register_vm_builtins expects ([allow_override = 1])"};
+  const int allow = n == 1 ? static_cast<int>(arg_int(args, 0, fn, "allow_override")) : 1;
+  const int rc = tvmb200_register_vm_builtins(allow);
+  if (rc < 0) return -1;
+  ret_int(result, rc);
+  TVMB200_VM_END();
+}
+
+}  // namespace
+
+extern "C" int tvmb200_register_vm_builtins(int allow_override) {
+  typedef int (*PFN_Create)(void*, TVMFFISafeCallType, void (*)(void*), TVMFFIObjectHandle*);
+  typedef int (*PFN_SetGlobal)(const TVMFFIByteArray*, TVMFFIObjectHandle, int);
+  typedef int (*PFN_DecRef)(TVMFFIObjectHandle);
+  static PFN_Create create = reinterpret_cast<PFN_Create>(ffi_sym("TVMFFIFunctionCreate"));
+  static PFN_SetGlobal set_global = reinterpret_cast<PFN_SetGlobal>(ffi_sym("TVMFFIFunctionSetGlobal"));
+  static PFN_DecRef dec_ref = reinterpret_cast<PFN_DecRef>(ffi_sym("TVMFFIObjectDecRef"));
+  if (!create || !set_global || !dec_ref) {
+    raise("RuntimeError", "tvmb200_register_vm_builtins: libtvm_ffi.so is not loaded in this process");
+    return -1;
+  }
+  int count = 0;
+  for (const VmBuiltin& b : kVmBuiltins) {
+    TVMFFIObjectHandle f = nullptr;
+    if (create(nullptr, b.fn, nullptr, &f) != 0) return -1;
+    const TVMFFIByteArray name{b.name, std::strlen(b.name)};
+    const int rc = set_global(&name, f, allow_override);
+    dec_ref(f);
+    if (rc != 0) return -1;
+    ++count;
+  }
+  return count;
+}
+
+namespace {
 }  // namespace
 
 #define TVMB200_EXPORT(name, impl)                                                                      \
@@ -639,3 +986,4 @@ TVMB200_EXPORT(compact_kv_copy, impl_compact_kv_copy)
 TVMB200_EXPORT(set_rope_params, impl_set_rope_params)
 TVMB200_EXPORT(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)
 TVMB200_EXPORT(launch_count, impl_launch_count)
+TVMB200_EXPORT(register_vm_builtins, impl_register_vm_builtins)
