@@ -268,24 +268,30 @@ def run_own(args):
     if world > 1:
         dist.barrier()
     K = args.steps
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
-    ev_end = torch.cuda.Event(enable_timing=True)
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = capi.launch_count()
+    # pass 1 -- the timed region of `value`: exactly K steps, nothing but the step's own launches on the stream (an
+    # event recorded between the kernels would break their programmatic dependent launch and cost ~10 us per step)
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
-        ev[0].record()
-        for i in range(K):
-            w.run_rotary_append(capi)
-            ev[2 * i + 1].record()
-            w.run_decode(capi)
-            ev[2 * i + 2].record()
-        ev_end.record()
+        e_beg.record()
+        for _ in range(K):
+            step()
+        e_end.record()
         torch.cuda.synchronize()
     launches = capi.launch_count() - n0
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev_end)
-    decode_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(K)) / K
+    total_ms = e_beg.elapsed_time(e_end)
+    # pass 2 -- roofline of the dominant kernel: the same K steps with CUDA events around every decode launch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
+    for i in range(K):
+        w.run_rotary_append(capi)
+        ev[2 * i].record()
+        w.run_decode(capi)
+        ev[2 * i + 1].record()
+    torch.cuda.synchronize()
+    decode_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(K)) / K
     if world > 1:
         t = torch.tensor([total_ms, decode_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

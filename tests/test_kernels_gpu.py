@@ -219,6 +219,52 @@ def test_decode_batch64(capi, dtype):
     _run_decode(capi, rng, list(rng.integers(1, 700, 64)), 32, 8, 128, dtype)
 
 
+def test_decode_step_is_cuda_graph_capturable(capi):
+    """the per-layer sequence (fused rotary + append, split-KV decode, merge -- the last two launched as
+    programmatic dependents) captured into one CUDA graph and replayed gives the eager result bit for bit; nothing in
+    the path allocates or synchronises once the workspace is sized."""
+    import torch
+
+    rng = np.random.default_rng(17)
+    dtype, hq, hkv, d = "bfloat16", 32, 8, 128
+    kv_lens = [4096, 17, 2000, 900]
+    B = len(kv_lens)
+    c = make_paged_cache(rng, kv_lens, hkv, d, dtype)
+    pages = to_dev(c["pages"], dtype)
+    qkv = to_dev(rand16(rng, (B, hq + 2 * hkv, d), dtype), dtype)
+    qpos = _i32(np.array(kv_lens, np.int32) - 1)
+    slots = _i32(np.array([int(c["page_values"][c["page_indptr"][b + 1] - 1]) * 16 + (kv_lens[b] - 1) % 16
+                           for b in range(B)], np.int32))
+    kofs = _i32(np.zeros(B, np.int32))
+    ip, pv, li = _i32(c["page_indptr"]), _i32(c["page_values"]), _i32(c["length_info"])
+    tdt = qkv.dtype
+    q = torch.empty((B, hq, d), dtype=tdt, device="cuda")
+    k = torch.empty((B, hkv, d), dtype=tdt, device="cuda")
+    v = torch.empty((B, hkv, d), dtype=tdt, device="cuda")
+    o = torch.empty((B, hq, d), dtype=tdt, device="cuda")
+    lse = torch.empty((B, hq), dtype=torch.float32, device="cuda")
+
+    def step():
+        capi.split_rotary_append(qkv, qpos, slots, q, k, v, pages, 1, 1.0, 5e5)
+        capi.attention_decode(q, pages, ip, pv, li, kofs, qpos, o, lse, 0, 1.0, 5e5, d ** -0.5)
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        step()  # sizes the workspace outside the capture
+        torch.cuda.synchronize()
+        want_o, want_lse = o.clone(), lse.clone()
+        o.zero_()
+        lse.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            step()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o, want_o) and torch.equal(lse, want_lse)
+
+
 @pytest.mark.parametrize("kv_lens", [[11, 70, 300, 0, 16], [8192, 3, 4097]])
 def test_decode_gather_single_rank(capi, kv_lens):
     """tvmb200_attention_decode_gather with world = 1 (this rank is its own peer): the gathered buffer, the local
