@@ -366,25 +366,49 @@ def run_e2e(args, w, world, dist=None):
             left -= n
     torch.cuda.synchronize()
     seq_ids, ones = list(range(B)), [1] * B
-    d_qkv = torch.empty_like(w.qkv)
+    # Host buffers in, host buffers out, every step -- pipelined the way a serving loop would: the pinned-host -> device
+    # copy of step i+1's qkv and the device -> pinned-host copy of step i's O run on a copy stream while step i / i+1
+    # compute; two device buffers each, events for the hand-offs.  All copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    d_qkv = [torch.empty_like(w.qkv) for _ in range(2)]
+    d_o = [torch.empty_like(w.o) for _ in range(2)]
     h_out = torch.empty(w.o.shape, dtype=torch.bfloat16).pin_memory()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]   # compute of the step that last used buffer pair i is done
 
-    def step():
-        cache.begin_forward(seq_ids, ones)
-        d_qkv.copy_(w.h_qkv, non_blocking=True)
-        cache.attention_with_fused_qkv(0, w.sm_scale, d_qkv, w.o)
-        h_out.copy_(w.o, non_blocking=True)
-        cache.end_forward()
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[i & 1])
+            d_qkv[i & 1].copy_(w.h_qkv, non_blocking=True)
+            ev_in[i & 1].record(copy_stream)
 
-    for _ in range(3):  # context is now L + 2 after warm-up; every timed step appends one more token per sequence
-        step()
+    def run_steps(n, first):
+        upload(first)
+        for i in range(first, first + n):
+            if i + 1 < first + n:
+                upload(i + 1)
+            cache.begin_forward(seq_ids, ones)
+            main.wait_event(ev_in[i & 1])
+            cache.attention_with_fused_qkv(0, w.sm_scale, d_qkv[i & 1], d_o[i & 1])
+            ev_out[i & 1].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_out[i & 1])
+                h_out.copy_(d_o[i & 1], non_blocking=True)
+                ev_free[i & 1].record(copy_stream)
+            cache.end_forward()
+
+    for e in ev_free:
+        e.record(main)
+    run_steps(3, 0)  # context is now L + 2 after warm-up; every timed step appends one more token per sequence
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        step()
+    run_steps(K, 3)
+    main.wait_stream(copy_stream)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
@@ -399,7 +423,8 @@ def run_e2e(args, w, world, dist=None):
     return {"value": round(world * (w.step_bytes() + extra_kv) / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
             "h2d_bytes_per_step": int(w.h_qkv.numel() * 2 + aux_ints * 4), "d2h_bytes_per_step": int(h_out.numel() * 2),
             "ms_per_step": round(ms, 5), "steps": K,
-            "api": "tvm_b200.kv_cache.PagedKVCache.begin_forward/attention_with_fused_qkv (C ABI tvmb200_cache_*)"}
+            "api": "tvm_b200.kv_cache.PagedKVCache.begin_forward/attention_with_fused_qkv (C ABI tvmb200_cache_*); "
+                   "H2D of the next step and D2H of the previous one overlap the compute on a copy stream"}
 
 
 def run_prefill(args, capi, rank, world, dev, peaks, peak_src):
