@@ -311,7 +311,7 @@ def run_own(args):
         "tok_s_layer": round(world * w.B / (ms_per_step * 1e-3), 1),
         "roofline": {"bound": "hbm", "kernel": "decode_kernel(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(dec_gbs / hbm_peak, 4), "traffic": NCU_DRAM_BYTES["decode_c2"],
-                     "traffic_source": "profiles/r1_decode_v2_ncu.md: dram read+write of one launch, ncu --set full",
+                     "traffic_source": "profiles/r1_decode_v3_ncu.md: dram read+write of one launch, ncu --set full",
                      "peak_source": f"of {peak_src}", "algorithmic_bytes": w.decode_bytes(),
                      "kernel_ms": round(decode_ms, 5), "frac_of_spec_8000": round(dec_gbs / 8000.0, 4)},
         "gpu_launches": int(launches),
