@@ -65,6 +65,19 @@ TVMB200_API int tvmb200_reserve_workspace(int device_id, int64_t bytes);
 TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
 
 /*!
+ * \brief RoPE frequency scaling the reference compiles into every PrimFunc that rotates (`rope_scaling` dict ->
+ *  switch_rope_freq_func, position_embedding.py:257-299: fused_rope and the inline-RoPE paths of the attention kernels,
+ *  _kernel_common.py:115-127).  A loaded library needs it as state: kind TVMB200_ROPE_SCALING_NONE = rope_freq_default,
+ *  TVMB200_ROPE_SCALING_LLAMA3 = rope_freq_llama3 (position_embedding.py:130-160; Llama-3.1: factor 8, low 1, high 4,
+ *  original_max_position_embeddings 8192).  Applies to tvmb200_split_rotary[_append] and to rotary_mode = 1 of the
+ *  attention entries, for every call made afterwards in this process.  Other rope types are rejected.
+ */
+#define TVMB200_ROPE_SCALING_NONE 0
+#define TVMB200_ROPE_SCALING_LLAMA3 1
+TVMB200_API int tvmb200_set_rope_scaling(int32_t kind, float factor, float low_freq_factor, float high_freq_factor,
+                                         float original_max_position_embeddings);
+
+/*!
  * \brief Prefill implementation selector (test / profiling hook): 0 = auto (tcgen05 path for eligible shapes
  *        with >= 2048 folded rows, generic mma.sync path otherwise), 1 = force generic, 2 = force tcgen05
  *        wherever it is eligible (head_dim 128, rotary_mode 0, mask none/causal, no sliding window).

@@ -64,6 +64,20 @@ def from_bits16(b: np.ndarray, dtype: str) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # RoPE  (position_embedding.py:31-67 rope_freq_default, :500-521 _rope; _kernel_common.py:115-127)
 # ------------------------------------------------------------------------------------------------
+# Frequency scaling the reference bakes into its PrimFuncs at build time (`rope_scaling` dict -> switch_rope_freq_func,
+# position_embedding.py:257-299).  None = rope_freq_default; {"rope_type": "llama3", factor, low_freq_factor,
+# high_freq_factor, original_max_position_embeddings} = rope_freq_llama3 (position_embedding.py:130-160).  Module state,
+# like the kernels' tvmb200_set_rope_scaling: set_rope_scaling(None) restores the default.
+_ROPE_SCALING = None
+
+
+def set_rope_scaling(rs):
+    global _ROPE_SCALING
+    if rs is not None and rs.get("rope_type") != "llama3":
+        raise ValueError(f"oracle: rope_type {rs.get('rope_type')!r} is not restated (default and llama3 are)")
+    _ROPE_SCALING = dict(rs) if rs is not None else None
+
+
 def rope_rotate(x: np.ndarray, pos: np.ndarray, theta: float, scale: float, dtype: str,
                 rotary_dim: int | None = None) -> np.ndarray:
     """x: [n, H, D] (values in dtype), pos: [n] int.  Returns rotated x rounded to dtype.
@@ -78,7 +92,20 @@ def rope_rotate(x: np.ndarray, pos: np.ndarray, theta: float, scale: float, dtyp
     expo = ((d * 2) % rd).astype(np.float32) / np.float32(rd)
     denom = np.power(np.float32(theta), expo).astype(np.float32)  # [rd]
     s = np.asarray(pos, dtype=np.float32) * np.float32(scale)  # [n]
-    freq = (s[:, None] / denom[None, :]).astype(np.float32)  # [n, rd]
+    if _ROPE_SCALING is None:
+        freq = (s[:, None] / denom[None, :]).astype(np.float32)  # [n, rd]
+    else:
+        # rope_freq_llama3: orig = 1/theta^e; smooth = clip(alpha*orig - beta, 0, 1);
+        # freq = s * ((1 - smooth) * orig / factor + smooth * orig), all in float32
+        rs = _ROPE_SCALING
+        f32 = np.float32
+        inv_diff = 1.0 / (rs["high_freq_factor"] - rs["low_freq_factor"])
+        alpha = f32(rs["original_max_position_embeddings"] / (2 * np.pi) * inv_diff)
+        beta = f32(rs["low_freq_factor"] * inv_diff)
+        orig = (f32(1) / denom).astype(np.float32)
+        smooth = np.maximum(f32(0), np.minimum(f32(1), alpha * orig - beta)).astype(np.float32)
+        inv = ((f32(1) - smooth) * orig * f32(1.0 / rs["factor"]) + smooth * orig).astype(np.float32)
+        freq = (s[:, None] * inv[None, :]).astype(np.float32)
     cos = np.cos(freq.astype(np.float64)).astype(np.float32)[:, None, :]
     sin = np.sin(freq.astype(np.float64)).astype(np.float32)[:, None, :]
     xr = x[..., :rd]

@@ -310,6 +310,68 @@ def test_decode_inline_rope(capi, dtype):
     _run_decode(capi, rng, [11, 70, 300], 32, 8, 128, dtype, rotary_mode=1)
 
 
+LLAMA31 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+           "original_max_position_embeddings": 8192}
+
+
+@pytest.fixture()
+def llama3_rope(capi):
+    """llama3 frequency scaling (rope_freq_llama3, position_embedding.py:130-160) on both sides: kernels and oracle"""
+    capi.set_rope_scaling(LLAMA31)
+    ok.set_rope_scaling(LLAMA31)
+    yield capi
+    capi.set_rope_scaling(None)
+    ok.set_rope_scaling(None)
+
+
+def test_rope_llama3_against_the_reference_golden(llama3_rope):
+    """tests/golden/rope_llama3.npz: outputs of the reference's own fused_rope and inline-RoPE decode built with the
+    Llama-3.1 rope_scaling (oracle/ref_harness/gen_golden_rope.py)."""
+    import torch
+    from pathlib import Path
+
+    capi = llama3_rope
+    g = np.load(Path(__file__).parent / "golden" / "rope_llama3.npz")
+    theta, scale = float(g["params"][0]), float(g["params"][1])
+    n, hq, hkv, d = g["qkv"].shape[0], 8, 2, 128
+    q = torch.empty((n, hq, d), dtype=torch.float16, device="cuda")
+    k = torch.empty((n, hkv, d), dtype=torch.float16, device="cuda")
+    v = torch.empty((n, hkv, d), dtype=torch.float16, device="cuda")
+    capi.split_rotary(torch.from_numpy(g["qkv"]).cuda(), _i32(g["pos"]), q, k, v, 1, scale, theta)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(v), g["v"].astype(np.float32))
+    for i, pos in enumerate(g["pos"]):  # the angle is a float32: its ulp grows with the position (see the oracle test)
+        atol = 4e-3 + 3e-7 * float(pos)
+        assert_close(f"q[{i}]", to_np(q)[i], g["q"][i].astype(np.float32), atol=atol)
+        assert_close(f"k[{i}]", to_np(k)[i], g["k"][i].astype(np.float32), atol=atol)
+    B = g["qd"].shape[0]
+    o = torch.empty((B, hq, d), dtype=torch.float16, device="cuda")
+    lse = torch.empty((B, hq), dtype=torch.float32, device="cuda")
+    capi.attention_decode(torch.from_numpy(g["qd"]).cuda(), torch.from_numpy(g["pages"]).cuda(), _i32(g["page_indptr"]),
+                          _i32(g["page_values"]), _i32(g["length_info"]), _i32(g["kofs"]), _i32(g["qpos"]), o, lse, 1,
+                          scale, theta, d ** -0.5)
+    torch.cuda.synchronize()
+    assert_close("decode O", to_np(o), g["o"].astype(np.float32), atol=6e-3)
+    assert_close("decode LSE", to_np(lse), g["lse"], atol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rope_llama3_inline_paths_vs_oracle(llama3_rope, dtype):
+    """every kernel with an inline-RoPE path under llama3 scaling: decode, paged prefill, ragged prefill"""
+    rng = np.random.default_rng(18)
+    _run_decode(llama3_rope, rng, [11, 70, 300], 32, 8, 128, dtype, rotary_mode=1, theta=5e5)
+    _run_paged_prefill(llama3_rope, rng, [3, 17, 40], [20, 100, 333], 32, 8, 128, dtype, causal=0, rotary_mode=1)
+    _run_ragged(llama3_rope, rng, [10, 65, 130], [10, 65, 130], 32, 8, 128, dtype, causal=1, rotary_mode=1)
+
+
+def test_rope_scaling_rejects_unknown_kinds(capi):
+    with pytest.raises(Exception, match="not implemented"):
+        capi.set_rope_scaling({"rope_type": "yarn"})
+    L = capi.lib()
+    assert L.tvmb200_set_rope_scaling(7, 1.0, 1.0, 4.0, 8192.0) != 0
+    assert b"unsupported" in L.tvmb200_last_error()
+
+
 # ---------------------------------------------------------------------------------------------------
 def _run_ragged(capi, rng, q_lens, kv_lens, hq, hkv, d, dtype, causal=1, rotary_mode=0, tree=None, q_scale=1.0,
                 v_scale=1.0):

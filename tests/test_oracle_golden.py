@@ -8,6 +8,7 @@ import pytest
 
 from oracle import kernels as ok
 from tests.golden_replay import load, qkv_for, scenario_names
+from tests.util import assert_close
 
 
 def _arr(a):
@@ -122,3 +123,34 @@ def test_oracle_matches_reference_outputs(name):
                     else:
                         assert np.array_equal(kk, z[f"k_{idx}"][layer].astype(np.float32)), f"{name} op {idx}: K dump differs"
     assert checked > 0
+
+
+def test_oracle_llama3_rope_scaling_matches_the_reference():
+    """tests/golden/rope_llama3.npz was produced by the reference's own fused_rope and _attention_decode_cpu (inline
+    RoPE) built with rope_scaling = llama3 (oracle/ref_harness/gen_golden_rope.py)."""
+    from pathlib import Path
+
+    g = np.load(Path(__file__).parent / "golden" / "rope_llama3.npz")
+    theta, scale, factor, low, high, orig = [float(x) for x in g["params"]]
+    ok.set_rope_scaling({"rope_type": "llama3", "factor": factor, "low_freq_factor": low, "high_freq_factor": high,
+                         "original_max_position_embeddings": orig})
+    try:
+        q, k, v = ok.split_rotary(g["qkv"].astype(np.float32), g["pos"], 8, 2, 1, theta, scale, "float16")
+        assert np.array_equal(v, g["v"].astype(np.float32))
+        # the angle pos * inv_freq is a float32: its ulp is 6e-8 * pos for the high-frequency dims (0.006 rad at
+        # pos = 1e5), and powf differs by an ulp between libm and NumPy -- the slack grows with the position
+        for i, pos in enumerate(g["pos"]):
+            atol = 4e-3 + 3e-7 * float(pos)
+            assert_close(f"q[{i}]", q[i], g["q"][i].astype(np.float32), atol=atol)
+            assert_close(f"k[{i}]", k[i], g["k"][i].astype(np.float32), atol=atol)
+        o, lse = ok.attention_decode(g["qd"].astype(np.float32), g["pages"].astype(np.float32), g["page_indptr"],
+                                     g["page_values"], g["length_info"], g["kofs"], g["qpos"], 1, scale, theta, 128 ** -0.5,
+                                     "float16")
+        assert_close("decode O", o, g["o"].astype(np.float32), atol=6e-3)   # positions up to 5e4 inside (see above)
+        assert_close("decode LSE", lse, g["lse"], atol=2e-2)
+        # and the unscaled oracle must NOT match: the fixture really exercises the scaling
+        ok.set_rope_scaling(None)
+        q0, _, _ = ok.split_rotary(g["qkv"].astype(np.float32), g["pos"], 8, 2, 1, theta, scale, "float16")
+        assert np.abs(q0 - g["q"].astype(np.float32)).max() > 0.1
+    finally:
+        ok.set_rope_scaling(None)

@@ -154,6 +154,21 @@ def split_rotary_append(qkv, q_rope_position, append_position, q, k, v, pages, a
                                              apply_rope, rope_scale, rope_theta, _dt(qkv), _stream(qkv)))
 
 
+def set_rope_scaling(rope_scaling=None):
+    """rope_scaling: None / {} (default frequencies) or the reference's dict {"rope_type": "llama3", "factor", "low_freq_factor",
+    "high_freq_factor", "original_max_position_embeddings"}.  Process-wide, like the reference's build-time choice."""
+    L = lib()
+    L.tvmb200_set_rope_scaling.argtypes = [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    if not rope_scaling:
+        _check(L.tvmb200_set_rope_scaling(0, 1.0, 0.0, 1.0, 1.0))
+        return
+    if rope_scaling.get("rope_type") != "llama3":
+        raise TvmB200Error(f"rope_type {rope_scaling.get('rope_type')!r} is not implemented (default and llama3 are)")
+    _check(L.tvmb200_set_rope_scaling(1, float(rope_scaling["factor"]), float(rope_scaling["low_freq_factor"]),
+                                      float(rope_scaling["high_freq_factor"]),
+                                      float(rope_scaling["original_max_position_embeddings"])))
+
+
 def merge_state_inplace(v, s, v_other, s_other):
     _check(lib().tvmb200_merge_state_inplace(_p(v), _p(s), _p(v_other), _p(s_other), v.shape[0], v.shape[1],
                                              v.shape[2], _dt(v), _stream(v)))

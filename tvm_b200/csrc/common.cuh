@@ -242,10 +242,25 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// RoPE inverse-frequency denominator of the reference: theta^((2d mod rd)/rd)
-// (position_embedding.py:63 rope_freq_default)
-__device__ __forceinline__ float rope_denominator(int d, int rotary_dim, float theta) {
-  return powf(theta, static_cast<float>((d * 2) % rotary_dim) / static_cast<float>(rotary_dim));
+// RoPE frequency scaling: the reference bakes a `rope_scaling` dict into its PrimFuncs at build time
+// (switch_rope_freq_func, position_embedding.py:257-299); here it is process state set by tvmb200_set_rope_scaling and
+// copied into every launch.  kind 0 = rope_freq_default, 1 = rope_freq_llama3 (position_embedding.py:130-160).
+struct RopeScaling {
+  int kind;
+  float inv_factor, alpha, beta;  // llama3: 1/factor, orig_max_pos / (2 pi (high - low)), low / (high - low)
+};
+RopeScaling rope_scaling();  // current process-wide setting (core.cu)
+
+// The denominator the rotation angle is divided by: freq = pos * scale / rope_denominator(d).
+//   default: theta^((2d mod rd)/rd)                                  (position_embedding.py:63)
+//   llama3:  1 / (orig * ((1 - smooth) / factor + smooth)), orig = theta^-((2d mod rd)/rd),
+//            smooth = clamp(alpha * orig - beta, 0, 1)                (position_embedding.py:143-153)
+__device__ __forceinline__ float rope_denominator(int d, int rotary_dim, float theta, const RopeScaling& rs) {
+  const float den = powf(theta, static_cast<float>((d * 2) % rotary_dim) / static_cast<float>(rotary_dim));
+  if (rs.kind == 0) return den;
+  const float orig = 1.0f / den;
+  const float smooth = fmaxf(0.0f, fminf(1.0f, rs.alpha * orig - rs.beta));
+  return 1.0f / ((1.0f - smooth) * orig * rs.inv_factor + smooth * orig);
 }
 
 // block-wide exclusive scan helper for the device-side work schedulers.  vals in smem [n+1]:

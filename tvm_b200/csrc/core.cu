@@ -71,6 +71,13 @@ int get_workspace(int64_t bytes, void** out) {
 
 int32_t layer_sliding_window_size() { return g_layer_sliding_window_size.load(); }
 
+static std::mutex g_rope_mu;
+static RopeScaling g_rope_scaling = {0, 1.0f, 0.0f, 0.0f};
+RopeScaling rope_scaling() {
+  std::lock_guard<std::mutex> lk(g_rope_mu);
+  return g_rope_scaling;
+}
+
 }  // namespace tvmb200
 
 extern "C" const char* tvmb200_last_error(void) { return tvmb200::last_error_ref().c_str(); }
@@ -78,6 +85,24 @@ extern "C" const char* tvmb200_version(void) { return "tvm_b200 0.1 (sm_100a)"; 
 extern "C" int64_t tvmb200_launch_count(void) { return tvmb200::g_launch_count.load(); }
 extern "C" void tvmb200_set_layer_sliding_window_size(int32_t size) {
   tvmb200::g_layer_sliding_window_size.store(size);
+}
+extern "C" int tvmb200_set_rope_scaling(int32_t kind, float factor, float low_freq_factor, float high_freq_factor,
+                                        float original_max_position_embeddings) {
+  TVMB200_CHECK(kind == TVMB200_ROPE_SCALING_NONE || kind == TVMB200_ROPE_SCALING_LLAMA3,
+                "set_rope_scaling: kind %d unsupported (0 = none, 1 = llama3; gptj / llama4 / longrope / yarn are not implemented)", kind);
+  tvmb200::RopeScaling rs = {0, 1.0f, 0.0f, 0.0f};
+  if (kind == TVMB200_ROPE_SCALING_LLAMA3) {
+    TVMB200_CHECK(factor > 0.f && high_freq_factor != low_freq_factor && original_max_position_embeddings > 0.f,
+                  "set_rope_scaling: llama3 needs factor > 0, high_freq_factor != low_freq_factor, original_max_position_embeddings > 0");
+    const double inv_diff = 1.0 / (static_cast<double>(high_freq_factor) - static_cast<double>(low_freq_factor));
+    rs.kind = 1;
+    rs.inv_factor = static_cast<float>(1.0 / factor);
+    rs.alpha = static_cast<float>(original_max_position_embeddings / (2.0 * 3.14159265358979323846) * inv_diff);
+    rs.beta = static_cast<float>(low_freq_factor * inv_diff);
+  }
+  std::lock_guard<std::mutex> lk(tvmb200::g_rope_mu);
+  tvmb200::g_rope_scaling = rs;
+  return 0;
 }
 extern "C" int tvmb200_reserve_workspace(int device_id, int64_t bytes) {
   TVMB200_CHECK(device_id >= 0 && device_id < 64, "device id %d out of range", device_id);

@@ -53,6 +53,7 @@ struct DecodeParams {
   int rotary_mode;
   float rope_scale;
   float rope_theta;
+  RopeScaling rs;
   float scale_log2;  // sm_scale * log2(e)
 };
 
@@ -107,7 +108,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   __syncthreads();
   block_exclusive_scan(s_chunk_off, B, s_scan_tmp);
   if (ROPE) {
-    for (int d = threadIdx.x; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta);
+    for (int d = threadIdx.x; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta, p.rs);
     __syncthreads();
   }
   const int total_chunks = s_chunk_off[B];
@@ -731,6 +732,7 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   p.rotary_mode = rotary_mode;
   p.rope_scale = rope_scale;
   p.rope_theta = rope_theta;
+  p.rs = rope_scaling();
   p.scale_log2 = sm_scale * kLog2e;
 
   CUtensorMap tmap;

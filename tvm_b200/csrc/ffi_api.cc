@@ -339,6 +339,20 @@ int impl_set_rope_params(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   TVMB200_FFI_END();
 }
 
+// (kind, factor, low_freq_factor, high_freq_factor, original_max_position_embeddings): the rope_scaling dict the
+// reference bakes into its PrimFuncs (position_embedding.py:257-299); kind 0 = default, 1 = llama3
+int impl_set_rope_scaling(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "set_rope_scaling";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 5, fn);
+  if (tvmb200_set_rope_scaling(static_cast<int32_t>(arg_int(args, 0, fn, "kind")), static_cast<float>(arg_float(args, 1, fn, "factor")),
+                               static_cast<float>(arg_float(args, 2, fn, "low_freq_factor")),
+                               static_cast<float>(arg_float(args, 3, fn, "high_freq_factor")),
+                               static_cast<float>(arg_float(args, 4, fn, "original_max_position_embeddings"))) != 0)
+    throw Err{"ValueError", tvmb200_last_error()};
+  TVMB200_FFI_END();
+}
+
 // (layer_sliding_window_size)
 int impl_set_layer_sliding_window_size(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   static const char* fn = "set_layer_sliding_window_size";
@@ -985,5 +999,6 @@ TVMB200_EXPORT(compact_kv_copy, impl_compact_kv_copy)
 // module state the reference bakes in at TIR build time
 TVMB200_EXPORT(set_rope_params, impl_set_rope_params)
 TVMB200_EXPORT(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)
+TVMB200_EXPORT(set_rope_scaling, impl_set_rope_scaling)
 TVMB200_EXPORT(launch_count, impl_launch_count)
 TVMB200_EXPORT(register_vm_builtins, impl_register_vm_builtins)

@@ -116,7 +116,7 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
                     uint4* __restrict__ q, uint4* __restrict__ k, uint4* __restrict__ v,
                     int num_qo_heads, int num_kv_heads, int head_dim, int rotary_dim,
                     int apply_rope, float rope_scale, float rope_theta, uint4* __restrict__ pages,
-                    const int32_t* __restrict__ append_pos, int page_size) {
+                    const int32_t* __restrict__ append_pos, int page_size, const RopeScaling rs) {
   extern __shared__ float2 cs[];  // [rotary_dim/2] (cos, sin)
   pdl_launch_dependents();  // a dependent launched programmatically (the decode kernel) may start its prologue now
   const int64_t t = blockIdx.x;
@@ -126,7 +126,7 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
   if (apply_rope > 0) {
     const float pos = static_cast<float>(position_map[t]) * rope_scale;
     for (int d = threadIdx.x; d < rotary_dim / 2; d += blockDim.x) {
-      const float freq = pos / rope_denominator(d, rotary_dim, rope_theta);
+      const float freq = pos / rope_denominator(d, rotary_dim, rope_theta, rs);
       float s, c;
       sincosf(freq, &s, &c);
       cs[d] = make_float2(c, s);
@@ -309,12 +309,12 @@ extern "C" int tvmb200_split_rotary(const void* qkv, const int32_t* position_map
     split_rotary_kernel<__half, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
         static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
-        nullptr, nullptr, 16);
+        nullptr, nullptr, 16, rope_scaling());
   } else {
     split_rotary_kernel<__nv_bfloat16, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
         static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
-        nullptr, nullptr, 16);
+        nullptr, nullptr, 16, rope_scaling());
   }
   TVMB200_LAUNCH_OK();
   return 0;
@@ -339,12 +339,12 @@ extern "C" int tvmb200_split_rotary_append(const void* qkv, const int32_t* q_rop
     split_rotary_kernel<__half, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), q_rope_position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
         static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
-        static_cast<uint4*>(pages), append_position_map, page_size);
+        static_cast<uint4*>(pages), append_position_map, page_size, rope_scaling());
   } else {
     split_rotary_kernel<__nv_bfloat16, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), q_rope_position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
         static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta,
-        static_cast<uint4*>(pages), append_position_map, page_size);
+        static_cast<uint4*>(pages), append_position_map, page_size, rope_scaling());
   }
   TVMB200_LAUNCH_OK();
   return 0;

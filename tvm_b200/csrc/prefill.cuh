@@ -37,6 +37,7 @@ struct PrefillParams {
   int tree_k_rope;  // tree ragged: K rope position is q_rope_position[kv row] (tree_attn.py:429)
   float rope_scale;
   float rope_theta;
+  RopeScaling rs;
   float scale_log2;
 };
 

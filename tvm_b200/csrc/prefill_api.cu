@@ -28,6 +28,7 @@ static void fill_base(PrefillParams& p, const void* q, const int32_t* q_indptr, 
   p.rotary_mode = rotary_mode;
   p.rope_scale = rope_scale;
   p.rope_theta = rope_theta;
+  p.rs = rope_scaling();
   p.scale_log2 = sm_scale * kLog2e;
 }
 

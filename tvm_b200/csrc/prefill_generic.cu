@@ -137,7 +137,7 @@ prefill_generic_kernel(const PrefillParams p) {
   const int n_kv_tiles = (kv_end + BN - 1) / BN;
 
   if (p.rotary_mode == 1) {
-    for (int d = tid; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta);
+    for (int d = tid; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta, p.rs);
   }
 
   // ---- loaders -----------------------------------------------------------------------------------
