@@ -112,6 +112,12 @@ class DecodeWorkload:
         capi.split_rotary_append(self.qkv, self.q_rope_position, self.append_position, self.q, self.k, self.v,
                                  self.pages, 1, self.rope_scale, self.rope_theta)
 
+    def run_step_fused(self, capi):
+        """the whole step -- f_split_rotary + f_transpose_append + f_attention_decode -- as one launch (+ the merge)"""
+        capi.attention_decode_fused_qkv(self.qkv, self.q_rope_position, self.append_position, self.pages, self.page_indptr,
+                                        self.page_values, self.length_info, self.k_rope_pos_offset, self.o, self.lse, 1,
+                                        self.rope_scale, self.rope_theta, self.sm_scale)
+
     def run_decode_gather(self, capi, gather):
         """decode of this rank's KV-head shard; the kernel stores its heads into every rank's gathered buffer"""
         return gather.decode(capi, self.q, self.pages, self.page_indptr, self.page_values, self.length_info,
@@ -259,8 +265,7 @@ def run_own(args):
     # used for the barrier / max-over-ranks timing.  The head-sharded mode (--workload c4) is the one with a real
     # exchange (per-head outputs are re-assembled) and keeps its all-gather inside the timed step.
     def step():
-        w.run_rotary_append(capi)
-        w.run_decode(capi)
+        w.run_step_fused(capi)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -283,12 +288,12 @@ def run_own(args):
     if world > 1:
         dist.barrier()
     total_ms = e_beg.elapsed_time(e_end)
-    # pass 2 -- roofline of the dominant kernel: the same K steps with CUDA events around every decode launch
+    # pass 2 -- roofline of the dominant kernel (the fused decode launch + its split-KV merge): the same K steps with
+    # CUDA events around every launch pair
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
     for i in range(K):
-        w.run_rotary_append(capi)
         ev[2 * i].record()
-        w.run_decode(capi)
+        w.run_step_fused(capi)
         ev[2 * i + 1].record()
     torch.cuda.synchronize()
     decode_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(K)) / K
@@ -299,20 +304,20 @@ def run_own(args):
     ms_per_step = total_ms / K
     value = world * w.step_bytes() / (ms_per_step * 1e-3) / 1e9
     hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
-    dec_gbs = w.decode_bytes() / (decode_ms * 1e-3) / 1e9
+    dec_gbs = w.step_bytes() / (decode_ms * 1e-3) / 1e9
     out = {
         "metric": "decode_attn_hbm_gbps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C2 Llama-3-8B decode: batch 64/GPU x 4096 ctx, 32q/8kv heads, D128, page16, bf16 "
-                               "paged KV; step = split_rotary+append+decode of one layer",
+                               "paged KV; step = split_rotary+append+decode of one layer (one fused launch + the split-KV merge)",
                    "global_batch": w.B * world, "seq_len": w.L, "parallelism": f"batch-split x{world} (no data-path collective)",
                    "l2": "KV working set 1 GiB/GPU > 126 MB L2 (no flush needed)"},
         "tok_s_layer": round(world * w.B / (ms_per_step * 1e-3), 1),
-        "roofline": {"bound": "hbm", "kernel": "decode_kernel(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
+        "roofline": {"bound": "hbm", "kernel": "decode_kernel<FUSED qkv>(+decode_merge_kernel)", "achieved": round(dec_gbs, 1),
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(dec_gbs / hbm_peak, 4), "traffic": NCU_DRAM_BYTES["decode_c2"],
                      "traffic_source": "profiles/r1_decode_v3_ncu.md: dram read+write of one launch, ncu --set full",
-                     "peak_source": f"of {peak_src}", "algorithmic_bytes": w.decode_bytes(),
+                     "peak_source": f"of {peak_src}", "algorithmic_bytes": w.step_bytes(),
                      "kernel_ms": round(decode_ms, 5), "frac_of_spec_8000": round(dec_gbs / 8000.0, 4)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),

@@ -158,6 +158,27 @@ TVMB200_API int tvmb200_attention_decode_gather(const void* q, const void* pages
 TVMB200_API int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream);
 
 /*!
+ * \brief The whole decode step of AttentionWithFusedQKV in ONE launch (+ the split-KV merge): f_split_rotary,
+ *  f_transpose_append and f_attention_decode (paged_kv_cache.cc:1360, :1371, decode at :2261-2290) for a batch in which
+ *  every sequence appends exactly one token.  q and the new k are read from the fused
+ *  qkv [batch, Hq+2Hkv, D] and rotated at q_rope_position[b] when apply_rope > 0 (RoPE mode "normal"; the cached K is
+ *  stored rotated) exactly like f_split_rotary; the new k / v are written to slot append_position_map[b] of `pages` --
+ *  which must be the last slot of sequence b, as BeginForward lays it out -- by the work item that owns that page, which
+ *  also patches them into its staged copy, so the attention sees them.  The q / k / v temporaries are never
+ *  materialised.  Results agree with the three-call sequence within the fp tolerance (the rotation is the same
+ *  arithmetic; the pages end up bit-identical).  head_dim 128 only.
+ */
+TVMB200_API int tvmb200_attention_decode_fused_qkv(const void* qkv, const int32_t* q_rope_position,
+                                       const int32_t* append_position_map, void* pages,
+                                       const int32_t* page_indptr, const int32_t* page_values,
+                                       const int32_t* length_info, const int32_t* k_rope_pos_offset,
+                                       void* output, float* lse, int32_t batch_size, int32_t nnz_pages,
+                                       int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                       int32_t page_size, int32_t head_dim, int sliding_window,
+                                       int64_t apply_rope, float rope_scale, float rope_theta, float sm_scale,
+                                       int dtype, tvmb200_stream_t stream);
+
+/*!
  * \brief f_split_rotary immediately followed by f_transpose_append, in ONE launch (SURVEY 8(f) "next": fused
  *  rotary + append).  Replaces the back-to-back callback pair of AttentionWithFusedQKV when the append precedes
  *  the attention (paged_kv_cache.cc:1360 then :1371): q, k, v are written exactly as tvmb200_split_rotary writes

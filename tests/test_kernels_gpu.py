@@ -219,6 +219,59 @@ def test_decode_batch64(capi, dtype):
     _run_decode(capi, rng, list(rng.integers(1, 700, 64)), 32, 8, 128, dtype)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("apply_rope", [1, 0])
+@pytest.mark.parametrize("kv_lens", [[11, 16, 17, 300, 1], [4096, 2049, 33]])
+def test_decode_fused_qkv_matches_the_three_call_step(capi, dtype, apply_rope, kv_lens):
+    """tvmb200_attention_decode_fused_qkv = split_rotary + transpose_append + attention_decode: the pages must end up
+    bit-identical to the three-call sequence, O / LSE within the tolerance of it AND of the oracle's restatement of
+    the three callbacks (split-KV and single-chunk sequences, new token at the start / middle / end of a page)."""
+    import torch
+
+    rng = np.random.default_rng(19)
+    hq, hkv, d = 32, 8, 128
+    B = len(kv_lens)
+    c = make_paged_cache(rng, kv_lens, hkv, d, dtype)
+    qkv = rand16(rng, (B, hq + 2 * hkv, d), dtype)
+    qpos = (np.array(kv_lens) - 1 + 7).astype(np.int32)      # position of the new token (an arbitrary rope offset)
+    slots = np.array([int(c["page_values"][c["page_indptr"][b + 1] - 1]) * 16 + (kv_lens[b] - 1) % 16 for b in range(B)],
+                     np.int32)
+    kofs = np.full(B, 7, np.int32)
+    sm, theta = d ** -0.5, 5e5
+    # oracle: the three callbacks
+    wq, wk, wv = ok.split_rotary(qkv, qpos, hq, hkv, apply_rope, theta, 1.0, dtype)
+    wpages = c["pages"].copy()
+    ok.transpose_append(wpages, wk, wv, slots)
+    wo, wl = ok.attention_decode(wq, wpages, c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos, 0, 1.0,
+                                 theta, sm, dtype)
+    dqkv = to_dev(qkv, dtype)
+    ip, pv, li = _i32(c["page_indptr"]), _i32(c["page_values"]), _i32(c["length_info"])
+    tdt = dqkv.dtype
+    # three calls
+    p3 = to_dev(c["pages"], dtype)
+    q = torch.empty((B, hq, d), dtype=tdt, device="cuda")
+    k = torch.empty((B, hkv, d), dtype=tdt, device="cuda")
+    v = torch.empty((B, hkv, d), dtype=tdt, device="cuda")
+    o3 = torch.empty((B, hq, d), dtype=tdt, device="cuda")
+    l3 = torch.empty((B, hq), dtype=torch.float32, device="cuda")
+    capi.split_rotary_append(dqkv, _i32(qpos), _i32(slots), q, k, v, p3, apply_rope, 1.0, theta)
+    capi.attention_decode(q, p3, ip, pv, li, _i32(kofs), _i32(qpos), o3, l3, 0, 1.0, theta, sm)
+    # one call
+    p1 = to_dev(c["pages"], dtype)
+    o1 = torch.full((B, hq, d), float("nan"), dtype=tdt, device="cuda")
+    l1 = torch.full((B, hq), float("nan"), dtype=torch.float32, device="cuda")
+    n0 = capi.launch_count()
+    capi.attention_decode_fused_qkv(dqkv, _i32(qpos), _i32(slots), p1, ip, pv, li, _i32(kofs), o1, l1, apply_rope, 1.0,
+                                    theta, sm)
+    torch.cuda.synchronize()
+    assert capi.launch_count() - n0 <= 2          # decode (+ merge when a sequence is split)
+    assert torch.equal(p1, p3)                     # the appended k / v are the very same values
+    assert_close("fused O vs three calls", to_np(o1), to_np(o3))
+    assert_close("fused LSE vs three calls", to_np(l1), to_np(l3))
+    assert_close("fused O vs oracle", to_np(o1), wo)
+    assert_close("fused LSE vs oracle", to_np(l1), wl)
+
+
 def test_decode_step_is_cuda_graph_capturable(capi):
     """the per-layer sequence (fused rotary + append, split-KV decode, merge -- the last two launched as
     programmatic dependents) captured into one CUDA graph and replayed gives the eager result bit for bit; nothing in

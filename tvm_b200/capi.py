@@ -60,6 +60,8 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_merge_state_inplace.argtypes = [P, P, P, P, I64, I32, I32, c_int, P]
     L.tvmb200_attention_decode.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
                                            c_int, c_int, F, F, F, c_int, P]
+    L.tvmb200_attention_decode_fused_qkv.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
+                                                     c_int, I64, F, F, F, c_int, P]
     L.tvmb200_attention_decode_gather.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
                                                   c_int, c_int, F, F, F, c_int, P, P, I32, I32, ctypes.c_uint32, P]
     L.tvmb200_wait_peer_flags.argtypes = [P, I32, ctypes.c_uint32, P]
@@ -181,6 +183,17 @@ def attention_decode(q, pages, page_indptr, page_values, length_info, k_rope_pos
         _p(q), _p(pages), _p(page_indptr), _p(page_values), _p(length_info), _p(k_rope_pos_offset),
         _p(q_rope_position), _p(output), _p(lse), q.shape[0], page_values.shape[0], P, q.shape[1], Hkv, page, D,
         1 if length_info.dim() == 2 else 0, rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages), _stream(q)))
+
+
+def attention_decode_fused_qkv(qkv, q_rope_position, append_position, pages, page_indptr, page_values, length_info,
+                               k_rope_pos_offset, output, lse, apply_rope, rope_scale, rope_theta, sm_scale):
+    """f_split_rotary + f_transpose_append + f_attention_decode of a one-token-per-sequence batch in one launch."""
+    P, _, Hkv, page, D = pages.shape
+    hq = qkv.shape[1] - 2 * Hkv
+    _check(lib().tvmb200_attention_decode_fused_qkv(
+        _p(qkv), _p(q_rope_position), _p(append_position), _p(pages), _p(page_indptr), _p(page_values), _p(length_info),
+        _p(k_rope_pos_offset), _p(output), _p(lse), qkv.shape[0], page_values.shape[0], P, hq, Hkv, page, D,
+        1 if length_info.dim() == 2 else 0, apply_rope, rope_scale, rope_theta, sm_scale, _dt(pages), _stream(qkv)))
 
 
 def attention_decode_gather(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output,

@@ -263,6 +263,12 @@ __device__ __forceinline__ float rope_denominator(int d, int rotary_dim, float t
   return 1.0f / ((1.0f - smooth) * orig * rs.inv_factor + smooth * orig);
 }
 
+// cos * x + sin * partner with ONE fixed rounding sequence (product, then fused multiply-add), so that every kernel
+// that rotates -- split_rotary, the inline-RoPE loads, the fused decode step -- produces the same bits
+__device__ __forceinline__ float rope_mix(float c, float x, float s, float partner) {
+  return __fmaf_rn(c, x, __fmul_rn(s, partner));
+}
+
 // block-wide exclusive scan helper for the device-side work schedulers.  vals in smem [n+1]:
 // on entry s[i] (i<n) holds the count of item i; on exit s[i] = sum_{j<i}, s[n] = total.
 // All threads of the block must call it.  tmp: smem scratch of >= 33 ints.

@@ -48,6 +48,12 @@ struct DecodeParams {
   int num_kv_heads;
   int group;  // Hq / Hkv
   int chunk_pages;
+  // fused split_rotary + transpose_append + decode (FUSED instantiation): q / new k / new v are read from the fused
+  // qkv tensor, rotated in the kernel, and the new token is written to its page slot by the item that owns that page
+  const void* qkv;              // [B, Hq + 2 Hkv, D]
+  const int32_t* append_slot;   // [B] slot id (page * 16 + offset) of the new token = the sequence's last slot, or -1
+  void* pages;                  // [P, 2, Hkv, 16, D]
+  int fused_apply_rope;
   int always_partial;  // every item writes fp32 partials, the merge kernel produces all outputs (peer-gather mode)
   int sliding;  // length_info is [3,B]
   int rotary_mode;
@@ -69,7 +75,7 @@ struct DecodeCfg {
   static constexpr int kHalfBytes = kPage * 128;           // 2 KiB per TMA box
 };
 
-template <typename T, int D, int NW, int NSTAGE, bool ROPE>
+template <typename T, int D, int NW, int NSTAGE, bool ROPE, bool FUSED>
 __global__ void __launch_bounds__(NW * 32)
 decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   using Cfg = DecodeCfg<D>;
@@ -107,7 +113,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   }
   __syncthreads();
   block_exclusive_scan(s_chunk_off, B, s_scan_tmp);
-  if (ROPE) {
+  if (ROPE || FUSED) {
     for (int d = threadIdx.x; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta, p.rs);
     __syncthreads();
   }
@@ -158,17 +164,27 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
 
     // ---- Q^T fragments (B operand, [k = d][n = q head]) -----------------------------------------
     uint32_t qf[KS][2];
-    if (ROPE) {
-      // rotate the group's Q rows at q_rope_position[b] into shared memory (_kernel_common.py:115-127)
+    if (ROPE || FUSED) {
+      // rotate the group's Q rows at q_rope_position[b] into shared memory (_kernel_common.py:115-127); FUSED reads
+      // them from the fused qkv tensor like f_split_rotary (position_embedding.py:444-565) and skips the rotation
+      // when the cache's RoPE mode is "none"
       const float qpos = static_cast<float>(p.q_rope_position[b]) * p.rope_scale;
-      const T* qg = static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g) * D;
+      const T* qg = FUSED ? static_cast<const T*>(p.qkv) +
+                                (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.num_kv_heads) + h * g) * D
+                          : static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g) * D;
+      const bool rotate = !FUSED || p.fused_apply_rope;
       for (int it = threadIdx.x; it < g * (D / 2); it += blockDim.x) {
         const int qh = it / (D / 2), d = it - qh * (D / 2);
-        float sn, cs;
-        sincosf(qpos / s_denom[d], &sn, &cs);
         const T xl = qg[qh * D + d], xh = qg[qh * D + d + D / 2];
-        s_q[qh * D + d] = DT<T>::from_f(cs * DT<T>::to_f(xl) + sn * DT<T>::to_f(DT<T>::neg(xh)));
-        s_q[qh * D + d + D / 2] = DT<T>::from_f(cs * DT<T>::to_f(xh) + sn * DT<T>::to_f(xl));
+        if (rotate) {
+          float sn, cs;
+          sincosf(qpos / s_denom[d], &sn, &cs);
+          s_q[qh * D + d] = DT<T>::from_f(rope_mix(cs, DT<T>::to_f(xl), sn, DT<T>::to_f(DT<T>::neg(xh))));
+          s_q[qh * D + d + D / 2] = DT<T>::from_f(rope_mix(cs, DT<T>::to_f(xh), sn, DT<T>::to_f(xl)));
+        } else {
+          s_q[qh * D + d] = xl;
+          s_q[qh * D + d + D / 2] = xh;
+        }
       }
       __syncthreads();
       const bool qv = qrow < g;
@@ -237,6 +253,47 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
       const uint32_t kb = stages_base + st * Cfg::kStageBytes;
       const uint32_t vb = kb + Cfg::kBlockBytes;
 
+      if (FUSED) {
+        // f_transpose_append for this (sequence, kv head): the new token is the sequence's last slot.  The warp that
+        // holds the last page rotates the new k, drops k and v into their row of the staged page (so this step's
+        // attention sees them) and writes them to the page in HBM (so the next steps do).  D = 128: 4 elements / lane.
+        if (pg0 + warp + j * NW == n_pages_seq - 1 && p.append_slot[b] >= 0) {
+          const int r = last_page_len - 1;
+          const int pid = page_id_of(j);
+          const T* kn = static_cast<const T*>(p.qkv) +
+                        (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.num_kv_heads) + p.num_qo_heads + h) * D;
+          const T* vn = kn + static_cast<int64_t>(p.num_kv_heads) * D;
+          const int e0 = lane * 4;
+          const bool lower = e0 < D / 2;
+          uint2 kx = *reinterpret_cast<const uint2*>(kn + e0);
+          const uint2 kp = *reinterpret_cast<const uint2*>(kn + (lower ? e0 + D / 2 : e0 - D / 2));
+          const uint2 vx = *reinterpret_cast<const uint2*>(vn + e0);
+          if (p.fused_apply_rope) {
+            const float pos = static_cast<float>(p.q_rope_position[b]) * p.rope_scale;
+            T* xe = reinterpret_cast<T*>(&kx);
+            const T* pe = reinterpret_cast<const T*>(&kp);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float sn, cs;
+              sincosf(pos / s_denom[(e0 + e) & (D / 2 - 1)], &sn, &cs);
+              const float partner = DT<T>::to_f(lower ? DT<T>::neg(pe[e]) : pe[e]);
+              xe[e] = DT<T>::from_f(rope_mix(cs, DT<T>::to_f(xe[e]), sn, partner));
+            }
+          }
+          const int c = lane >> 1;  // 16-byte chunk of the row
+          const uint32_t off = (c >> 3) * Cfg::kHalfBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4) + (lane & 1) * 8;
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(kb + off), "r"(kx.x), "r"(kx.y) : "memory");
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(vb + off), "r"(vx.x), "r"(vx.y) : "memory");
+          T* pg = static_cast<T*>(p.pages);
+          const int64_t row_k = ((static_cast<int64_t>(pid) * 2 + 0) * p.num_kv_heads + h) * Cfg::kPage + r;
+          const int64_t row_v = ((static_cast<int64_t>(pid) * 2 + 1) * p.num_kv_heads + h) * Cfg::kPage + r;
+          *reinterpret_cast<uint2*>(pg + row_k * D + e0) = kx;
+          *reinterpret_cast<uint2*>(pg + row_v * D + e0) = vx;
+          fence_proxy_async();  // generic-proxy writes before the next TMA refill of this stage
+          __syncwarp();
+        }
+      }
+
       // slot validity of this page
       const int slot0 = (pg0 + warp + j * NW) * Cfg::kPage;
       uint32_t vmask;  // bit t = slot0 + t is a live KV entry
@@ -288,8 +345,8 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
             float sn, cs;
             sincosf(pos / s_denom[j * 8 + e], &sn, &cs);
             const float xl = DT<T>::to_f(le[e]), xh = DT<T>::to_f(he[e]);
-            le[e] = DT<T>::from_f(cs * xl + sn * DT<T>::to_f(DT<T>::neg(he[e])));
-            he[e] = DT<T>::from_f(cs * xh + sn * xl);
+            le[e] = DT<T>::from_f(rope_mix(cs, xl, sn, DT<T>::to_f(DT<T>::neg(he[e]))));
+            he[e] = DT<T>::from_f(rope_mix(cs, xh, sn, xl));
           }
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(al), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ah), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
@@ -625,14 +682,14 @@ int get_tmap_2d_cached(CUtensorMap* out, const void* base, int dtype, uint64_t r
   return 0;
 }
 
-template <typename T, int D, int NW, int NSTAGE, bool ROPE>
+template <typename T, int D, int NW, int NSTAGE, bool ROPE, bool FUSED>
 static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
                          cudaStream_t st, const PeerGather& pg) {
   using Cfg = DecodeCfg<D>;
   const size_t smem = 1024 + static_cast<size_t>(NW) * NSTAGE * Cfg::kStageBytes + NW * NSTAGE * 8 +
                       (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int) + 16 + (D / 2) * sizeof(float) +
                       8 * D * sizeof(T);
-  auto kern = decode_kernel<T, D, NW, NSTAGE, ROPE>;
+  auto kern = decode_kernel<T, D, NW, NSTAGE, ROPE, FUSED>;
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchAttribute pdl[1];
   pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -662,8 +719,12 @@ template <typename T, int D, int NW, int NSTAGE>
 static int launch_decode(const CUtensorMap& tmap, const DecodeParams& p, int grid, bool need_merge,
                          cudaStream_t st, const PeerGather& pg) {
   // inline RoPE is a separate instantiation so the default (pre-rotated K) path keeps its register budget
-  return p.rotary_mode == 1 ? launch_decode_impl<T, D, NW, NSTAGE, true>(tmap, p, grid, need_merge, st, pg)
-                            : launch_decode_impl<T, D, NW, NSTAGE, false>(tmap, p, grid, need_merge, st, pg);
+  if (p.qkv != nullptr) {
+    if constexpr (D == 128) return launch_decode_impl<T, D, NW, NSTAGE, false, true>(tmap, p, grid, need_merge, st, pg);
+    return set_error("attention_decode_fused_qkv: head_dim %d unsupported (128)", D);
+  }
+  return p.rotary_mode == 1 ? launch_decode_impl<T, D, NW, NSTAGE, true, false>(tmap, p, grid, need_merge, st, pg)
+                            : launch_decode_impl<T, D, NW, NSTAGE, false, false>(tmap, p, grid, need_merge, st, pg);
 }
 
 }  // namespace tvmb200
@@ -676,7 +737,8 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
                         int32_t batch_size, int32_t nnz_pages, int64_t num_pages, int32_t num_qo_heads,
                         int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int sliding_window,
                         int rotary_mode, float rope_scale, float rope_theta, float sm_scale, int dtype,
-                        tvmb200_stream_t stream, const PeerGather& pg) {
+                        tvmb200_stream_t stream, const PeerGather& pg, const void* fused_qkv = nullptr,
+                        const int32_t* append_slot = nullptr, int fused_apply_rope = 0) {
   TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "attention_decode: unsupported dtype %d", dtype);
   TVMB200_CHECK(page_size == 16, "attention_decode: page_size %d unsupported (the B200 path is built for 16-slot pages)", page_size);
   TVMB200_CHECK(head_dim == 128 || head_dim == 64, "attention_decode: head_dim %d unsupported (64 or 128)", head_dim);
@@ -728,6 +790,10 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   p.group = group;
   p.chunk_pages = chunk_pages;
   p.always_partial = pg.n > 0 ? 1 : 0;
+  p.qkv = fused_qkv;
+  p.append_slot = append_slot;
+  p.pages = const_cast<void*>(pages);
+  p.fused_apply_rope = fused_apply_rope;
   p.sliding = sliding_window ? 1 : 0;
   p.rotary_mode = rotary_mode;
   p.rope_scale = rope_scale;
@@ -761,6 +827,25 @@ extern "C" int tvmb200_attention_decode(const void* q, const void* pages, const 
   return decode_entry(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
                       batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window,
                       rotary_mode, rope_scale, rope_theta, sm_scale, dtype, stream, pg);
+}
+
+extern "C" int tvmb200_attention_decode_fused_qkv(const void* qkv, const int32_t* q_rope_position,
+                                                  const int32_t* append_position_map, void* pages,
+                                                  const int32_t* page_indptr, const int32_t* page_values,
+                                                  const int32_t* length_info, const int32_t* k_rope_pos_offset,
+                                                  void* output, float* lse, int32_t batch_size, int32_t nnz_pages,
+                                                  int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads,
+                                                  int32_t page_size, int32_t head_dim, int sliding_window,
+                                                  int64_t apply_rope, float rope_scale, float rope_theta, float sm_scale,
+                                                  int dtype, tvmb200_stream_t stream) {
+  TVMB200_CHECK(head_dim == 128, "attention_decode_fused_qkv: head_dim %d unsupported (128)", head_dim);
+  TVMB200_CHECK(qkv != nullptr && append_position_map != nullptr && pages != nullptr, "attention_decode_fused_qkv: null argument");
+  PeerGather pg = {};
+  // rotary_mode 0: the cached K is already rotated (RoPE mode "normal") or never rotated ("none"); q and the new k
+  // are rotated here when apply_rope > 0
+  return decode_entry(nullptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
+                      batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window, 0,
+                      rope_scale, rope_theta, sm_scale, dtype, stream, pg, qkv, append_position_map, apply_rope > 0 ? 1 : 0);
 }
 
 static int get_done_counter(int32_t** out) {

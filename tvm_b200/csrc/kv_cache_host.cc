@@ -1018,7 +1018,16 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
     trace_append();
     if (!plan) Rc(tvmb200_transpose_append(pages, tmp_k_, tmp_v_, dev(v_append_pos_), n, num_total_pages_, hkv, ps, d, dtype_, st));
   };
-  if (append_before_attn_) {
+  // A plain decode step (one new token per sequence, a single block depth, K cached rotated or un-rotated, D = 128) runs
+  // f_split_rotary + f_transpose_append + f_attention_decode as ONE launch (tvmb200_attention_decode_fused_qkv); the call
+  // trace still records the three callbacks in the reference's order.
+  const bool fuse_step = !plan && append_before_attn_ && num_depths_ == 1 && use_decode_kernel_[0] &&
+                         is_chain_on_depths_[0] && !page_indices_[0].empty() && rope_mode_ != TVMB200_ROPE_INLINE && d == 128 &&
+                         attn_kinds_[layer_id] != TVMB200_ATTN_MHA_SLIDING && !support_sw_ &&
+                         static_cast<int64_t>(v_qo_indptr_[0].size - 1) == n;
+  if (append_before_attn_ && fuse_step) {
+    trace_append();
+  } else if (append_before_attn_) {
     // the reference's f_split_rotary -> f_transpose_append pair (paged_kv_cache.cc:1360, :1371) as one launch
     trace_append();
     if (!plan)
@@ -1089,7 +1098,12 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
         TRACE(sw_flavour ? "decode_sliding_window" : "decode",
               {TF({n, hq, d}), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro), TI(v_q_rope_pos_),
                TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta), SF(sm_scale)});
-        if (!plan)
+        if (fuse_step)
+          Rc(tvmb200_attention_decode_fused_qkv(qkv, dev(v_q_rope_pos_), dev(v_append_pos_), pages, dev(pip), dev(piv), dev(li),
+                                                dev(kro), out, lse, B, nnz, num_total_pages_, hq, hkv, ps, d, 0, apply_rope,
+                                                static_cast<float>(scale), static_cast<float>(theta),
+                                                static_cast<float>(sm_scale), dtype_, st));
+        else if (!plan)
           Rc(tvmb200_attention_decode(tmp_q_, pages, dev(pip), dev(piv), dev(li), dev(kro), dev(v_q_rope_pos_), out, lse, B,
                                       nnz, num_total_pages_, hq, hkv, ps, d, sw_flavour ? 1 : 0, rot, static_cast<float>(scale),
                                       static_cast<float>(theta), static_cast<float>(sm_scale), dtype_, st));

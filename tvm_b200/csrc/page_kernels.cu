@@ -169,7 +169,7 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
         const float2 f = cs[d0 + e];
         // reference: cos*x + sin*(d < rd/2 ? -x[d+rd/2] : x[d-rd/2]), negation done in dtype
         const float partner = DT<T>::to_f(lower ? DT<T>::neg(pe[e]) : pe[e]);
-        oe[e] = DT<T>::from_f(f.x * DT<T>::to_f(xe[e]) + f.y * partner);
+        oe[e] = DT<T>::from_f(rope_mix(f.x, DT<T>::to_f(xe[e]), f.y, partner));
       }
       x = o;
     }
