@@ -38,7 +38,7 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant kernel on the named workload,
 # from the committed `ncu --set full` captures under profiles/ (a profiler number: reported next to the algorithmic
 # bytes, never used for timing)
-NCU_DRAM_BYTES = {"decode_c2": 1074441000 + 6551808, "prefill_c3": 402785280 + 220196864}
+NCU_DRAM_BYTES = {"decode_c2": 1074640000 + 6002176, "prefill_c3": 402785280 + 220196864}
 
 
 def measured_peaks():
