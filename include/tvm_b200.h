@@ -154,6 +154,16 @@ TVMB200_API int tvmb200_attention_decode_gather(const void* q, const void* pages
                                     void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
                                     int32_t rank, uint32_t epoch, tvmb200_stream_t stream);
 
+/*! \brief tvmb200_attention_decode_fused_qkv and tvmb200_attention_decode_gather in one: the whole decode step of a KV-head
+ *  shard (rotary + append + decode) with the head re-assembly over peer memory, two launches in total. */
+TVMB200_API int tvmb200_attention_decode_fused_qkv_gather(
+    const void* qkv, const int32_t* q_rope_position, const int32_t* append_position_map, void* pages,
+    const int32_t* page_indptr, const int32_t* page_values, const int32_t* length_info, const int32_t* k_rope_pos_offset,
+    void* output, float* lse, int32_t batch_size, int32_t nnz_pages, int64_t num_pages, int32_t num_qo_heads,
+    int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int sliding_window, int64_t apply_rope, float rope_scale,
+    float rope_theta, float sm_scale, int dtype, void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
+    int32_t rank, uint32_t epoch, tvmb200_stream_t stream);
+
 /*! \brief Block the stream until flags[r] has reached `epoch` for every r < world (see tvmb200_attention_decode_gather). */
 TVMB200_API int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream);
 

@@ -265,6 +265,16 @@ def test_decode_fused_qkv_matches_the_three_call_step(capi, dtype, apply_rope, k
                                     theta, sm)
     torch.cuda.synchronize()
     assert capi.launch_count() - n0 <= 2          # decode (+ merge when a sequence is split)
+    # ... and the same step with the single-rank peer gather (this rank is its own peer)
+    p2 = to_dev(c["pages"], dtype)
+    o2, l2 = torch.empty_like(o1), torch.empty_like(l1)
+    gathered = torch.full((B, hq, d), float("nan"), dtype=tdt, device="cuda")
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    capi.attention_decode_fused_qkv_gather(dqkv, _i32(qpos), _i32(slots), p2, ip, pv, li, _i32(kofs), o2, l2, apply_rope,
+                                           1.0, theta, sm, [gathered.data_ptr()], [flags.data_ptr()], 0, 1)
+    capi.wait_peer_flags(flags, 1, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(p2, p1) and torch.equal(o2, o1) and torch.equal(l2, l1) and torch.equal(gathered, o1)
     assert torch.equal(p1, p3)                     # the appended k / v are the very same values
     assert_close("fused O vs three calls", to_np(o1), to_np(o3))
     assert_close("fused LSE vs three calls", to_np(l1), to_np(l3))

@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_attention_decode_gather.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
                                                   c_int, c_int, F, F, F, c_int, P, P, I32, I32, ctypes.c_uint32, P]
     L.tvmb200_wait_peer_flags.argtypes = [P, I32, ctypes.c_uint32, P]
+    L.tvmb200_attention_decode_fused_qkv_gather.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, I32, I32, I32,
+                                                            c_int, I64, F, F, F, c_int, P, P, I32, I32, ctypes.c_uint32, P]
     L.tvmb200_attention_prefill_paged.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I64, I32, I32,
                                                   I32, I32, c_int, I32, c_int, c_int, F, F, F, c_int, P]
     L.tvmb200_attention_prefill_ragged.argtypes = [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32,
@@ -210,6 +212,21 @@ def attention_decode_gather(q, pages, page_indptr, page_values, length_info, k_r
         _p(q_rope_position), _p(output), _p(lse), q.shape[0], page_values.shape[0], P, q.shape[1], Hkv, page, D,
         1 if length_info.dim() == 2 else 0, rotary_mode, rope_scale, rope_theta, sm_scale, _dt(pages),
         ctypes.cast(outs, c_void_p), ctypes.cast(flags, c_void_p), world, rank, epoch & 0xFFFFFFFF, _stream(q)))
+
+
+def attention_decode_fused_qkv_gather(qkv, q_rope_position, append_position, pages, page_indptr, page_values, length_info,
+                                      k_rope_pos_offset, output, lse, apply_rope, rope_scale, rope_theta, sm_scale,
+                                      peer_output_ptrs, peer_flag_ptrs, rank, epoch):
+    P, _, Hkv, page, D = pages.shape
+    hq = qkv.shape[1] - 2 * Hkv
+    world = len(peer_output_ptrs)
+    outs = (c_void_p * world)(*[int(x) for x in peer_output_ptrs])
+    flags = (c_void_p * world)(*[int(x) for x in peer_flag_ptrs])
+    _check(lib().tvmb200_attention_decode_fused_qkv_gather(
+        _p(qkv), _p(q_rope_position), _p(append_position), _p(pages), _p(page_indptr), _p(page_values), _p(length_info),
+        _p(k_rope_pos_offset), _p(output), _p(lse), qkv.shape[0], page_values.shape[0], P, hq, Hkv, page, D,
+        1 if length_info.dim() == 2 else 0, apply_rope, rope_scale, rope_theta, sm_scale, _dt(pages),
+        ctypes.cast(outs, c_void_p), ctypes.cast(flags, c_void_p), world, rank, epoch & 0xFFFFFFFF, _stream(qkv)))
 
 
 def wait_peer_flags(flags, world, epoch):

@@ -863,6 +863,23 @@ static int get_done_counter(int32_t** out) {
   return 0;
 }
 
+static int fill_peer_gather(PeerGather* pg, void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
+                            int32_t rank, uint32_t epoch, int32_t num_qo_heads) {
+  TVMB200_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "attention_decode_gather: world %d / rank %d (1..8 ranks of one box)", world, rank);
+  TVMB200_CHECK(peer_outputs != nullptr && peer_flags != nullptr, "attention_decode_gather: peer pointer arrays are null");
+  pg->n = world;
+  pg->rank = rank;
+  pg->head_offset = rank * num_qo_heads;
+  pg->total_heads = world * num_qo_heads;
+  pg->epoch = epoch;
+  for (int i = 0; i < world; ++i) {
+    TVMB200_CHECK(peer_outputs[i] != nullptr && peer_flags[i] != nullptr, "attention_decode_gather: peer %d pointer is null", i);
+    pg->out[i] = peer_outputs[i];
+    pg->flags[i] = peer_flags[i];
+  }
+  return get_done_counter(&pg->done);
+}
+
 extern "C" int tvmb200_attention_decode_gather(const void* q, const void* pages, const int32_t* page_indptr,
                                                const int32_t* page_values, const int32_t* length_info,
                                                const int32_t* k_rope_pos_offset, const int32_t* q_rope_position,
@@ -872,24 +889,29 @@ extern "C" int tvmb200_attention_decode_gather(const void* q, const void* pages,
                                                float rope_scale, float rope_theta, float sm_scale, int dtype,
                                                void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
                                                int32_t rank, uint32_t epoch, tvmb200_stream_t stream) {
-  TVMB200_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "attention_decode_gather: world %d / rank %d (1..8 ranks of one box)", world, rank);
-  TVMB200_CHECK(peer_outputs != nullptr && peer_flags != nullptr, "attention_decode_gather: peer pointer arrays are null");
   PeerGather pg = {};
-  pg.n = world;
-  pg.rank = rank;
-  pg.head_offset = rank * num_qo_heads;
-  pg.total_heads = world * num_qo_heads;
-  pg.epoch = epoch;
-  for (int i = 0; i < world; ++i) {
-    TVMB200_CHECK(peer_outputs[i] != nullptr && peer_flags[i] != nullptr, "attention_decode_gather: peer %d pointer is null", i);
-    pg.out[i] = peer_outputs[i];
-    pg.flags[i] = peer_flags[i];
-  }
-  if (int rc = get_done_counter(&pg.done)) return rc;
+  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads)) return rc;
   if (batch_size <= 0) return 0;
   return decode_entry(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
                       batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window,
                       rotary_mode, rope_scale, rope_theta, sm_scale, dtype, stream, pg);
+}
+
+extern "C" int tvmb200_attention_decode_fused_qkv_gather(
+    const void* qkv, const int32_t* q_rope_position, const int32_t* append_position_map, void* pages,
+    const int32_t* page_indptr, const int32_t* page_values, const int32_t* length_info, const int32_t* k_rope_pos_offset,
+    void* output, float* lse, int32_t batch_size, int32_t nnz_pages, int64_t num_pages, int32_t num_qo_heads,
+    int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int sliding_window, int64_t apply_rope, float rope_scale,
+    float rope_theta, float sm_scale, int dtype, void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
+    int32_t rank, uint32_t epoch, tvmb200_stream_t stream) {
+  TVMB200_CHECK(head_dim == 128, "attention_decode_fused_qkv_gather: head_dim %d unsupported (128)", head_dim);
+  TVMB200_CHECK(qkv != nullptr && append_position_map != nullptr && pages != nullptr, "attention_decode_fused_qkv_gather: null argument");
+  PeerGather pg = {};
+  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads)) return rc;
+  if (batch_size <= 0) return 0;
+  return decode_entry(nullptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
+                      batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window, 0,
+                      rope_scale, rope_theta, sm_scale, dtype, stream, pg, qkv, append_position_map, apply_rope > 0 ? 1 : 0);
 }
 
 extern "C" int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream) {

@@ -97,3 +97,15 @@ class PeerHeadGather:
                                      self.buf_ptrs[par], self.flag_ptrs, self.rank, self.epoch)
         capi.wait_peer_flags(self.flags, self.world, self.epoch)
         return self.bufs[par]
+
+    def decode_fused_qkv(self, capi, qkv, q_rope_position, append_position, pages, page_indptr, page_values, length_info,
+                         k_rope_pos_offset, output, lse, apply_rope, rope_scale, rope_theta, sm_scale):
+        """the whole decode step of this rank's shard (rotary + append + decode) + the peer gather: two launches"""
+        self.epoch += 1
+        par = self.epoch & 1
+        capi.attention_decode_fused_qkv_gather(qkv, q_rope_position, append_position, pages, page_indptr, page_values,
+                                               length_info, k_rope_pos_offset, output, lse, apply_rope, rope_scale,
+                                               rope_theta, sm_scale, self.buf_ptrs[par], self.flag_ptrs, self.rank,
+                                               self.epoch)
+        capi.wait_peer_flags(self.flags, self.world, self.epoch)
+        return self.bufs[par]
