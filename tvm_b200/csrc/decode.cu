@@ -260,6 +260,9 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
         if (pg0 + warp + j * NW == n_pages_seq - 1 && p.append_slot[b] >= 0) {
           const int r = last_page_len - 1;
           const int pid = page_id_of(j);
+          // the documented precondition: the append slot IS the sequence's last slot (BeginForward's layout for a
+          // decode step).  Anything else would silently attend to a stale row: fail loudly instead.
+          if (p.append_slot[b] != pid * Cfg::kPage + r) __trap();
           const T* kn = static_cast<const T*>(p.qkv) +
                         (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.num_kv_heads) + p.num_qo_heads + h) * D;
           const T* vn = kn + static_cast<int64_t>(p.num_kv_heads) * D;
@@ -840,6 +843,7 @@ extern "C" int tvmb200_attention_decode_fused_qkv(const void* qkv, const int32_t
                                                   int dtype, tvmb200_stream_t stream) {
   TVMB200_CHECK(head_dim == 128, "attention_decode_fused_qkv: head_dim %d unsupported (128)", head_dim);
   TVMB200_CHECK(qkv != nullptr && append_position_map != nullptr && pages != nullptr, "attention_decode_fused_qkv: null argument");
+  TVMB200_CHECK(!sliding_window, "attention_decode_fused_qkv: per-sequence sliding windows append after the attention; use the separate calls");
   PeerGather pg = {};
   // rotary_mode 0: the cached K is already rotated (RoPE mode "normal") or never rotated ("none"); q and the new k
   // are rotated here when apply_rope > 0
@@ -906,6 +910,7 @@ extern "C" int tvmb200_attention_decode_fused_qkv_gather(
     int32_t rank, uint32_t epoch, tvmb200_stream_t stream) {
   TVMB200_CHECK(head_dim == 128, "attention_decode_fused_qkv_gather: head_dim %d unsupported (128)", head_dim);
   TVMB200_CHECK(qkv != nullptr && append_position_map != nullptr && pages != nullptr, "attention_decode_fused_qkv_gather: null argument");
+  TVMB200_CHECK(!sliding_window, "attention_decode_fused_qkv_gather: per-sequence sliding windows append after the attention; use the separate calls");
   PeerGather pg = {};
   if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads)) return rc;
   if (batch_size <= 0) return 0;
