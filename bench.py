@@ -483,7 +483,7 @@ def run_c4(args, capi, rank, world, dev, peaks, peak_src):
         import torch.distributed as dist
 
         gather_kind = args.gather
-        if gather_kind == "p2p":
+        if gather_kind in ("p2p", "p2p-unfused"):
             try:
                 gather = sharding.PeerHeadGather(B, Hq, w.D, torch.bfloat16, dev)
             except Exception as e:  # symmetric memory unavailable on this box: the NCCL all-gather still works
@@ -502,6 +502,9 @@ def run_c4(args, capi, rank, world, dev, peaks, peak_src):
             assert torch.allclose(got.float(), want.float(), atol=2e-3, rtol=1e-2), "peer-gathered heads differ from decode + NCCL all-gather"
 
     def step():
+        if gather is not None and gather_kind == "p2p-unfused":  # rotary+append launch, then decode + head gather
+            w.run_rotary_append(capi)
+            return w.run_decode_gather(capi, gather)
         if gather is not None:  # rotary + append + decode + head gather: one fused launch, the merge, the flag wait
             return gather.decode_fused_qkv(capi, w.qkv, w.q_rope_position, w.append_position, w.pages, w.page_indptr,
                                            w.page_values, w.length_info, w.k_rope_pos_offset, w.o, w.lse, 1, w.rope_scale,
@@ -538,7 +541,8 @@ def run_c4(args, capi, rank, world, dev, peaks, peak_src):
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": {"workload": "C4 Llama-3-70B GQA decode: batch 256 x 8192 ctx, 64q/8kv heads sharded by KV-head group, "
                                   "D128, page16, bf16; step = split_rotary+append+decode+re-assembly of the per-head O on every rank",
-                      "head_gather": {"p2p": "in-kernel NVLink peer stores + flags (tvmb200_attention_decode_gather)",
+                      "head_gather": {"p2p": "in-kernel NVLink peer stores + flags, fused qkv step (tvmb200_attention_decode_fused_qkv_gather)",
+                                      "p2p-unfused": "in-kernel NVLink peer stores + flags (tvmb200_attention_decode_gather)",
                                       "nccl": "ncclAllGather behind the kernel", "none": "single GPU"}[gather_kind],
                       "global_batch": B, "seq_len": L, "parallelism": f"tp{world} (KV-head groups)",
                       "l2": "KV working set >= 1 GiB/GPU > 126 MB L2"},
@@ -583,7 +587,7 @@ def main():
     ap.add_argument("--workload", default="decode", choices=["decode", "prefill", "c4"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p",
+    ap.add_argument("--gather", choices=["p2p", "p2p-unfused", "nccl"], default="p2p",
                     help="c4 workload: how the per-head outputs are re-assembled across ranks")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs: launch lists)")
     args = ap.parse_args()
