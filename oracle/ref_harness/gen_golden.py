@@ -219,8 +219,72 @@ def prog_tree_attn():
     return p
 
 
+def prog_random(seed):
+    """Randomised differential scenario: a few hundred cache operations drawn at random -- prefill chunks, decode
+    steps over random subsets, forks at random positions (also of forked sequences), popn (kept inside a sequence's own
+    last block, as the reference requires), removals -- so that the host cache's page allocation, block tree, copy-on-
+    fork and aux-array construction are compared with the reference far off the hand-written paths."""
+    rng = np.random.default_rng(seed)
+    p = Program()
+    length, tail = {}, {}     # seq -> total length, tokens appended since its last fork point / creation
+    next_id = 0
+    total = 0
+    cap = 1800                # max_total_seq is 2048
+    for _ in range(60):
+        live = sorted(length)
+        r = rng.random()
+        if (r < 0.25 or not live) and len(live) < 12 and total < cap - 80:
+            n = int(rng.integers(1, 70))
+            p.forward([(next_id, n)])
+            length[next_id], tail[next_id] = n, n
+            next_id += 1
+            total += n
+        elif r < 0.40 and live and len(live) < 12 and total < cap - 80:
+            parent = int(rng.choice(live))
+            pos = int(rng.integers(1, length[parent] + 1)) if rng.random() < 0.7 else -1
+            n = int(rng.integers(1, 40))
+            p.forward([((next_id, parent, pos), n)])
+            base = length[parent] if pos == -1 else pos
+            length[next_id], tail[next_id] = base + n, n
+            tail[parent] = min(tail[parent], length[parent] - base) if pos != -1 else 0
+            next_id += 1
+            total += n
+        elif r < 0.80 and live and total < cap - len(live) * 8:
+            k = int(rng.integers(1, len(live) + 1))
+            sel = [int(x) for x in rng.choice(live, size=k, replace=False)]
+            if rng.random() < 0.7:
+                batch = [(s_, 1) for s_ in sel]                       # decode
+            else:
+                batch = [(s_, int(rng.integers(1, 8))) for s_ in sel]  # short multi-token appends
+            p.forward(batch)
+            for s_, n in batch:
+                length[s_] += n
+                tail[s_] += n
+                total += n
+        elif r < 0.90 and live:
+            s_ = int(rng.choice(live))
+            if tail[s_] > 1:
+                n = int(rng.integers(1, tail[s_]))
+                p.op(op="popn", seq=s_, n=n)
+                length[s_] -= n
+                tail[s_] -= n
+        elif live:
+            leaves = [s_ for s_ in live]
+            s_ = int(rng.choice(leaves))
+            p.op(op="remove", seq=s_)
+            del length[s_], tail[s_]
+        if rng.random() < 0.15:
+            p.op(op="query")
+    p.dump_all({s_: min(n, 40) for s_, n in length.items()})
+    p.op(op="query")
+    return p
+
+
 SCENARIOS = {
     # name: (program builder, cache kwargs)
+    "random_a": (lambda: prog_random(11), dict(rope_mode=1)),
+    "random_b": (lambda: prog_random(12), dict(rope_mode=0)),
+    "random_c": (lambda: prog_random(13), dict(rope_mode=2, num_layers=2)),
     "prefill_and_decode": (prog_prefill_and_decode, dict(rope_mode=1)),
     "remove_and_popn": (prog_remove_and_popn, dict(rope_mode=1)),
     "fork": (prog_fork, dict(rope_mode=1)),
