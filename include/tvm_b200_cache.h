@@ -86,6 +86,42 @@ TVMB200_API int tvmb200_cache_get_query_positions(tvmb200_cache_t c, const int32
 TVMB200_API int tvmb200_cache_attention_with_fused_qkv(tvmb200_cache_t c, int64_t layer_id, double sm_scale,
                                                        const void* qkv, void* o, int64_t qkv_rows,
                                                        tvmb200_stream_t stream);
+/*!
+ * \brief self_attention(layer_id, sm_scale, q [n, Hq, D], k, v [n, Hkv, D], o [n, Hq, D], lse [n, Hq] f32)
+ *  (`vm.builtin.attention_kv_cache_self_attention`, kv_state.cc:84-90; SelfAttention, paged_kv_cache.cc:1404-1445 ->
+ *  MHASelfAttnInternal :2182-2206): the step's tokens against themselves (causal, or the token-tree mask); nothing is
+ *  read from or appended to the pages.  rows = n must equal the batch's total append length.
+ */
+TVMB200_API int tvmb200_cache_self_attention(tvmb200_cache_t c, int64_t layer_id, double sm_scale, const void* q,
+                                             const void* k, const void* v, void* o, float* lse, int64_t rows,
+                                             tvmb200_stream_t stream);
+/*!
+ * \brief cross_attention(layer_id, sm_scale, q, o, lse) (`vm.builtin.attention_kv_cache_cross_attention`,
+ *  kv_state.cc:91-96; CrossAttention, paged_kv_cache.cc:1447-1485 -> MHACrossAttnInternal :2216-2299 with
+ *  is_first_kernel = true, causal = false): q against the cached KV of every block depth, merged in place.  When no
+ *  depth holds a page, (o, lse) are left untouched, as in the reference.
+ */
+TVMB200_API int tvmb200_cache_cross_attention(tvmb200_cache_t c, int64_t layer_id, double sm_scale, const void* q, void* o,
+                                              float* lse, int64_t rows, tvmb200_stream_t stream);
+/*!
+ * \brief attention_with_shared_kv(source_layer_id, sm_scale, q, current_k, current_v, o)
+ *  (`vm.builtin.attention_kv_cache_attention_with_shared_kv`, kv_state.cc:97-104; AttentionWithSharedKV,
+ *  paged_kv_cache.cc:1487-1529): a layer without its own KV queries the K / V of `source_layer_id` after that layer's
+ *  attention_with_fused_qkv of the same step; current_k / current_v (already rotated) are only read when the batch
+ *  appends after the attention.
+ */
+TVMB200_API int tvmb200_cache_attention_with_shared_kv(tvmb200_cache_t c, int64_t source_layer_id, double sm_scale,
+                                                       const void* q, const void* current_k, const void* current_v,
+                                                       void* o, int64_t rows, tvmb200_stream_t stream);
+/*!
+ * \brief merge_attn_output_inplace(o_self, lse_self, o_cross, lse_cross)
+ *  (`vm.builtin.attention_kv_cache_merge_attn_output_inplace`, kv_state.cc:109-115; MergeAttnOutputInplace,
+ *  paged_kv_cache.cc:1553-1559 = f_merge_inplace[1]): (o_self, lse_self) <- merge with (o_cross, lse_cross).
+ *  o_*: [n, num_heads, head_dim], lse_*: [n, num_heads] f32.
+ */
+TVMB200_API int tvmb200_cache_merge_attn_output_inplace(tvmb200_cache_t c, void* o_self, float* lse_self,
+                                                        const void* o_cross, const float* lse_cross, int64_t n,
+                                                        int64_t num_heads, int64_t head_dim, tvmb200_stream_t stream);
 /*! \brief k_out, v_out: [num_layers, end-start, Hkv, D] device tensors (DebugGetKV, paged_kv_cache.cc:1690-1725). */
 TVMB200_API int tvmb200_cache_debug_get_kv(tvmb200_cache_t c, int64_t seq_id, int64_t start_pos, int64_t end_pos,
                                            void* k_out, void* v_out, tvmb200_stream_t stream);

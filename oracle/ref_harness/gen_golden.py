@@ -40,8 +40,22 @@ class Program:
         self.ops.append({"op": "clear"})
         self.known = set()
 
-    def forward(self, batch, trees=None, leaves=None):
-        """batch items: (seq_id, len) or ((seq_id, parent, fork_pos), len) -- the reference's apply_attention."""
+    def forward_split(self, batch):
+        """begin_forward + per layer self_attention / cross_attention / merge_attn_output_inplace on the batch's q, k, v
+        (kv_state.cc:84-115), then popn of the reserved lengths: these entries append nothing, so the reservation is
+        rolled back and the cache content stays defined.  Lengths >= 2 keep the batch a prefill (append after attention),
+        so the cross part only reads tokens that were really appended."""
+        assert all(ln >= 2 for _, ln in batch)
+        self.seed += 1
+        self.ops.append({"op": "forward_split", "seq_ids": [s for s, _ in batch], "lens": [ln for _, ln in batch],
+                         "seed": self.seed})
+        for s, ln in batch:
+            self.ops.append({"op": "popn", "seq": s, "n": ln})
+
+    def forward(self, batch, trees=None, leaves=None, shared=False):
+        """batch items: (seq_id, len) or ((seq_id, parent, fork_pos), len) -- the reference's apply_attention.
+        shared: every layer's attention_with_fused_qkv is followed by attention_with_shared_kv on the same layer with a
+        second query (test_attention_with_shared_kv, ..._cpu.py:654-703)."""
         seq_ids, lens = [], []
         for item, ln in batch:
             if isinstance(item, tuple):
@@ -62,6 +76,8 @@ class Program:
                 flat += t[-ln:]
         self.seed += 1
         self.ops.append({"op": "forward", "seq_ids": seq_ids, "lens": lens, "tree": flat, "seed": self.seed})
+        if shared:
+            self.ops[-1]["shared"] = True
         if leaves is not None:
             self.ops.append({"op": "commit", "seq_ids": seq_ids, "leaves": leaves})
 
@@ -280,8 +296,55 @@ def prog_random(seed):
     return p
 
 
+def prog_shared_kv():
+    """prefill, chunked prefill, decode and a fork, every step followed by a shared-KV query of the same layer."""
+    p = Program()
+    ln = {}
+    for b in [[(0, 3)], [(0, 2)], [(0, 1)], [(1, 37), (2, 18)], [(0, 30), (1, 1), (2, 16)], [(0, 1), (1, 1), (2, 1)],
+              [((3, 1, 20), 9)], [(0, 1), (3, 1)], [(1, 1), (2, 1), (3, 5)]]:
+        p.forward(list(b), shared=True)
+        for item, n in b:
+            if isinstance(item, tuple):
+                sid, _, pos = item
+                ln[sid] = pos + n
+            else:
+                ln[item] = ln.get(item, 0) + n
+    p.dump_all(ln)
+    return p
+
+
+def prog_self_cross_merge():
+    """self_attention + cross_attention + merge_attn_output_inplace on an empty cache (nothing to cross-attend), on
+    cached sequences, on a mixed batch (one fresh sequence), and across a fork (two block depths)."""
+    p = Program()
+    p.op(op="add", seq=0)
+    p.op(op="add", seq=1)
+    p.forward_split([(0, 5), (1, 19)])
+    p.forward([(0, 21), (1, 40)])
+    p.forward_split([(0, 7), (1, 2)])
+    p.op(op="add", seq=2)
+    p.forward_split([(0, 3), (2, 33), (1, 16)])
+    p.forward([(0, 1), (1, 1)])
+    p.forward([((3, 1, 25), 6), ((4, 1, -1), 18)])
+    p.forward_split([(3, 4), (4, 9), (1, 2), (0, 17)])
+    p.forward([(0, 1), (1, 1), (3, 1), (4, 1)])
+    p.dump_all({0: 23, 1: 42, 3: 32, 4: 60})
+    p.op(op="query")
+    return p
+
+
 SCENARIOS = {
     # name: (program builder, cache kwargs)
+    "layer_sliding": (prog_prefill_and_decode, dict(rope_mode=0, num_layers=2, attn_kinds=[3, 0], layer_sliding_window_size=20)),
+    "layer_sliding_inline_rope": (prog_prefill_and_decode, dict(rope_mode=2, num_layers=2, attn_kinds=[0, 3],
+                                                                layer_sliding_window_size=35)),
+    "shared_kv": (prog_shared_kv, dict(rope_mode=2, num_layers=2)),
+    # window 32 > the longest chunk appended behind cached tokens (30): a query farther than the window from EVERY cached
+    # key makes the reference's CPU prefill kernel return NaN (0 / 0 on the fully masked row), which pins nothing
+    "shared_kv_layer_sliding": (prog_shared_kv, dict(rope_mode=0, num_layers=2, attn_kinds=[3, 0],
+                                                     layer_sliding_window_size=32)),
+    "self_cross_merge": (prog_self_cross_merge, dict(rope_mode=0)),
+    "self_cross_merge_inline_rope": (prog_self_cross_merge, dict(rope_mode=2, num_layers=2)),
     "random_a": (lambda: prog_random(11), dict(rope_mode=1)),
     "random_b": (lambda: prog_random(12), dict(rope_mode=0)),
     "random_c": (lambda: prog_random(13), dict(rope_mode=2, num_layers=2)),
@@ -295,7 +358,14 @@ SCENARIOS = {
     "tree_attn": (prog_tree_attn, dict(rope_mode=1)),
 }
 BASE = dict(num_layers=1, num_qo_heads=4, num_kv_heads=1, head_dim=128, dtype="float16", reserved_nseq=32,
-            max_total_seq=2048, prefill_chunk=512, page_size=16, rope_scale=1.0, rope_theta=1e4)
+            max_total_seq=2048, prefill_chunk=512, page_size=16, rope_scale=1.0, rope_theta=1e4,
+            layer_sliding_window_size=None, attn_kinds=None)
+
+
+def q2_for(seed, num_layers, n, hq, d, dtype="float16"):
+    """The second (shared-KV) query of a step, [num_layers, n, hq, d]."""
+    rng = np.random.default_rng(seed + 500000)
+    return rng.random((num_layers, n, hq, d), dtype=np.float32).astype(dtype)
 
 
 def run_reference(name):
@@ -307,6 +377,10 @@ def run_reference(name):
     cfg = dict(BASE)
     cfg.update(kw)
     prog = builder()
+    if cfg["attn_kinds"] is not None and any(k != 0 for k in cfg["attn_kinds"]):
+        # DebugGetKV only takes all-MHA caches (paged_kv_cache.cc:1715-1717): the dump is replaced by the error check
+        prog.ops = [o for o in prog.ops if o["op"] != "debug_get_kv"]
+        prog.ops.append({"op": "debug_get_kv_rejected", "seq": 0})
     rc = RefCache(**cfg)
     L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
     arrays = {}
@@ -341,19 +415,68 @@ def run_reference(name):
             rc.call("attention_kv_cache_debug_get_kv", op["seq"], op["start"], op["end"], kk, vv)
             arrays[f"k_{idx}"] = kk.numpy()
             arrays[f"v_{idx}"] = vv.numpy()
+        elif k == "debug_get_kv_rejected":
+            kk = tvm.runtime.empty((L, 1, hkv, d), cfg["dtype"], device=rc.dev)
+            try:
+                rc.call("attention_kv_cache_debug_get_kv", op["seq"], 0, 1, kk, kk)
+                raise AssertionError("the reference accepted DebugGetKV on a non-MHA layer")
+            except tvm.error.InternalError as e:
+                assert "Only MHA is supported for DebugGetKV" in str(e)
         elif k == "forward":
             tree = tvm_ffi.Shape(op["tree"]) if op["tree"] is not None else None
             rc.call("kv_state_begin_forward", tvm_ffi.Shape(op["seq_ids"]), tvm_ffi.Shape(op["lens"]), tree)
             n = sum(op["lens"])
             qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
             outs = []
+            q2 = q2_for(op["seed"], L, n, hq, d, cfg["dtype"]) if op.get("shared") else None
+            shared_outs = []
             for layer in range(L):
                 o = tvm.runtime.empty((n, hq, d), cfg["dtype"], device=rc.dev)
                 rc.call("attention_kv_cache_attention_with_fused_qkv", layer, d ** -0.5,
                         tvm.runtime.tensor(qkv[layer], device=rc.dev), o)
                 outs.append(o.numpy())
+                if q2 is not None:
+                    # rope is none or inline in these scenarios, so the step's raw k / v are the "current" k / v
+                    assert cfg["rope_mode"] != 1
+                    o2 = tvm.runtime.empty((n, hq, d), cfg["dtype"], device=rc.dev)
+                    rc.call("attention_kv_cache_attention_with_shared_kv", layer, d ** -0.5,
+                            tvm.runtime.tensor(q2[layer], device=rc.dev),
+                            tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq:hq + hkv]), device=rc.dev),
+                            tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq + hkv:]), device=rc.dev), o2)
+                    shared_outs.append(o2.numpy())
             rc.call("kv_state_end_forward")
             arrays[f"o_{idx}"] = np.stack(outs)
+            if shared_outs:
+                arrays[f"os_{idx}"] = np.stack(shared_outs)
+            res["num_available_pages"] = int(rc.call("attention_kv_cache_get_num_available_pages"))
+        elif k == "forward_split":
+            rc.call("kv_state_begin_forward", tvm_ffi.Shape(op["seq_ids"]), tvm_ffi.Shape(op["lens"]), None)
+            n = sum(op["lens"])
+            qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
+            merged, merged_lse, selfs, crosses = [], [], [], []
+            for layer in range(L):
+                dev = rc.dev
+                q = tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, :hq]), device=dev)
+                kk = tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq:hq + hkv]), device=dev)
+                vv = tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq + hkv:]), device=dev)
+                o_self = tvm.runtime.tensor(np.zeros((n, hq, d), cfg["dtype"]), device=dev)
+                lse_self = tvm.runtime.tensor(np.full((n, hq), -5e4, "float32"), device=dev)
+                # cross_attention leaves (o, lse) untouched when no sequence of the batch has a cached page
+                o_cross = tvm.runtime.tensor(np.zeros((n, hq, d), cfg["dtype"]), device=dev)
+                lse_cross = tvm.runtime.tensor(np.full((n, hq), -5e4, "float32"), device=dev)
+                rc.call("attention_kv_cache_self_attention", layer, d ** -0.5, q, kk, vv, o_self, lse_self)
+                rc.call("attention_kv_cache_cross_attention", layer, d ** -0.5, q, o_cross, lse_cross)
+                selfs.append(o_self.numpy())
+                crosses.append(o_cross.numpy())
+                ret = rc.call("attention_kv_cache_merge_attn_output_inplace", o_self, lse_self, o_cross, lse_cross)
+                assert len(ret) == 2
+                merged.append(o_self.numpy())
+                merged_lse.append(lse_self.numpy())
+            rc.call("kv_state_end_forward")
+            arrays[f"o_{idx}"] = np.stack(merged)
+            arrays[f"lse_{idx}"] = np.stack(merged_lse)
+            arrays[f"oself_{idx}"] = np.stack(selfs)
+            arrays[f"ocross_{idx}"] = np.stack(crosses)
             res["num_available_pages"] = int(rc.call("attention_kv_cache_get_num_available_pages"))
         else:
             raise ValueError(k)

@@ -107,7 +107,9 @@ class RefCache:
             "attention_kv_cache_enable_sliding_window_for_seq", "attention_kv_cache_commit_accepted_token_tree_nodes",
             "attention_kv_cache_attention_with_fused_qkv", "attention_kv_cache_empty",
             "attention_kv_cache_get_num_available_pages", "attention_kv_cache_get_total_sequence_length",
-            "attention_kv_cache_debug_get_kv", "attention_kv_cache_get_query_positions"]}
+            "attention_kv_cache_debug_get_kv", "attention_kv_cache_get_query_positions",
+            "attention_kv_cache_self_attention", "attention_kv_cache_cross_attention",
+            "attention_kv_cache_attention_with_shared_kv", "attention_kv_cache_merge_attn_output_inplace"]}
         cache_config = [reserved_nseq, max_total_seq, prefill_chunk, page_size, int(support_sliding_window)]
         if layer_sliding_window_size is not None:
             cache_config.append(layer_sliding_window_size)
@@ -119,7 +121,7 @@ class RefCache:
             tvm.runtime.empty((), dtype, device=self.dev),
             fns["transpose_append"], None, ["tirx", fns["prefill_ragged"]], ["tirx", fns["prefill"]],
             ["tirx", fns["decode"]], ["tirx", fns["prefill_sliding_window"]], ["tirx", fns["decode_sliding_window"]],
-            ["tirx", fns["tree_paged"]], ["tirx", fns["tree_ragged"]], [], [fns["merge"]], fns["split_rotary"],
+            ["tirx", fns["tree_paged"]], ["tirx", fns["tree_ragged"]], [], [fns["merge"], fns["merge"]], fns["split_rotary"],
             fns["copy_single_page"], fns["debug_get_kv"], fns["compact_copy"])
 
     def _wrap(self, name, fn):

@@ -5,15 +5,13 @@ Checked per op: the callback trace (bit-exact int32 arrays), the attention outpu
 import numpy as np
 import pytest
 
-from tests.golden_replay import load, replay, scenario_names
+from tests.golden_replay import base_scenario_names, load, replay
 from tests.util import assert_close, to_np
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("impl", [0, 2])
-@pytest.mark.parametrize("name", scenario_names())
-def test_scenario_matches_reference(built_lib, name, impl):
+def run_scenario(name, impl):
     from tvm_b200 import capi
 
     meta, _ = load(name)
@@ -34,8 +32,26 @@ def test_scenario_matches_reference(built_lib, name, impl):
         else:
             assert np.array_equal(to_np(kk), gk.astype(np.float32)), f"{name} op {idx}: K dump differs"
 
+    def on_shared(idx, outs, golden_os):
+        for layer, o in enumerate(outs):
+            assert_close(f"{name} op {idx} layer {layer} shared-KV O", to_np(o), golden_os[layer].astype(np.float32))
+
+    def on_split(idx, got, z):
+        for key in ("oself", "ocross", "o"):
+            for layer, o in enumerate(got[key]):
+                assert_close(f"{name} op {idx} layer {layer} {key}", to_np(o), z[f"{key}_{idx}"][layer].astype(np.float32))
+        for layer, lse in enumerate(got["lse"]):
+            assert_close(f"{name} op {idx} layer {layer} merged lse", to_np(lse), z[f"lse_{idx}"][layer])
+        n_checked[0] += 1
+
     try:
-        replay(name, device=0, on_forward=on_forward, on_kv=on_kv)
+        replay(name, device=0, on_forward=on_forward, on_kv=on_kv, on_shared=on_shared, on_split=on_split)
     finally:
         capi.set_prefill_impl(0)
     assert n_checked[0] > 0
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+@pytest.mark.parametrize("name", base_scenario_names())
+def test_scenario_matches_reference(built_lib, name, impl):
+    run_scenario(name, impl)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import kernels as ok
-from tests.golden_replay import load, qkv_for, scenario_names
+from tests.golden_replay import load, q2_for, qkv_for, scenario_names
 from tests.util import assert_close
 
 
@@ -32,28 +32,20 @@ class OracleMachine:
         self.pages = [np.zeros((npages, 2, hkv, ps, d), np.float32) for _ in range(L)]
         self.theta, self.scale = cfg["rope_theta"], cfg["rope_scale"]
 
-    def run_forward(self, trace, qkv):
-        hq, hkv = self.cfg["num_qo_heads"], self.cfg["num_kv_heads"]
-        outs, layer = [], -1
-        q = k = v = o = lse = tmp = None
-        for c in trace:
+    def attend(self, calls, layer, q, k, v):
+        """Executes a run of attention / merge callbacks (one AttentionInternal, SelfAttention or CrossAttention of the
+        reference) on q and the step's k / v; returns (o, lse), both None when nothing was computed."""
+        o = lse = tmp = None
+        sw = self.cfg.get("layer_sliding_window_size") or 1024
+        for c in calls:
             fn, a = c["fn"], c["args"]
-            if fn == "split_rotary":
-                if layer >= 0:
-                    outs.append(o)
-                layer += 1
-                q, k, v = ok.split_rotary(qkv[layer].astype(np.float32), _arr(a[1]), hq, hkv, a[5]["s"], self.theta, self.scale, self.dt)
-                o = lse = tmp = None
-            elif fn == "transpose_append":
-                ok.transpose_append(self.pages[layer], k, v, _arr(a[3]))
-            elif fn in ("prefill_ragged", "tree_ragged"):
-                if fn == "prefill_ragged":
-                    o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), _arr(a[6]), a[9]["s"],
-                                                         a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], self.dt)
-                else:
-                    o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), None, 0, a[10]["s"],
-                                                         a[11]["s"], a[12]["s"], a[13]["s"], self.dt, mn_indptr=_arr(a[6]),
-                                                         tree_mask=_arr(a[7]))
+            if fn == "prefill_ragged":
+                o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), _arr(a[6]), a[9]["s"],
+                                                     a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], self.dt)
+            elif fn == "tree_ragged":
+                o, lse = ok.attention_prefill_ragged(q, _arr(a[1]), k, v, _arr(a[4]), _arr(a[5]), None, 0, a[10]["s"],
+                                                     a[11]["s"], a[12]["s"], a[13]["s"], self.dt, mn_indptr=_arr(a[6]),
+                                                     tree_mask=_arr(a[7]))
             elif fn in ("prefill", "prefill_sliding_window", "decode", "decode_sliding_window", "tree_paged"):
                 P = self.pages[layer]
                 if fn.startswith("decode"):
@@ -66,7 +58,7 @@ class OracleMachine:
                 else:
                     r = ok.attention_prefill_paged(q, _arr(a[1]), P, _arr(a[3]), _arr(a[4]), _arr(a[5]), _arr(a[6]), _arr(a[7]),
                                                    a[10]["s"], a[11]["s"], a[12]["s"], a[13]["s"], a[14]["s"], self.dt,
-                                                   sliding_window_size=1024 if fn.endswith("sliding_window") else 0)
+                                                   sliding_window_size=sw if fn.endswith("sliding_window") else 0)
                 if o is None:
                     o, lse = r
                 else:
@@ -74,9 +66,58 @@ class OracleMachine:
             elif fn == "merge":
                 o, lse = ok.merge_state_inplace(o, lse, tmp[0], tmp[1], self.dt)
             else:
-                raise AssertionError(f"unexpected callback {fn} inside a forward")
-        outs.append(o)
-        return outs
+                raise AssertionError(f"unexpected callback {fn} inside an attention")
+        return o, lse
+
+    def run_forward(self, trace, qkv, q2=None):
+        """attention_with_fused_qkv per layer (split_rotary .. transpose_append), each optionally followed by the
+        attention_with_shared_kv calls of the same layer on q2.  Returns (outs, shared_outs)."""
+        hq, hkv = self.cfg["num_qo_heads"], self.cfg["num_kv_heads"]
+        starts = [i for i, c in enumerate(trace) if c["fn"] == "split_rotary"] + [len(trace)]
+        outs, shared_outs = [], []
+        for layer in range(len(starts) - 1):
+            calls = trace[starts[layer]:starts[layer + 1]]
+            q, k, v = ok.split_rotary(qkv[layer].astype(np.float32), _arr(calls[0]["args"][1]), hq, hkv,
+                                      calls[0]["args"][5]["s"], self.theta, self.scale, self.dt)
+            ia = next(i for i, c in enumerate(calls) if c["fn"] == "transpose_append")
+            if ia == 1:  # append before the attention: what follows is the fused attention (+ the same plan again on q2)
+                ok.transpose_append(self.pages[layer], k, v, _arr(calls[ia]["args"][3]))
+                rest = calls[2:]
+                m = len(rest) // 2 if q2 is not None else len(rest)
+                fused, shared = rest[:m], rest[m:]
+                if q2 is not None:
+                    assert [c["fn"] for c in fused] == [c["fn"] for c in shared]
+                outs.append(self.attend(fused, layer, q, k, v)[0])
+            else:        # attention first (self + cross), then the append, then the shared-KV query
+                outs.append(self.attend(calls[1:ia], layer, q, k, v)[0])
+                shared = calls[ia + 1:]
+            if q2 is not None:
+                # the step's raw k / v are the "current" k / v (rope is none or inline in the shared-KV scenarios)
+                shared_outs.append(self.attend(shared, layer, q2[layer].astype(np.float32), k, v)[0])
+            if ia != 1:
+                ok.transpose_append(self.pages[layer], k, v, _arr(calls[ia]["args"][3]))
+        return outs, shared_outs
+
+    def run_split(self, trace, qkv):
+        """self_attention, cross_attention, merge_attn_output_inplace per layer on the raw q, k, v of the step."""
+        hq, hkv = self.cfg["num_qo_heads"], self.cfg["num_kv_heads"]
+        L = self.cfg["num_layers"]
+        self_fns = ("prefill_ragged", "tree_ragged")
+        starts = [i for i, c in enumerate(trace) if c["fn"] in self_fns] + [len(trace)]
+        assert len(starts) == L + 1
+        res = []
+        for layer in range(L):
+            calls = trace[starts[layer]:starts[layer + 1]]
+            assert calls[-1]["fn"] == "merge"
+            x = qkv[layer].astype(np.float32)
+            q, k, v = x[:, :hq], x[:, hq:hq + hkv], x[:, hq + hkv:]
+            o_self, lse_self = self.attend(calls[:1], layer, q, k, v)
+            o_cross, lse_cross = self.attend(calls[1:-1], layer, q, k, v)
+            if o_cross is None:  # no cached page in the batch: the harness' initial values stay
+                o_cross, lse_cross = np.zeros_like(o_self), np.full_like(lse_self, -5e4)
+            o, lse = ok.merge_state_inplace(o_self.copy(), lse_self.copy(), o_cross, lse_cross, self.dt)
+            res.append(dict(o=o, lse=lse, oself=o_self, ocross=o_cross))
+        return res
 
     def run_other(self, trace):
         dumps, layer = [], 0
@@ -108,11 +149,24 @@ def test_oracle_matches_reference_outputs(name):
         elif op["op"] == "forward":
             n = sum(op["lens"])
             qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
-            outs = m.run_forward(res["trace"], qkv)
+            q2 = q2_for(op["seed"], L, n, hq, d, cfg["dtype"]) if op.get("shared") else None
+            outs, shared_outs = m.run_forward(res["trace"], qkv, q2)
             want = z[f"o_{idx}"].astype(np.float32)
             for layer in range(L):
                 _close(f"{name} op {idx} layer {layer} O", outs[layer], want[layer])
+                if q2 is not None:
+                    _close(f"{name} op {idx} layer {layer} shared-KV O", shared_outs[layer], z[f"os_{idx}"][layer].astype(np.float32))
             checked += 1
+        elif op["op"] == "forward_split":
+            n = sum(op["lens"])
+            qkv = qkv_for(op["seed"], L, n, hq, hkv, d, cfg["dtype"])
+            for layer, r in enumerate(m.run_split(res["trace"], qkv)):
+                for key in ("o", "oself", "ocross"):
+                    _close(f"{name} op {idx} layer {layer} {key}", r[key], z[f"{key}_{idx}"][layer].astype(np.float32))
+                _close(f"{name} op {idx} layer {layer} lse", r["lse"], z[f"lse_{idx}"][layer], atol=2e-3, rtol=1e-3)
+            checked += 1
+        elif op["op"] == "debug_get_kv_rejected":
+            pass
         else:
             dumps = m.run_other(res["trace"])
             if op["op"] == "debug_get_kv":

@@ -621,8 +621,8 @@ int impl_launch_count(const TVMFFIAny*, int32_t, TVMFFIAny* result) {
 // NAME (src/runtime/vm/kv_state.cc:33-116, paged_kv_cache.cc:2535-2639; callers python/tvm/relax/frontend/nn/llm/
 // kv_cache.py:124-351); register_vm_builtins() re-registers those names onto tvm_b200's cache (kv_cache_host.cc), so the
 // unmodified model runs on the sm_100a kernels.  The cache travels through the VM registers as an opaque pointer; the
-// callback arguments of the constructor (13..27) are accepted and ignored.  Unsupported entries (MLA, disaggregation,
-// cross / shared-KV attention) are registered too and raise.
+// callback arguments of the constructor (13..27) are accepted and ignored.  Unsupported entries (MLA, disaggregation) are
+// registered too and raise.
 // =====================================================================================================
 tvmb200_cache_t arg_cache(const TVMFFIAny* args, int i, const char* fn) {
   if (args[i].type_index != kTVMFFIOpaquePtr || args[i].v_ptr == nullptr)
@@ -884,8 +884,107 @@ int vm_attention_with_fused_qkv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny*
   TVMB200_VM_NONE();
   TVMB200_VM_END();
 }
+// shared checks of the q / k / v / o / lse tensors of the split attention entries (kv_state.cc:84-115)
+void expect_cuda_3d(const Tensor& t, const char* fn, const char* name) {
+  if (t.t->device.device_type != kDLCUDA) throw Err{"ValueError", fmt("%s: %s must be a CUDA tensor (there is no CPU fallback)", fn, name)};
+  if (t.ndim() != 3) throw Err{"ValueError", fmt("%s: %s must be 3-D", fn, name)};
+  (void)kv_dtype(t, fn, name);
+}
+void expect_lse(const Tensor& lse, const Tensor& q, const char* fn, const char* name) {
+  if (lse.t->device.device_type != kDLCUDA) throw Err{"ValueError", fmt("%s: %s must be a CUDA tensor", fn, name)};
+  expect_f32(lse, fn, name);
+  if (lse.ndim() != 2 || lse.shape(0) != q.shape(0) || lse.shape(1) != q.shape(1))
+    throw Err{"ValueError", fmt("%s: %s must be [total_len, num_qo_heads] float32", fn, name)};
+}
+int vm_self_attention(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_self_attention";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 8, fn);
+  const Tensor q = arg_tensor(a, 3, fn, "q_data"), k = arg_tensor(a, 4, fn, "k_data"), v = arg_tensor(a, 5, fn, "v_data");
+  const Tensor o = arg_tensor(a, 6, fn, "o_data"), lse = arg_tensor(a, 7, fn, "lse_data");
+  expect_cuda_3d(q, fn, "q_data");
+  expect_cuda_3d(k, fn, "k_data");
+  expect_cuda_3d(v, fn, "v_data");
+  expect_cuda_3d(o, fn, "o_data");
+  expect_lse(lse, q, fn, "lse_data");
+  if (k.shape(0) != q.shape(0) || v.shape(0) != q.shape(0) || o.shape(0) != q.shape(0))
+    throw Err{"ValueError", fmt("%s: q / k / v / o must have the same number of rows", fn)};
+  cache_rc(tvmb200_cache_self_attention(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+                                        q.data, k.data, v.data, o.data, static_cast<float*>(lse.data), q.shape(0),
+                                        env_stream(q.t->device.device_id)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_cross_attention(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_cross_attention";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 6, fn);
+  const Tensor q = arg_tensor(a, 3, fn, "q_data"), o = arg_tensor(a, 4, fn, "o_data"), lse = arg_tensor(a, 5, fn, "lse_data");
+  expect_cuda_3d(q, fn, "q_data");
+  expect_cuda_3d(o, fn, "o_data");
+  expect_lse(lse, q, fn, "lse_data");
+  if (o.shape(0) != q.shape(0)) throw Err{"ValueError", fmt("%s: q and o must have the same number of rows", fn)};
+  cache_rc(tvmb200_cache_cross_attention(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+                                         q.data, o.data, static_cast<float*>(lse.data), q.shape(0),
+                                         env_stream(q.t->device.device_id)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+int vm_attention_with_shared_kv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_attention_with_shared_kv";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 7, fn);
+  const Tensor q = arg_tensor(a, 3, fn, "q_data"), k = arg_tensor(a, 4, fn, "current_k_data");
+  const Tensor v = arg_tensor(a, 5, fn, "current_v_data"), o = arg_tensor(a, 6, fn, "o_data");
+  expect_cuda_3d(q, fn, "q_data");
+  expect_cuda_3d(k, fn, "current_k_data");
+  expect_cuda_3d(v, fn, "current_v_data");
+  expect_cuda_3d(o, fn, "o_data");
+  if (k.shape(0) != q.shape(0) || v.shape(0) != q.shape(0) || o.shape(0) != q.shape(0))
+    throw Err{"ValueError", fmt("%s: q / current_k / current_v / o must have the same number of rows", fn)};
+  cache_rc(tvmb200_cache_attention_with_shared_kv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "source_layer_id"),
+                                                  arg_float(a, 2, fn, "sm_scale"), q.data, k.data, v.data, o.data, q.shape(0),
+                                                  env_stream(q.t->device.device_id)));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+// returns Array<Tensor>{o_self_attn, lse_self_attn}, built with tvm-ffi's own "ffi.Array" constructor
+int vm_merge_attn_output_inplace(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.attention_kv_cache_merge_attn_output_inplace";
+  typedef int (*PFN_GetGlobal)(const TVMFFIByteArray*, TVMFFIObjectHandle*);
+  typedef int (*PFN_Call)(TVMFFIObjectHandle, TVMFFIAny*, int32_t, TVMFFIAny*);
+  typedef int (*PFN_DecRef)(TVMFFIObjectHandle);
+  static PFN_GetGlobal get_global = reinterpret_cast<PFN_GetGlobal>(ffi_sym("TVMFFIFunctionGetGlobal"));
+  static PFN_Call call = reinterpret_cast<PFN_Call>(ffi_sym("TVMFFIFunctionCall"));
+  static PFN_DecRef dec_ref = reinterpret_cast<PFN_DecRef>(ffi_sym("TVMFFIObjectDecRef"));
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 5, fn);
+  if (!get_global || !call || !dec_ref) throw Err{"RuntimeError", "libtvm_ffi.so is not loaded"};
+  const Tensor os = arg_tensor(a, 1, fn, "o_self_attn"), ls = arg_tensor(a, 2, fn, "lse_self_attn");
+  const Tensor oc = arg_tensor(a, 3, fn, "o_cross_attn"), lc = arg_tensor(a, 4, fn, "lse_cross_attn");
+  expect_cuda_3d(os, fn, "o_self_attn");
+  expect_cuda_3d(oc, fn, "o_cross_attn");
+  expect_lse(ls, os, fn, "lse_self_attn");
+  expect_lse(lc, os, fn, "lse_cross_attn");
+  expect_same_dtype(os, oc, fn, "o_cross_attn vs o_self_attn");
+  for (int i = 0; i < 3; ++i)
+    if (oc.shape(i) != os.shape(i)) throw Err{"ValueError", fmt("%s: o_cross_attn must have the shape of o_self_attn", fn)};
+  cache_rc(tvmb200_cache_merge_attn_output_inplace(arg_cache(a, 0, fn), os.data, static_cast<float*>(ls.data), oc.data,
+                                                   static_cast<const float*>(lc.data), os.shape(0), os.shape(1), os.shape(2),
+                                                   env_stream(os.t->device.device_id)));
+  static const char kArray[] = "ffi.Array";
+  const TVMFFIByteArray name{kArray, sizeof(kArray) - 1};
+  TVMFFIObjectHandle ctor = nullptr;
+  if (get_global(&name, &ctor) != 0) return -1;
+  if (ctor == nullptr) throw Err{"RuntimeError", "tvm-ffi global function ffi.Array is missing"};
+  TVMFFIAny pair[2] = {a[1], a[2]};
+  const int rc = call(ctor, pair, 2, result);
+  dec_ref(ctor);
+  if (rc != 0) return -1;
+  TVMB200_VM_END();
+}
 int vm_unsupported(void*, const TVMFFIAny*, int32_t, TVMFFIAny*) {
-  return raise("RuntimeError", "tvm_b200: this vm.builtin KV-cache entry (MLA / disaggregation / cross or shared-KV attention) is "
+  return raise("RuntimeError", "tvm_b200: this vm.builtin KV-cache entry (MLA / disaggregation) is "
                                "outside the PagedKVCache MHA hot path and is not implemented");
 }
 
@@ -913,11 +1012,11 @@ const VmBuiltin kVmBuiltins[] = {
     {"vm.builtin.kv_cache_disagg_prepare_recv", vm_unsupported},
     {"vm.builtin.kv_cache_disagg_mark_send", vm_unsupported},
     {"vm.builtin.attention_kv_cache_debug_get_kv_mla", vm_unsupported},
-    {"vm.builtin.attention_kv_cache_self_attention", vm_unsupported},
-    {"vm.builtin.attention_kv_cache_cross_attention", vm_unsupported},
-    {"vm.builtin.attention_kv_cache_attention_with_shared_kv", vm_unsupported},
+    {"vm.builtin.attention_kv_cache_self_attention", vm_self_attention},
+    {"vm.builtin.attention_kv_cache_cross_attention", vm_cross_attention},
+    {"vm.builtin.attention_kv_cache_attention_with_shared_kv", vm_attention_with_shared_kv},
+    {"vm.builtin.attention_kv_cache_merge_attn_output_inplace", vm_merge_attn_output_inplace},
     {"vm.builtin.attention_kv_cache_append_mla_kv", vm_unsupported},
-    {"vm.builtin.attention_kv_cache_merge_attn_output_inplace", vm_unsupported},
 };
 
 // (allow_override) -> number of names registered

@@ -113,6 +113,14 @@ class Cache {
   }
   void AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void* qkv, void* o, int64_t rows,
                              cudaStream_t stream);
+  void SelfAttention(int64_t layer_id, double sm_scale, const void* q, const void* k, const void* v, void* o, float* lse,
+                     int64_t rows, cudaStream_t stream);
+  void CrossAttention(int64_t layer_id, double sm_scale, const void* q, void* o, float* lse, int64_t rows,
+                      cudaStream_t stream);
+  void AttentionWithSharedKV(int64_t source_layer_id, double sm_scale, const void* q, const void* cur_k, const void* cur_v,
+                             void* o, int64_t rows, cudaStream_t stream);
+  void MergeAttnOutputInplace(void* o_self, float* lse_self, const void* o_cross, const float* lse_cross, int64_t n,
+                              int64_t num_heads, int64_t head_dim, cudaStream_t stream);
   void DebugGetKV(int64_t seq_id, int64_t start, int64_t end, void* k_out, void* v_out, cudaStream_t stream);
   void QueryPositions(const int32_t** ptr, int64_t* n, cudaStream_t stream) {
     SyncAux(stream);
@@ -280,8 +288,13 @@ class Cache {
   }
   void BuildAuxViews();
   void SyncAux(cudaStream_t compute);
-  void CrossAttention(int64_t local_layer, void* q, void* o, float* lse, double sm_scale, bool is_first, bool causal,
-                      cudaStream_t st);
+  int64_t CheckLayer(int64_t layer_id) const;
+  void MarkAttentionDone(cudaStream_t st);
+  void SelfAttnInternal(const void* q, const void* k, const void* v, void* o, float* lse, double sm_scale, cudaStream_t st);
+  bool CrossAttnInternal(int64_t layer_id, const void* q, void* o, float* lse, double sm_scale, bool is_first, bool causal,
+                         const void* fused_qkv, cudaStream_t st);
+  void AttentionInternal(int64_t layer_id, const void* q, const void* k, const void* v, void* o, double sm_scale,
+                         const void* fused_qkv, cudaStream_t st);
 
   // ---- trace helpers ----
   struct Arg {
@@ -995,11 +1008,141 @@ void Cache::SyncAux(cudaStream_t compute) {
   dirty_ = false;
 }
 
-void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void* qkv, void* o, int64_t rows,
-                                  cudaStream_t st) {
+// MHASelfAttnInternal (paged_kv_cache.cc:2182-2206): the new tokens against themselves, causal or tree-masked.
+void Cache::SelfAttnInternal(const void* q, const void* k, const void* v, void* o, float* lse, double sm_scale,
+                             cudaStream_t st) {
+  const int64_t n = total_append_;
+  const int32_t hq = static_cast<int32_t>(num_qo_heads_), hkv = static_cast<int32_t>(num_kv_heads_),
+                d = static_cast<int32_t>(head_dim_);
+  const bool plan = planning_only();
+  const int rot = rope_mode_ == TVMB200_ROPE_INLINE;
+  if (is_chain_on_depths_[0]) {
+    TRACE("prefill_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
+                             TI(v_q_rope_pos_), TI(v_k_ragged_rope_off_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(1),
+                             SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
+    if (!plan)
+      Rc(tvmb200_attention_prefill_ragged(q, dev(v_cur_len_indptr_), k, v, dev(v_cur_len_indptr_), dev(v_q_rope_pos_),
+                                          dev(v_k_ragged_rope_off_), o, lse, static_cast<int32_t>(cur_batch_),
+                                          static_cast<int32_t>(n), static_cast<int32_t>(n), hq, hkv, d, 1, rot,
+                                          static_cast<float>(rotary_scale_), static_cast<float>(rotary_theta_),
+                                          static_cast<float>(sm_scale), dtype_, st));
+  } else {
+    TRACE("tree_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
+                          TI(v_q_rope_pos_), TI(v_tree_mn_[0]), TI(v_tree_mask_[0]), TF({n, hq, d}), TF({n, hq}, "float32"),
+                          SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
+    if (!plan)
+      Rc(tvmb200_attention_prefill_tree_ragged(q, dev(v_cur_len_indptr_), k, v, dev(v_cur_len_indptr_), dev(v_q_rope_pos_),
+                                               dev(v_tree_mn_[0]), dev(v_tree_mask_[0]), o, lse,
+                                               static_cast<int32_t>(cur_batch_), static_cast<int32_t>(n),
+                                               static_cast<int32_t>(n), hq, hkv, d, rot, static_cast<float>(rotary_scale_),
+                                               static_cast<float>(rotary_theta_), static_cast<float>(sm_scale), dtype_, st));
+  }
+}
+
+// MHACrossAttnInternal (paged_kv_cache.cc:2216-2299): q against the cached pages of every block depth; the first kernel
+// writes (o, lse), every later one writes the temporaries and is merged in place.  fused_qkv != nullptr: the decode
+// depth runs as the fused split_rotary + transpose_append + decode launch on the un-split qkv.
+bool Cache::CrossAttnInternal(int64_t layer_id, const void* q, void* o, float* lse_out, double sm_scale, bool is_first,
+                              bool causal, const void* fused_qkv, cudaStream_t st) {
+  const int64_t local = layer_id - layer_begin_;
+  const int64_t n = total_append_;
+  const int32_t hq = static_cast<int32_t>(num_qo_heads_), hkv = static_cast<int32_t>(num_kv_heads_),
+                d = static_cast<int32_t>(head_dim_), ps = static_cast<int32_t>(page_size_);
+  const bool plan = planning_only();
+  void* pages = plan ? nullptr : pages_[local];
+  const int rot = rope_mode_ == TVMB200_ROPE_INLINE;
+  const int64_t apply_rope = rope_mode_ == TVMB200_ROPE_NORMAL;
+  const bool layer_sw = attn_kinds_[layer_id] == TVMB200_ATTN_MHA_SLIDING;
+  const bool sw_flavour = support_sw_ || layer_sw;  // the `_sliding_window` kernels take [3,B] length_info
+  bool cross_done = false;
+  for (int dd = 0; dd < num_depths_; ++dd) {
+    if (page_indices_[dd].empty()) continue;
+    void* out = is_first ? o : tmp_o_;
+    float* lse = is_first ? lse_out : tmp_lse_;
+    const View &pip = layer_sw ? v_page_indptr_sw_[dd] : v_page_indptr_[dd];
+    const View &piv = layer_sw ? v_page_indices_sw_[dd] : v_page_indices_[dd];
+    const View &li = layer_sw ? v_length_info_sw_[dd] : v_length_info_[dd];
+    const View &kro = layer_sw ? v_k_rope_off_sw_[dd] : v_k_rope_off_[dd];
+    const double theta = layer_sw ? 10000.0 : rotary_theta_;
+    const double scale = layer_sw ? 1.0 : rotary_scale_;
+    const int32_t B = static_cast<int32_t>(v_qo_indptr_[dd].size - 1);
+    const int32_t nnz = static_cast<int32_t>(piv.size);
+    if (append_before_attn_ && !is_chain_on_depths_[dd]) {
+      TRACE("tree_paged", {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li),
+                           TI(kro), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta),
+                           SF(sm_scale), TI(v_tree_mn_[dd]), TI(v_tree_mask_[dd])});
+      if (!plan)
+        Rc(tvmb200_attention_prefill_tree_paged(q, dev(v_qo_indptr_[dd]), pages, dev(pip), dev(piv), dev(li), dev(kro),
+                                                dev(v_q_rope_pos_), out, lse, B, static_cast<int32_t>(n), nnz,
+                                                num_total_pages_, hq, hkv, ps, d, rot, static_cast<float>(scale),
+                                                static_cast<float>(theta), static_cast<float>(sm_scale), dev(v_tree_mn_[dd]),
+                                                dev(v_tree_mask_[dd]), dtype_, st));
+    } else if (use_decode_kernel_[dd]) {
+      TRACE(sw_flavour ? "decode_sliding_window" : "decode",
+            {TF({n, hq, d}), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro), TI(v_q_rope_pos_),
+             TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta), SF(sm_scale)});
+      if (fused_qkv != nullptr)
+        Rc(tvmb200_attention_decode_fused_qkv(fused_qkv, dev(v_q_rope_pos_), dev(v_append_pos_), pages, dev(pip), dev(piv),
+                                              dev(li), dev(kro), out, lse, B, nnz, num_total_pages_, hq, hkv, ps, d, 0,
+                                              apply_rope, static_cast<float>(scale), static_cast<float>(theta),
+                                              static_cast<float>(sm_scale), dtype_, st));
+      else if (!plan)
+        Rc(tvmb200_attention_decode(q, pages, dev(pip), dev(piv), dev(li), dev(kro), dev(v_q_rope_pos_), out, lse, B, nnz,
+                                    num_total_pages_, hq, hkv, ps, d, sw_flavour ? 1 : 0, rot, static_cast<float>(scale),
+                                    static_cast<float>(theta), static_cast<float>(sm_scale), dtype_, st));
+    } else {
+      TRACE(sw_flavour ? "prefill_sliding_window" : "prefill",
+            {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro),
+             TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(causal ? 1 : 0), SI(rot), SF(scale), SF(theta),
+             SF(sm_scale)});
+      if (!plan)
+        Rc(tvmb200_attention_prefill_paged(q, dev(v_qo_indptr_[dd]), pages, dev(pip), dev(piv), dev(li), dev(kro),
+                                           dev(v_q_rope_pos_), out, lse, B, static_cast<int32_t>(n), nnz, num_total_pages_,
+                                           hq, hkv, ps, d, sw_flavour ? 1 : 0, sw_flavour ? static_cast<int32_t>(layer_sws_) : 0,
+                                           causal ? 1 : 0, rot, static_cast<float>(scale), static_cast<float>(theta),
+                                           static_cast<float>(sm_scale), dtype_, st));
+    }
+    if (!is_first) {
+      TRACE("merge", {TF({n, hq, d}), TF({n, hq}, "float32"), TF({n, hq, d}), TF({n, hq}, "float32")});
+      if (!plan) Rc(tvmb200_merge_state_inplace(o, lse_out, tmp_o_, tmp_lse_, n, hq, d, dtype_, st));
+    } else {
+      is_first = false;
+    }
+    cross_done = true;
+  }
+  return cross_done;
+}
+
+// AttentionInternal (paged_kv_cache.cc:2161-2180)
+void Cache::AttentionInternal(int64_t layer_id, const void* q, const void* k, const void* v, void* o, double sm_scale,
+                              const void* fused_qkv, cudaStream_t st) {
+  bool is_first = true;
+  if (!append_before_attn_) {
+    is_first = false;
+    SelfAttnInternal(q, k, v, o, merged_lse_, sm_scale, st);
+  }
+  const bool self_done = !is_first;
+  const bool causal = !append_before_attn_ && attn_kinds_[layer_id] == TVMB200_ATTN_MHA_SLIDING;
+  const bool cross_done = CrossAttnInternal(layer_id, q, o, merged_lse_, sm_scale, is_first, causal, fused_qkv, st);
+  HCHECK(self_done || cross_done, "Both self-attention and cross-attention are not computed.");
+}
+
+int64_t Cache::CheckLayer(int64_t layer_id) const {
   const int64_t local = layer_id - layer_begin_;
   HCHECK(local >= 0 && local < num_layers_, "layer_id %ld is outside this cache's layers [%ld, %ld)", (long)layer_id,
          (long)layer_begin_, (long)(layer_begin_ + num_layers_));
+  return local;
+}
+
+void Cache::MarkAttentionDone(cudaStream_t st) {
+  if (planning_only()) return;
+  HCUDA(cudaEventRecord(ev_attn_done_, st));
+  HCUDA(cudaEventRecord(ev_aux_readers_[aux_cur_], st));
+}
+
+void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void* qkv, void* o, int64_t rows,
+                                  cudaStream_t st) {
+  const int64_t local = CheckLayer(layer_id);
   const int64_t n = total_append_;
   HCHECK(n <= rows, "qkv has %ld rows but the batch appends %ld tokens", (long)rows, (long)n);
   SyncAux(st);
@@ -1040,100 +1183,57 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   }
 
   // Part 5: attention
-  bool is_first = true;
-  const int rot = rope_mode_ == TVMB200_ROPE_INLINE;
-  if (!append_before_attn_) {
-    is_first = false;
-    if (is_chain_on_depths_[0]) {
-      TRACE("prefill_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
-                               TI(v_q_rope_pos_), TI(v_k_ragged_rope_off_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(1),
-                               SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
-      if (!plan)
-        Rc(tvmb200_attention_prefill_ragged(tmp_q_, dev(v_cur_len_indptr_), tmp_k_, tmp_v_, dev(v_cur_len_indptr_),
-                                            dev(v_q_rope_pos_), dev(v_k_ragged_rope_off_), o, merged_lse_,
-                                            static_cast<int32_t>(cur_batch_), static_cast<int32_t>(n), static_cast<int32_t>(n),
-                                            hq, hkv, d, 1, rot, static_cast<float>(rotary_scale_),
-                                            static_cast<float>(rotary_theta_), static_cast<float>(sm_scale), dtype_, st));
-    } else {
-      TRACE("tree_ragged", {TF({n, hq, d}), TI(v_cur_len_indptr_), TF({n, hkv, d}), TF({n, hkv, d}), TI(v_cur_len_indptr_),
-                            TI(v_q_rope_pos_), TI(v_tree_mn_[0]), TI(v_tree_mask_[0]), TF({n, hq, d}), TF({n, hq}, "float32"),
-                            SI(rot), SF(rotary_scale_), SF(rotary_theta_), SF(sm_scale)});
-      if (!plan)
-        Rc(tvmb200_attention_prefill_tree_ragged(tmp_q_, dev(v_cur_len_indptr_), tmp_k_, tmp_v_, dev(v_cur_len_indptr_),
-                                                 dev(v_q_rope_pos_), dev(v_tree_mn_[0]), dev(v_tree_mask_[0]), o, merged_lse_,
-                                                 static_cast<int32_t>(cur_batch_), static_cast<int32_t>(n),
-                                                 static_cast<int32_t>(n), hq, hkv, d, rot, static_cast<float>(rotary_scale_),
-                                                 static_cast<float>(rotary_theta_), static_cast<float>(sm_scale), dtype_, st));
-    }
-  }
-  const bool self_done = !is_first;
-  const bool causal = !append_before_attn_ && attn_kinds_[layer_id] == TVMB200_ATTN_MHA_SLIDING;
-  bool cross_done = false;
-  {
-    const bool layer_sw = attn_kinds_[layer_id] == TVMB200_ATTN_MHA_SLIDING;
-    const bool sw_flavour = support_sw_ || layer_sw;  // the `_sliding_window` kernels take [3,B] length_info
-    for (int dd = 0; dd < num_depths_; ++dd) {
-      if (page_indices_[dd].empty()) continue;
-      void* out = is_first ? o : tmp_o_;
-      float* lse = is_first ? merged_lse_ : tmp_lse_;
-      const View &pip = layer_sw ? v_page_indptr_sw_[dd] : v_page_indptr_[dd];
-      const View &piv = layer_sw ? v_page_indices_sw_[dd] : v_page_indices_[dd];
-      const View &li = layer_sw ? v_length_info_sw_[dd] : v_length_info_[dd];
-      const View &kro = layer_sw ? v_k_rope_off_sw_[dd] : v_k_rope_off_[dd];
-      const double theta = layer_sw ? 10000.0 : rotary_theta_;
-      const double scale = layer_sw ? 1.0 : rotary_scale_;
-      const int32_t B = static_cast<int32_t>(v_qo_indptr_[dd].size - 1);
-      const int32_t nnz = static_cast<int32_t>(piv.size);
-      if (append_before_attn_ && !is_chain_on_depths_[dd]) {
-        TRACE("tree_paged", {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li),
-                             TI(kro), TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta),
-                             SF(sm_scale), TI(v_tree_mn_[dd]), TI(v_tree_mask_[dd])});
-        if (!plan)
-          Rc(tvmb200_attention_prefill_tree_paged(tmp_q_, dev(v_qo_indptr_[dd]), pages, dev(pip), dev(piv), dev(li), dev(kro),
-                                                  dev(v_q_rope_pos_), out, lse, B, static_cast<int32_t>(n), nnz,
-                                                  num_total_pages_, hq, hkv, ps, d, rot, static_cast<float>(scale),
-                                                  static_cast<float>(theta), static_cast<float>(sm_scale), dev(v_tree_mn_[dd]),
-                                                  dev(v_tree_mask_[dd]), dtype_, st));
-      } else if (use_decode_kernel_[dd]) {
-        TRACE(sw_flavour ? "decode_sliding_window" : "decode",
-              {TF({n, hq, d}), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro), TI(v_q_rope_pos_),
-               TF({n, hq, d}), TF({n, hq}, "float32"), SI(rot), SF(scale), SF(theta), SF(sm_scale)});
-        if (fuse_step)
-          Rc(tvmb200_attention_decode_fused_qkv(qkv, dev(v_q_rope_pos_), dev(v_append_pos_), pages, dev(pip), dev(piv), dev(li),
-                                                dev(kro), out, lse, B, nnz, num_total_pages_, hq, hkv, ps, d, 0, apply_rope,
-                                                static_cast<float>(scale), static_cast<float>(theta),
-                                                static_cast<float>(sm_scale), dtype_, st));
-        else if (!plan)
-          Rc(tvmb200_attention_decode(tmp_q_, pages, dev(pip), dev(piv), dev(li), dev(kro), dev(v_q_rope_pos_), out, lse, B,
-                                      nnz, num_total_pages_, hq, hkv, ps, d, sw_flavour ? 1 : 0, rot, static_cast<float>(scale),
-                                      static_cast<float>(theta), static_cast<float>(sm_scale), dtype_, st));
-      } else {
-        TRACE(sw_flavour ? "prefill_sliding_window" : "prefill",
-              {TF({n, hq, d}), TI(v_qo_indptr_[dd]), TF({num_total_pages_, 2, hkv, ps, d}), TI(pip), TI(piv), TI(li), TI(kro),
-               TI(v_q_rope_pos_), TF({n, hq, d}), TF({n, hq}, "float32"), SI(causal ? 1 : 0), SI(rot), SF(scale), SF(theta),
-               SF(sm_scale)});
-        if (!plan)
-          Rc(tvmb200_attention_prefill_paged(tmp_q_, dev(v_qo_indptr_[dd]), pages, dev(pip), dev(piv), dev(li), dev(kro),
-                                             dev(v_q_rope_pos_), out, lse, B, static_cast<int32_t>(n), nnz, num_total_pages_,
-                                             hq, hkv, ps, d, sw_flavour ? 1 : 0, sw_flavour ? static_cast<int32_t>(layer_sws_) : 0,
-                                             causal ? 1 : 0, rot, static_cast<float>(scale), static_cast<float>(theta),
-                                             static_cast<float>(sm_scale), dtype_, st));
-      }
-      if (!is_first) {
-        TRACE("merge", {TF({n, hq, d}), TF({n, hq}, "float32"), TF({n, hq, d}), TF({n, hq}, "float32")});
-        if (!plan) Rc(tvmb200_merge_state_inplace(o, merged_lse_, tmp_o_, tmp_lse_, n, hq, d, dtype_, st));
-      } else {
-        is_first = false;
-      }
-      cross_done = true;
-    }
-  }
-  HCHECK(self_done || cross_done, "Both self-attention and cross-attention are not computed.");
+  AttentionInternal(layer_id, tmp_q_, tmp_k_, tmp_v_, o, sm_scale, fuse_step ? qkv : nullptr, st);
   if (!append_before_attn_) append();
-  if (!plan) {
-    HCUDA(cudaEventRecord(ev_attn_done_, st));
-    HCUDA(cudaEventRecord(ev_aux_readers_[aux_cur_], st));
-  }
+  MarkAttentionDone(st);
+}
+
+// SelfAttention (paged_kv_cache.cc:1404-1445): q [n, Hq, D] against the step's own k / v [n, Hkv, D] (not the cache).
+void Cache::SelfAttention(int64_t layer_id, double sm_scale, const void* q, const void* k, const void* v, void* o,
+                          float* lse, int64_t rows, cudaStream_t st) {
+  CheckLayer(layer_id);
+  HCHECK(attn_kinds_[layer_id] == TVMB200_ATTN_MHA, "self_attention: layer %ld is not an MHA layer (MLA is not built)",
+         (long)layer_id);
+  HCHECK(rows == total_append_, "self_attention: the tensors have %ld rows but the batch appends %ld tokens", (long)rows,
+         (long)total_append_);
+  SyncAux(st);
+  SelfAttnInternal(q, k, v, o, lse, sm_scale, st);
+  MarkAttentionDone(st);
+}
+
+// CrossAttention (paged_kv_cache.cc:1447-1485): q against the cached KV of the layer, no causal mask.
+void Cache::CrossAttention(int64_t layer_id, double sm_scale, const void* q, void* o, float* lse, int64_t rows,
+                           cudaStream_t st) {
+  CheckLayer(layer_id);
+  HCHECK(attn_kinds_[layer_id] == TVMB200_ATTN_MHA, "cross_attention: layer %ld is not an MHA layer (MLA is not built)",
+         (long)layer_id);
+  HCHECK(rows == total_append_, "cross_attention: the tensors have %ld rows but the batch appends %ld tokens", (long)rows,
+         (long)total_append_);
+  SyncAux(st);
+  CrossAttnInternal(layer_id, q, o, lse, sm_scale, /*is_first=*/true, /*causal=*/false, nullptr, st);
+  MarkAttentionDone(st);
+}
+
+// AttentionWithSharedKV (paged_kv_cache.cc:1487-1529): another logical layer queries the K / V of `source_layer_id`
+// (pages already hold the step's tokens when the append ran before the source layer's attention).
+void Cache::AttentionWithSharedKV(int64_t source_layer_id, double sm_scale, const void* q, const void* cur_k,
+                                  const void* cur_v, void* o, int64_t rows, cudaStream_t st) {
+  CheckLayer(source_layer_id);
+  HCHECK(rows == total_append_, "attention_with_shared_kv: the tensors have %ld rows but the batch appends %ld tokens",
+         (long)rows, (long)total_append_);
+  SyncAux(st);
+  AttentionInternal(source_layer_id, q, cur_k, cur_v, o, sm_scale, nullptr, st);
+  MarkAttentionDone(st);
+}
+
+// MergeAttnOutputInplace (paged_kv_cache.cc:1553-1559): f_merge_inplace_[1] on caller tensors.
+void Cache::MergeAttnOutputInplace(void* o_self, float* lse_self, const void* o_cross, const float* lse_cross, int64_t n,
+                                   int64_t num_heads, int64_t head_dim, cudaStream_t st) {
+  TRACE("merge", {TF({n, num_heads, head_dim}), TF({n, num_heads}, "float32"), TF({n, num_heads, head_dim}),
+                  TF({n, num_heads}, "float32")});
+  if (!planning_only())
+    Rc(tvmb200_merge_state_inplace(o_self, lse_self, o_cross, lse_cross, n, static_cast<int32_t>(num_heads),
+                                   static_cast<int32_t>(head_dim), dtype_, st));
 }
 
 void Cache::CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n) {
@@ -1228,6 +1328,10 @@ void Cache::DebugGetKV(int64_t seq_id, int64_t start, int64_t end, void* k_out, 
       pos.push_back(b.page_ids[off / ps] * ps + off % ps);
     }
   }
+  // the reference dumps layer by layer and stops at the first non-MHA layer (paged_kv_cache.cc:1715-1717, indexed by the
+  // local layer id as there); here nothing is dumped in that case
+  for (int64_t l = 0; l < num_layers_; ++l)
+    HCHECK(attn_kinds_[l] == TVMB200_ATTN_MHA, "Only MHA is supported for DebugGetKV");
   View v;
   v.size = end - start;
   for (int64_t l = 0; l < num_layers_; ++l)
@@ -1311,6 +1415,27 @@ int tvmb200_cache_get_query_positions(tvmb200_cache_t c, const int32_t** p, int6
 int tvmb200_cache_attention_with_fused_qkv(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* qkv, void* o,
                                            int64_t rows, tvmb200_stream_t st) {
   CACHE_API_BEGIN(); c->impl->AttentionWithFusedQKV(layer, sm_scale, qkv, o, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+}
+int tvmb200_cache_self_attention(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* q, const void* k,
+                                 const void* v, void* o, float* lse, int64_t rows, tvmb200_stream_t st) {
+  CACHE_API_BEGIN(); c->impl->SelfAttention(layer, sm_scale, q, k, v, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+}
+int tvmb200_cache_cross_attention(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* q, void* o, float* lse,
+                                  int64_t rows, tvmb200_stream_t st) {
+  CACHE_API_BEGIN(); c->impl->CrossAttention(layer, sm_scale, q, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+}
+int tvmb200_cache_attention_with_shared_kv(tvmb200_cache_t c, int64_t source_layer, double sm_scale, const void* q,
+                                           const void* cur_k, const void* cur_v, void* o, int64_t rows, tvmb200_stream_t st) {
+  CACHE_API_BEGIN();
+  c->impl->AttentionWithSharedKV(source_layer, sm_scale, q, cur_k, cur_v, o, rows, static_cast<cudaStream_t>(st));
+  CACHE_API_END();
+}
+int tvmb200_cache_merge_attn_output_inplace(tvmb200_cache_t c, void* o_self, float* lse_self, const void* o_cross,
+                                            const float* lse_cross, int64_t n, int64_t num_heads, int64_t head_dim,
+                                            tvmb200_stream_t st) {
+  CACHE_API_BEGIN();
+  c->impl->MergeAttnOutputInplace(o_self, lse_self, o_cross, lse_cross, n, num_heads, head_dim, static_cast<cudaStream_t>(st));
+  CACHE_API_END();
 }
 int tvmb200_cache_debug_get_kv(tvmb200_cache_t c, int64_t s, int64_t a, int64_t b, void* k, void* v, tvmb200_stream_t st) {
   CACHE_API_BEGIN(); c->impl->DebugGetKV(s, a, b, k, v, static_cast<cudaStream_t>(st)); CACHE_API_END();

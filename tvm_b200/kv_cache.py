@@ -62,6 +62,10 @@ def _lib():
         L.tvmb200_cache_get_total_sequence_length.argtypes = [P, POINTER(I32)]
         L.tvmb200_cache_get_query_positions.argtypes = [P, POINTER(P), POINTER(I64), P]
         L.tvmb200_cache_attention_with_fused_qkv.argtypes = [P, I64, c_double, P, P, I64, P]
+        L.tvmb200_cache_self_attention.argtypes = [P, I64, c_double, P, P, P, P, P, I64, P]
+        L.tvmb200_cache_cross_attention.argtypes = [P, I64, c_double, P, P, P, I64, P]
+        L.tvmb200_cache_attention_with_shared_kv.argtypes = [P, I64, c_double, P, P, P, P, I64, P]
+        L.tvmb200_cache_merge_attn_output_inplace.argtypes = [P, P, P, P, P, I64, I64, I64, P]
         L.tvmb200_cache_debug_get_kv.argtypes = [P, I64, I64, I64, P, P, P]
         L.tvmb200_cache_pages.argtypes = [P, I64, POINTER(P), POINTER(I64)]
         L.tvmb200_cache_set_trace.argtypes = [P, I32]
@@ -177,6 +181,50 @@ class PagedKVCache:
             return
         capi._check(_lib().tvmb200_cache_attention_with_fused_qkv(self._h, layer_id, sm_scale, capi._p(qkv), capi._p(o),
                                                                   qkv.shape[0], capi._stream(qkv)))
+
+    def self_attention(self, layer_id, sm_scale, q, k, v, o, lse):
+        """q / o [n, Hq, D], k / v [n, Hkv, D], lse [n, Hq] f32: the step's tokens against themselves (kv_state.cc:84-90)."""
+        if self.device is None:
+            capi._check(_lib().tvmb200_cache_self_attention(self._h, layer_id, sm_scale, None, None, None, None, None,
+                                                            self._rows(q), None))
+            return
+        capi._check(_lib().tvmb200_cache_self_attention(self._h, layer_id, sm_scale, capi._p(q), capi._p(k), capi._p(v),
+                                                        capi._p(o), capi._p(lse), q.shape[0], capi._stream(q)))
+
+    def cross_attention(self, layer_id, sm_scale, q, o, lse):
+        """q against the cached KV of `layer_id`, no causal mask (kv_state.cc:91-96)."""
+        if self.device is None:
+            capi._check(_lib().tvmb200_cache_cross_attention(self._h, layer_id, sm_scale, None, None, None, self._rows(q), None))
+            return
+        capi._check(_lib().tvmb200_cache_cross_attention(self._h, layer_id, sm_scale, capi._p(q), capi._p(o), capi._p(lse),
+                                                         q.shape[0], capi._stream(q)))
+
+    def attention_with_shared_kv(self, source_layer_id, sm_scale, q, current_k, current_v, o):
+        """A layer without KV of its own attends over the K / V of `source_layer_id` (kv_state.cc:97-104)."""
+        if self.device is None:
+            capi._check(_lib().tvmb200_cache_attention_with_shared_kv(self._h, source_layer_id, sm_scale, None, None, None,
+                                                                      None, self._rows(q), None))
+            return
+        capi._check(_lib().tvmb200_cache_attention_with_shared_kv(self._h, source_layer_id, sm_scale, capi._p(q),
+                                                                  capi._p(current_k), capi._p(current_v), capi._p(o),
+                                                                  q.shape[0], capi._stream(q)))
+
+    def merge_attn_output_inplace(self, o_self, lse_self, o_cross, lse_cross):
+        """(o_self, lse_self) <- merge with (o_cross, lse_cross); returns the pair like the reference (kv_state.cc:109-115)."""
+        if self.device is None:
+            n = self._rows(o_self)
+            capi._check(_lib().tvmb200_cache_merge_attn_output_inplace(self._h, None, None, None, None, n, self.num_qo_heads,
+                                                                       self.head_dim, None))
+            return o_self, lse_self
+        capi._check(_lib().tvmb200_cache_merge_attn_output_inplace(self._h, capi._p(o_self), capi._p(lse_self),
+                                                                   capi._p(o_cross), capi._p(lse_cross), o_self.shape[0],
+                                                                   o_self.shape[1], o_self.shape[2], capi._stream(o_self)))
+        return o_self, lse_self
+
+    @staticmethod
+    def _rows(x):
+        """Planning-only caches take the row count (an int) where a device cache takes the tensor."""
+        return int(x) if isinstance(x, int) else int(x.shape[0])
 
     def debug_get_kv(self, seq_id, start_pos, end_pos, k_out=None, v_out=None):
         if self.device is None:
