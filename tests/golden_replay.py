@@ -122,8 +122,14 @@ def replay(name, device, on_forward=None, on_kv=None, on_shared=None, on_split=N
 
             from tvm_b200 import capi
 
+            kk = None
+            if device is not None:
+                import torch
+
+                kk = torch.zeros((L, 1, hkv, d), dtype=torch.float16 if cfg["dtype"] == "float16" else torch.bfloat16,
+                                 device="cuda")
             with pytest.raises(capi.TvmB200Error, match="Only MHA is supported for DebugGetKV"):
-                cache.debug_get_kv(op["seq"], 0, 1)
+                cache.debug_get_kv(op["seq"], 0, 1, kk, kk)
             cache.take_trace()  # the reference dumps the MHA layers in front of the offending one before it raises
             continue
         elif k == "forward":

@@ -15,7 +15,9 @@ NAMES = [
     "vm.builtin.attention_kv_cache_commit_accepted_token_tree_nodes", "vm.builtin.attention_kv_cache_empty",
     "vm.builtin.attention_kv_cache_get_num_available_pages", "vm.builtin.attention_kv_cache_get_total_sequence_length",
     "vm.builtin.attention_kv_cache_get_query_positions", "vm.builtin.attention_kv_cache_debug_get_kv",
-    "vm.builtin.attention_kv_cache_attention_with_fused_qkv",
+    "vm.builtin.attention_kv_cache_attention_with_fused_qkv", "vm.builtin.attention_kv_cache_self_attention",
+    "vm.builtin.attention_kv_cache_cross_attention", "vm.builtin.attention_kv_cache_attention_with_shared_kv",
+    "vm.builtin.attention_kv_cache_merge_attn_output_inplace",
 ]
 
 
@@ -52,6 +54,23 @@ def test_create_without_cuda_tensor_fails_loudly(built_lib):
         _create(f, torch.zeros((), dtype=torch.float16))
     with pytest.raises(Exception, match="cache returned by"):
         f["vm.builtin.kv_state_add_sequence"](3, 0)
+
+
+def test_split_attention_entries_reject_cpu_tensors(built_lib):
+    import torch
+
+    f = _register()
+    q = torch.zeros((2, 4, 128), dtype=torch.float16)
+    lse = torch.zeros((2, 4), dtype=torch.float32)
+    # no CPU fallback behind any of the entries
+    with pytest.raises(Exception, match="must be a CUDA tensor"):
+        f["vm.builtin.attention_kv_cache_self_attention"](0, 0, 1.0, q, q, q, q, lse)
+    with pytest.raises(Exception, match="must be a CUDA tensor"):
+        f["vm.builtin.attention_kv_cache_cross_attention"](0, 0, 1.0, q, q, lse)
+    with pytest.raises(Exception, match="must be a CUDA tensor"):
+        f["vm.builtin.attention_kv_cache_attention_with_shared_kv"](0, 0, 1.0, q, q, q, q)
+    with pytest.raises(Exception, match="must be a CUDA tensor"):
+        f["vm.builtin.attention_kv_cache_merge_attn_output_inplace"](0, q, lse, q, lse)
 
 
 @pytest.mark.gpu
