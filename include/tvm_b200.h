@@ -67,15 +67,31 @@ TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
 /*!
  * \brief RoPE frequency scaling the reference compiles into every PrimFunc that rotates (`rope_scaling` dict ->
  *  switch_rope_freq_func, position_embedding.py:257-299: fused_rope and the inline-RoPE paths of the attention kernels,
- *  _kernel_common.py:115-127).  A loaded library needs it as state: kind TVMB200_ROPE_SCALING_NONE = rope_freq_default,
- *  TVMB200_ROPE_SCALING_LLAMA3 = rope_freq_llama3 (position_embedding.py:130-160; Llama-3.1: factor 8, low 1, high 4,
- *  original_max_position_embeddings 8192).  Applies to tvmb200_split_rotary[_append] and to rotary_mode = 1 of the
- *  attention entries, for every call made afterwards in this process.  Other rope types are rejected.
+ *  _kernel_common.py:115-127).  A loaded library needs it as state, for every call made afterwards in this process:
+ *    TVMB200_ROPE_SCALING_NONE   rope_freq_default
+ *    TVMB200_ROPE_SCALING_LLAMA3 rope_freq_llama3 (position_embedding.py:130-160; Llama-3.1: factor 8, low 1, high 4,
+ *                                original_max_position_embeddings 8192) -- tvmb200_split_rotary[_append], rotary_mode = 1
+ *                                of the attention entries and the fused decode step
+ *    TVMB200_ROPE_SCALING_GPTJ   rope_freq_gptj + interleaved pairs (position_embedding.py:70-76, :509-514)
+ *    TVMB200_ROPE_SCALING_LLAMA4 rope_freq_llama4 (position_embedding.py:79-127; high == low selects its threshold branch)
+ *    TVMB200_ROPE_SCALING_YARN   rope_freq_yarn (position_embedding.py:192-254), set by tvmb200_set_rope_scaling_yarn;
+ *                                inv_theta_log_scale <= 0 means 1 / (2 ln rope_theta) (kv_cache.py:355-366)
+ *  gptj / llama4 / yarn are implemented by tvmb200_split_rotary[_append] only (rope mode "normal", where the cache
+ *  holds rotated K): while one of them is set, rotary_mode = 1 and the fused decode step with apply_rope > 0 are
+ *  rejected, and the host cache runs decode steps as split_rotary + append + decode.  longrope (`rope_ext_factors`) is
+ *  rejected: the reference's own longrope PrimFunc does not build at this commit, so it cannot be pinned.
  */
 #define TVMB200_ROPE_SCALING_NONE 0
 #define TVMB200_ROPE_SCALING_LLAMA3 1
+#define TVMB200_ROPE_SCALING_GPTJ 2
+#define TVMB200_ROPE_SCALING_LLAMA4 3
+#define TVMB200_ROPE_SCALING_YARN 5
 TVMB200_API int tvmb200_set_rope_scaling(int32_t kind, float factor, float low_freq_factor, float high_freq_factor,
                                          float original_max_position_embeddings);
+TVMB200_API int tvmb200_set_rope_scaling_yarn(float factor, float original_max_position_embeddings, float beta_fast,
+                                              float beta_slow, float inv_theta_log_scale);
+/*! \brief The kind set by the two functions above. */
+TVMB200_API int32_t tvmb200_get_rope_scaling_kind(void);
 
 /*!
  * \brief Prefill implementation selector (test / profiling hook): 0 = auto (tcgen05 path for eligible shapes

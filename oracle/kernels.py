@@ -65,52 +65,100 @@ def from_bits16(b: np.ndarray, dtype: str) -> np.ndarray:
 # RoPE  (position_embedding.py:31-67 rope_freq_default, :500-521 _rope; _kernel_common.py:115-127)
 # ------------------------------------------------------------------------------------------------
 # Frequency scaling the reference bakes into its PrimFuncs at build time (`rope_scaling` dict -> switch_rope_freq_func,
-# position_embedding.py:257-299).  None = rope_freq_default; {"rope_type": "llama3", factor, low_freq_factor,
-# high_freq_factor, original_max_position_embeddings} = rope_freq_llama3 (position_embedding.py:130-160).  Module state,
-# like the kernels' tvmb200_set_rope_scaling: set_rope_scaling(None) restores the default.
+# position_embedding.py:257-299).  None = rope_freq_default; {"rope_type": ...} selects rope_freq_gptj (:70-76),
+# rope_freq_llama4 (:79-127), rope_freq_llama3 (:130-160) or rope_freq_yarn (:223-254) with the dict's parameters
+# (longrope is not restated: the reference's own longrope PrimFunc does not build at this commit, so nothing could pin it).  Module state, like the kernels' tvmb200_set_rope_scaling: set_rope_scaling(None) restores the
+# default.
 _ROPE_SCALING = None
+_ROPE_TYPES = ("llama3", "gptj", "llama4", "yarn")
 
 
 def set_rope_scaling(rs):
     global _ROPE_SCALING
-    if rs is not None and rs.get("rope_type") != "llama3":
-        raise ValueError(f"oracle: rope_type {rs.get('rope_type')!r} is not restated (default and llama3 are)")
+    if rs is not None and rs.get("rope_type") not in _ROPE_TYPES:
+        raise ValueError(f"oracle: rope_type {rs.get('rope_type')!r} is not restated ({', '.join(_ROPE_TYPES)} are)")
     _ROPE_SCALING = dict(rs) if rs is not None else None
 
 
+def rope_cos_sin(s: np.ndarray, rd: int, theta: float):
+    """cos, sin [n, rd] (float32) of the rotation angle of element d at scaled position s[n], as the reference's
+    rope_freq_* functions compute them (float32 arithmetic, float64 only inside cos / sin)."""
+    f32 = np.float32
+    rs = _ROPE_SCALING
+    kind = rs.get("rope_type") if rs else None
+    d = np.arange(rd)
+    s = np.asarray(s, dtype=np.float32)
+    if kind in ("gptj", "llama4"):
+        e = 2 * (d // 2)
+        if kind == "gptj":
+            e = e % rd                                        # :72; llama4 has no modulo (:92)
+        expo = e.astype(np.float32) / f32(rd)
+    else:
+        expo = ((d * 2) % rd).astype(np.float32) / f32(rd)
+    denom = np.power(f32(theta), expo).astype(np.float32)     # [rd]
+    if kind in (None, "gptj"):
+        freq = (s[:, None] / denom[None, :]).astype(np.float32)
+    elif kind in ("llama3", "llama4"):
+        orig = (f32(1) / denom).astype(np.float32)
+        if kind == "llama4" and rs["high_freq_factor"] == rs["low_freq_factor"]:
+            wavelength = (f32(2 * np.pi) / orig).astype(np.float32)
+            thr = f32(rs["original_max_position_embeddings"] / rs["low_freq_factor"])
+            inv = np.where(wavelength > thr, (orig / f32(rs["factor"])).astype(np.float32), orig).astype(np.float32)
+        else:
+            # orig = 1/theta^e; smooth = clip(alpha*orig - beta, 0, 1); inv = (1 - smooth)*orig/factor + smooth*orig
+            inv_diff = 1.0 / (rs["high_freq_factor"] - rs["low_freq_factor"])
+            alpha = f32(rs["original_max_position_embeddings"] / (2 * np.pi) * inv_diff)
+            beta = f32(rs["low_freq_factor"] * inv_diff)
+            smooth = np.maximum(f32(0), np.minimum(f32(1), alpha * orig - beta)).astype(np.float32)
+            inv = ((f32(1) - smooth) * orig * f32(1.0 / rs["factor"]) + smooth * orig).astype(np.float32)
+        freq = (s[:, None] * inv[None, :]).astype(np.float32)
+    elif kind == "yarn":
+        # the correction range is in units of the element index d in [0, rd) and the ramp is NOT folded onto rd/2: the
+        # two halves of a rotated pair get different angles, exactly as the reference computes them (:244-249)
+        itls = rs.get("inv_theta_log_scale")
+        if itls is None:
+            itls = 1.0 / (2 * np.log(theta))                  # kv_cache.py:355-366
+        orig_max = rs["original_max_position_embeddings"]
+        low = max(rd * np.log(orig_max / (rs["beta_fast"] * 2 * np.pi)) * itls, 0)
+        high = min(rd * np.log(orig_max / (rs["beta_slow"] * 2 * np.pi)) * itls, rd - 1)
+        if low == high:
+            high = high + 0.001
+        freq_extra = (f32(1) / denom).astype(np.float32)
+        freq_inter = (f32(1) / (f32(rs["factor"]) * denom)).astype(np.float32)
+        ramp = ((d.astype(np.float32) - f32(low)) / f32(high - low)).astype(np.float32)
+        mask = (f32(1) - np.maximum(np.minimum(ramp, f32(1)), f32(0))).astype(np.float32)
+        inv = (freq_inter * (f32(1) - mask) + freq_extra * mask).astype(np.float32)
+        freq = (s[:, None] * inv[None, :]).astype(np.float32)
+    else:
+        raise ValueError(kind)
+    cos = np.cos(freq.astype(np.float64)).astype(np.float32)
+    sin = np.sin(freq.astype(np.float64)).astype(np.float32)
+    return cos, sin
+
+
 def rope_rotate(x: np.ndarray, pos: np.ndarray, theta: float, scale: float, dtype: str,
-                rotary_dim: int | None = None) -> np.ndarray:
+                rotary_dim: int | None = None, interleaved: bool = False) -> np.ndarray:
     """x: [n, H, D] (values in dtype), pos: [n] int.  Returns rotated x rounded to dtype.
 
-    freq = (pos*scale) / theta^((2d mod rd)/rd);  out[d] = cos*x[d] + sin*(d<rd/2 ? -x[d+rd/2] : x[d-rd/2]).
-    cos/sin/products in float32 like the reference; the result is cast to dtype once.
+    out[d] = cos[d]*x[d] + sin[d]*partner(d); partner = (d<rd/2 ? -x[d+rd/2] : x[d-rd/2]), or, interleaved (the gptj
+    layout of f_split_rotary, position_embedding.py:509-514), (d even ? -x[d+1] : x[d-1]).  The inline-RoPE helper of the
+    attention kernels (_kernel_common.py:115-127) always pairs by halves.  cos/sin/products in float32 like the
+    reference; the result is cast to dtype once.
     """
     x = np.asarray(x, dtype=np.float32)
     n, H, D = x.shape
     rd = D if rotary_dim is None else rotary_dim
-    d = np.arange(rd)
-    expo = ((d * 2) % rd).astype(np.float32) / np.float32(rd)
-    denom = np.power(np.float32(theta), expo).astype(np.float32)  # [rd]
     s = np.asarray(pos, dtype=np.float32) * np.float32(scale)  # [n]
-    if _ROPE_SCALING is None:
-        freq = (s[:, None] / denom[None, :]).astype(np.float32)  # [n, rd]
-    else:
-        # rope_freq_llama3: orig = 1/theta^e; smooth = clip(alpha*orig - beta, 0, 1);
-        # freq = s * ((1 - smooth) * orig / factor + smooth * orig), all in float32
-        rs = _ROPE_SCALING
-        f32 = np.float32
-        inv_diff = 1.0 / (rs["high_freq_factor"] - rs["low_freq_factor"])
-        alpha = f32(rs["original_max_position_embeddings"] / (2 * np.pi) * inv_diff)
-        beta = f32(rs["low_freq_factor"] * inv_diff)
-        orig = (f32(1) / denom).astype(np.float32)
-        smooth = np.maximum(f32(0), np.minimum(f32(1), alpha * orig - beta)).astype(np.float32)
-        inv = ((f32(1) - smooth) * orig * f32(1.0 / rs["factor"]) + smooth * orig).astype(np.float32)
-        freq = (s[:, None] * inv[None, :]).astype(np.float32)
-    cos = np.cos(freq.astype(np.float64)).astype(np.float32)[:, None, :]
-    sin = np.sin(freq.astype(np.float64)).astype(np.float32)[:, None, :]
+    cos, sin = rope_cos_sin(s, rd, theta)
+    cos, sin = cos[:, None, :], sin[:, None, :]
     xr = x[..., :rd]
     half = rd // 2
-    rot = np.concatenate([-xr[..., half:], xr[..., :half]], axis=-1)
+    if interleaved:
+        rot = np.empty_like(xr)
+        rot[..., 0::2] = -xr[..., 1::2]
+        rot[..., 1::2] = xr[..., 0::2]
+    else:
+        rot = np.concatenate([-xr[..., half:], xr[..., :half]], axis=-1)
     out = x.copy()
     out[..., :rd] = round_dtype(cos * xr + sin * rot, dtype)
     return out
@@ -119,13 +167,15 @@ def rope_rotate(x: np.ndarray, pos: np.ndarray, theta: float, scale: float, dtyp
 def split_rotary(qkv: np.ndarray, position_map: np.ndarray, num_q_heads: int, num_kv_heads: int,
                  apply_rope: int, theta: float, scale: float, dtype: str,
                  rotary_dim: int | None = None):
-    """f_split_rotary = llama_rope_with_position_map (position_embedding.py:444-565)."""
+    """f_split_rotary = llama_rope_with_position_map (position_embedding.py:444-565); the gptj scaling pairs
+    interleaved elements (:509-514), every other one pairs the two halves."""
     q = qkv[:, :num_q_heads].copy()
     k = qkv[:, num_q_heads:num_q_heads + num_kv_heads].copy()
     v = qkv[:, num_q_heads + num_kv_heads:].copy()
+    gptj = bool(_ROPE_SCALING) and _ROPE_SCALING.get("rope_type") == "gptj"
     if apply_rope > 0:
-        q = rope_rotate(q, position_map, theta, scale, dtype, rotary_dim)
-        k = rope_rotate(k, position_map, theta, scale, dtype, rotary_dim)
+        q = rope_rotate(q, position_map, theta, scale, dtype, rotary_dim, interleaved=gptj)
+        k = rope_rotate(k, position_map, theta, scale, dtype, rotary_dim, interleaved=gptj)
     return q, k, v
 
 

@@ -429,7 +429,7 @@ def test_rope_llama3_inline_paths_vs_oracle(llama3_rope, dtype):
 
 def test_rope_scaling_rejects_unknown_kinds(capi):
     with pytest.raises(Exception, match="not implemented"):
-        capi.set_rope_scaling({"rope_type": "yarn"})
+        capi.set_rope_scaling({"rope_type": "longrope"})
     L = capi.lib()
     assert L.tvmb200_set_rope_scaling(7, 1.0, 1.0, 4.0, 8192.0) != 0
     assert b"unsupported" in L.tvmb200_last_error()

@@ -208,3 +208,36 @@ def test_oracle_llama3_rope_scaling_matches_the_reference():
         assert np.abs(q0 - g["q"].astype(np.float32)).max() > 0.1
     finally:
         ok.set_rope_scaling(None)
+
+
+def _rope_variants():
+    import json
+    from pathlib import Path
+
+    g = np.load(Path(__file__).parent / "golden" / "rope_variants.npz")
+    return g, json.loads(bytes(g["meta"]).decode())
+
+
+@pytest.mark.parametrize("name", ["gptj", "gptj_rd64", "llama4", "llama4_equal_factors", "yarn"])
+def test_oracle_rope_variants_match_the_reference(name):
+    """tests/golden/rope_variants.npz: the reference's own fused_rope built with rope_scaling = gptj / llama4 / yarn
+    (oracle/ref_harness/gen_golden_rope_variants.py).  Same position-dependent slack as the llama3 fixture."""
+    g, meta = _rope_variants()
+    m = meta[name]
+    want_q, want_k = g[f"{name}_q"].astype(np.float32), g[f"{name}_k"].astype(np.float32)
+    ok.set_rope_scaling(m["rope_scaling"])
+    try:
+        q, k, v = ok.split_rotary(g[f"{name}_qkv"].astype(np.float32), g[f"{name}_pos"], 8, 2, 1, m["theta"], m["scale"],
+                                  "float16", m["rotary_dim"])
+    finally:
+        ok.set_rope_scaling(None)
+    assert np.array_equal(v, g[f"{name}_v"].astype(np.float32))
+    for i, pos in enumerate(g[f"{name}_pos"]):
+        atol = 4e-3 + 3e-7 * float(pos)
+        assert_close(f"{name} q[{i}]", q[i], want_q[i], atol=atol)
+        assert_close(f"{name} k[{i}]", k[i], want_k[i], atol=atol)
+    assert np.array_equal(q[0], want_q[0]) and np.array_equal(q[1], want_q[1])  # small angles: bit exact
+    # the default frequencies / pairing must NOT reproduce the fixture
+    q0, _, _ = ok.split_rotary(g[f"{name}_qkv"].astype(np.float32), g[f"{name}_pos"], 8, 2, 1, m["theta"], m["scale"],
+                               "float16", m["rotary_dim"])
+    assert np.abs(q0 - want_q).max() > 0.1

@@ -158,19 +158,43 @@ def split_rotary_append(qkv, q_rope_position, append_position, q, k, v, pages, a
                                              apply_rope, rope_scale, rope_theta, _dt(qkv), _stream(qkv)))
 
 
+ROPE_SCALING_KINDS = {"llama3": 1, "gptj": 2, "llama4": 3, "yarn": 5}
+
+
 def set_rope_scaling(rope_scaling=None):
-    """rope_scaling: None / {} (default frequencies) or the reference's dict {"rope_type": "llama3", "factor", "low_freq_factor",
-    "high_freq_factor", "original_max_position_embeddings"}.  Process-wide, like the reference's build-time choice."""
+    """rope_scaling: None / {} (default frequencies) or the reference's dict (switch_rope_freq_func,
+    position_embedding.py:257-299): {"rope_type": "llama3" | "llama4", "factor", "low_freq_factor", "high_freq_factor",
+    "original_max_position_embeddings"}, {"rope_type": "gptj"}, or {"rope_type": "yarn", "factor",
+    "original_max_position_embeddings", "beta_fast", "beta_slow"[, "inv_theta_log_scale"]}.  Process-wide, like the
+    reference's build-time choice.  gptj / llama4 / yarn only exist in split_rotary (see include/tvm_b200.h)."""
     L = lib()
-    L.tvmb200_set_rope_scaling.argtypes = [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
-    if not rope_scaling:
+    F = ctypes.c_float
+    L.tvmb200_set_rope_scaling.argtypes = [ctypes.c_int32, F, F, F, F]
+    L.tvmb200_set_rope_scaling_yarn.argtypes = [F, F, F, F, F]
+    if not rope_scaling or "rope_type" not in rope_scaling:
         _check(L.tvmb200_set_rope_scaling(0, 1.0, 0.0, 1.0, 1.0))
         return
-    if rope_scaling.get("rope_type") != "llama3":
-        raise TvmB200Error(f"rope_type {rope_scaling.get('rope_type')!r} is not implemented (default and llama3 are)")
-    _check(L.tvmb200_set_rope_scaling(1, float(rope_scaling["factor"]), float(rope_scaling["low_freq_factor"]),
-                                      float(rope_scaling["high_freq_factor"]),
-                                      float(rope_scaling["original_max_position_embeddings"])))
+    kind = ROPE_SCALING_KINDS.get(rope_scaling["rope_type"])
+    if kind is None:
+        raise TvmB200Error(f"rope_type {rope_scaling.get('rope_type')!r} is not implemented "
+                           f"(default, {', '.join(ROPE_SCALING_KINDS)} are)")
+    if kind == 2:
+        _check(L.tvmb200_set_rope_scaling(2, 1.0, 0.0, 1.0, 1.0))
+    elif kind == 5:
+        _check(L.tvmb200_set_rope_scaling_yarn(float(rope_scaling["factor"]),
+                                               float(rope_scaling["original_max_position_embeddings"]),
+                                               float(rope_scaling["beta_fast"]), float(rope_scaling["beta_slow"]),
+                                               float(rope_scaling.get("inv_theta_log_scale") or 0.0)))
+    else:
+        _check(L.tvmb200_set_rope_scaling(kind, float(rope_scaling["factor"]), float(rope_scaling["low_freq_factor"]),
+                                          float(rope_scaling["high_freq_factor"]),
+                                          float(rope_scaling["original_max_position_embeddings"])))
+
+
+def get_rope_scaling_kind() -> int:
+    L = lib()
+    L.tvmb200_get_rope_scaling_kind.restype = ctypes.c_int32
+    return int(L.tvmb200_get_rope_scaling_kind())
 
 
 def merge_state_inplace(v, s, v_other, s_other):

@@ -263,6 +263,63 @@ __device__ __forceinline__ float rope_denominator(int d, int rotary_dim, float t
   return 1.0f / ((1.0f - smooth) * orig * rs.inv_factor + smooth * orig);
 }
 
+// Element-wise RoPE variants of f_split_rotary that do not fit the "one angle per rotated pair" form above: kind 2 =
+// rope_freq_gptj (interleaved pairs, position_embedding.py:70-76, :509-514), 3 = rope_freq_llama4 (:79-127), 5 =
+// rope_freq_yarn (:223-254; the ramp runs over the element index, so the two halves of a pair get different angles).
+// Only tvmb200_split_rotary[_append] implements them (split_rotary_variant_kernel); kind 0 = none active.  While one is
+// active every in-kernel rotation (rotary_mode = 1 of the attention entries, the fused decode step) is rejected.
+struct RopeVariant {
+  int kind;
+  float p0, p1, p2, p3;
+  // gptj:   -
+  // llama4: p0 = 1/factor (smooth) or factor (equal factors), p1 = alpha or the wavelength threshold, p2 = beta,
+  //         p3 != 0: high_freq_factor == low_freq_factor (threshold branch)
+  // yarn (set): p0 = factor, p1 = original_max_position_embeddings, p2 = beta_fast, p3 = beta_slow; at launch p1 / p2
+  //         become (low, high - low) of the correction range for the launch's rotary_dim and theta
+  float inv_theta_log_scale;  // yarn; 0 = 1 / (2 ln theta) taken at launch (kv_cache.py:355-366)
+};
+RopeVariant rope_variant();  // current process-wide setting (core.cu)
+int check_no_rope_variant(const char* who);  // error (non-zero) when a variant is active (core.cu)
+
+// host: the stored form of kind 2 / 3 from the numbers of the reference's rope_scaling dict (llama3-style arguments)
+inline RopeVariant make_rope_variant(int kind, float factor, float low_freq_factor, float high_freq_factor,
+                                     float original_max_position_embeddings) {
+  RopeVariant rv = {kind, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (kind != 3) return rv;
+  if (high_freq_factor == low_freq_factor) {  // threshold branch (position_embedding.py:99-109)
+    rv.p0 = factor;
+    rv.p1 = original_max_position_embeddings / low_freq_factor;
+    rv.p3 = 1.f;
+    return rv;
+  }
+  const double inv_diff = 1.0 / (static_cast<double>(high_freq_factor) - static_cast<double>(low_freq_factor));
+  rv.p0 = static_cast<float>(1.0 / factor);
+  rv.p1 = static_cast<float>(original_max_position_embeddings / (2.0 * 3.14159265358979323846) * inv_diff);
+  rv.p2 = static_cast<float>(low_freq_factor * inv_diff);
+  return rv;
+}
+
+// the rotation angle of element d in [0, rotary_dim) at scaled position s, float32 like the reference
+__device__ __forceinline__ float rope_variant_angle(float s, int d, int rd, float theta, const RopeVariant& v) {
+  if (v.kind == 2) {
+    return s / powf(theta, static_cast<float>((2 * (d / 2)) % rd) / static_cast<float>(rd));
+  } else if (v.kind == 3) {
+    const float orig = 1.0f / powf(theta, static_cast<float>(2 * (d / 2)) / static_cast<float>(rd));
+    if (v.p3 != 0.0f) {
+      const float wavelength = 6.283185307179586f / orig;
+      return s * (wavelength > v.p1 ? orig / v.p0 : orig);
+    }
+    const float smooth = fmaxf(0.0f, fminf(1.0f, v.p1 * orig - v.p2));
+    return s * ((1.0f - smooth) * orig * v.p0 + smooth * orig);
+  } else {
+    const float den = powf(theta, static_cast<float>((d * 2) % rd) / static_cast<float>(rd));
+    const float extra = 1.0f / den, inter = 1.0f / (v.p0 * den);
+    const float ramp = (static_cast<float>(d) - v.p1) / v.p2;
+    const float mask = 1.0f - fmaxf(fminf(ramp, 1.0f), 0.0f);
+    return s * (inter * (1.0f - mask) + extra * mask);
+  }
+}
+
 // cos * x + sin * partner with ONE fixed rounding sequence (product, then fused multiply-add), so that every kernel
 // that rotates -- split_rotary, the inline-RoPE loads, the fused decode step -- produces the same bits
 __device__ __forceinline__ float rope_mix(float c, float x, float s, float partner) {

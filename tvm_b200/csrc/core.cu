@@ -78,6 +78,18 @@ RopeScaling rope_scaling() {
   return g_rope_scaling;
 }
 
+static RopeVariant g_rope_variant = {0, 0.f, 0.f, 0.f, 0.f, 0.f};
+RopeVariant rope_variant() {
+  std::lock_guard<std::mutex> lk(g_rope_mu);
+  return g_rope_variant;
+}
+int check_no_rope_variant(const char* who) {
+  const int kind = rope_variant().kind;
+  if (kind == 0) return 0;
+  return set_error("%s: rope scaling kind %d (gptj / llama4 / yarn) is only implemented by split_rotary (rope mode "
+                   "\"normal\"); rotations inside the attention kernels need the default or llama3 frequencies", who, kind);
+}
+
 }  // namespace tvmb200
 
 extern "C" const char* tvmb200_last_error(void) { return tvmb200::last_error_ref().c_str(); }
@@ -88,21 +100,45 @@ extern "C" void tvmb200_set_layer_sliding_window_size(int32_t size) {
 }
 extern "C" int tvmb200_set_rope_scaling(int32_t kind, float factor, float low_freq_factor, float high_freq_factor,
                                         float original_max_position_embeddings) {
-  TVMB200_CHECK(kind == TVMB200_ROPE_SCALING_NONE || kind == TVMB200_ROPE_SCALING_LLAMA3,
-                "set_rope_scaling: kind %d unsupported (0 = none, 1 = llama3; gptj / llama4 / longrope / yarn are not implemented)", kind);
+  TVMB200_CHECK(kind == TVMB200_ROPE_SCALING_NONE || kind == TVMB200_ROPE_SCALING_LLAMA3 || kind == TVMB200_ROPE_SCALING_GPTJ ||
+                    kind == TVMB200_ROPE_SCALING_LLAMA4,
+                "set_rope_scaling: kind %d unsupported (0 = none, 1 = llama3, 2 = gptj, 3 = llama4; yarn has its own setter, "
+                "longrope is not implemented)", kind);
   tvmb200::RopeScaling rs = {0, 1.0f, 0.0f, 0.0f};
-  if (kind == TVMB200_ROPE_SCALING_LLAMA3) {
-    TVMB200_CHECK(factor > 0.f && high_freq_factor != low_freq_factor && original_max_position_embeddings > 0.f,
-                  "set_rope_scaling: llama3 needs factor > 0, high_freq_factor != low_freq_factor, original_max_position_embeddings > 0");
-    const double inv_diff = 1.0 / (static_cast<double>(high_freq_factor) - static_cast<double>(low_freq_factor));
-    rs.kind = 1;
-    rs.inv_factor = static_cast<float>(1.0 / factor);
-    rs.alpha = static_cast<float>(original_max_position_embeddings / (2.0 * 3.14159265358979323846) * inv_diff);
-    rs.beta = static_cast<float>(low_freq_factor * inv_diff);
+  tvmb200::RopeVariant rv = {0, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (kind == TVMB200_ROPE_SCALING_LLAMA3 || kind == TVMB200_ROPE_SCALING_LLAMA4) {
+    const bool equal = high_freq_factor == low_freq_factor;
+    TVMB200_CHECK(factor > 0.f && original_max_position_embeddings > 0.f && (kind == TVMB200_ROPE_SCALING_LLAMA4 || !equal) &&
+                      (!equal || low_freq_factor != 0.f),
+                  "set_rope_scaling: llama3 / llama4 need factor > 0, original_max_position_embeddings > 0 and (llama3) "
+                  "high_freq_factor != low_freq_factor");
+    // both share the smooth-interpolation constants; llama3 rotates pair-wise (RopeScaling), llama4 element-wise
+    const tvmb200::RopeVariant v = tvmb200::make_rope_variant(3, factor, low_freq_factor, high_freq_factor,
+                                                              original_max_position_embeddings);
+    if (kind == TVMB200_ROPE_SCALING_LLAMA3)
+      rs = {1, v.p0, v.p1, v.p2};
+    else
+      rv = v;
+  } else if (kind == TVMB200_ROPE_SCALING_GPTJ) {
+    rv = tvmb200::make_rope_variant(2, 0.f, 0.f, 0.f, 0.f);
   }
   std::lock_guard<std::mutex> lk(tvmb200::g_rope_mu);
   tvmb200::g_rope_scaling = rs;
+  tvmb200::g_rope_variant = rv;
   return 0;
+}
+extern "C" int tvmb200_set_rope_scaling_yarn(float factor, float original_max_position_embeddings, float beta_fast,
+                                             float beta_slow, float inv_theta_log_scale) {
+  TVMB200_CHECK(factor > 0.f && original_max_position_embeddings > 0.f && beta_fast > 0.f && beta_slow > 0.f,
+                "set_rope_scaling_yarn: factor, original_max_position_embeddings, beta_fast and beta_slow must be positive");
+  std::lock_guard<std::mutex> lk(tvmb200::g_rope_mu);
+  tvmb200::g_rope_scaling = {0, 1.0f, 0.0f, 0.0f};
+  tvmb200::g_rope_variant = {5, factor, original_max_position_embeddings, beta_fast, beta_slow, inv_theta_log_scale};
+  return 0;
+}
+extern "C" int32_t tvmb200_get_rope_scaling_kind(void) {
+  std::lock_guard<std::mutex> lk(tvmb200::g_rope_mu);
+  return tvmb200::g_rope_variant.kind != 0 ? tvmb200::g_rope_variant.kind : tvmb200::g_rope_scaling.kind;
 }
 extern "C" int tvmb200_reserve_workspace(int device_id, int64_t bytes) {
   TVMB200_CHECK(device_id >= 0 && device_id < 64, "device id %d out of range", device_id);

@@ -803,6 +803,8 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   p.rope_theta = rope_theta;
   p.rs = rope_scaling();
   p.scale_log2 = sm_scale * kLog2e;
+  if (rotary_mode == 1 || fused_apply_rope)
+    if (int rc = check_no_rope_variant("attention_decode (in-kernel RoPE)")) return rc;
 
   CUtensorMap tmap;
   const uint64_t rows = static_cast<uint64_t>(num_pages) * 2 * num_kv_heads * page_size;

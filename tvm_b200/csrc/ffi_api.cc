@@ -340,7 +340,7 @@ int impl_set_rope_params(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
 }
 
 // (kind, factor, low_freq_factor, high_freq_factor, original_max_position_embeddings): the rope_scaling dict the
-// reference bakes into its PrimFuncs (position_embedding.py:257-299); kind 0 = default, 1 = llama3
+// reference bakes into its PrimFuncs (position_embedding.py:257-299); kind 0 = default, 1 = llama3, 2 = gptj, 3 = llama4
 int impl_set_rope_scaling(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   static const char* fn = "set_rope_scaling";
   TVMB200_FFI_BEGIN();
@@ -349,6 +349,20 @@ int impl_set_rope_scaling(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
                                static_cast<float>(arg_float(args, 2, fn, "low_freq_factor")),
                                static_cast<float>(arg_float(args, 3, fn, "high_freq_factor")),
                                static_cast<float>(arg_float(args, 4, fn, "original_max_position_embeddings"))) != 0)
+    throw Err{"ValueError", tvmb200_last_error()};
+  TVMB200_FFI_END();
+}
+
+// (factor, original_max_position_embeddings, beta_fast, beta_slow[, inv_theta_log_scale]): rope_scaling = yarn
+int impl_set_rope_scaling_yarn(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "set_rope_scaling_yarn";
+  TVMB200_FFI_BEGIN();
+  if (n != 4 && n != 5) throw Err{"TypeError", "set_rope_scaling_yarn expects (factor, original_max_position_embeddings, beta_fast, beta_slow[, inv_theta_log_scale])"};
+  if (tvmb200_set_rope_scaling_yarn(static_cast<float>(arg_float(args, 0, fn, "factor")),
+                                    static_cast<float>(arg_float(args, 1, fn, "original_max_position_embeddings")),
+                                    static_cast<float>(arg_float(args, 2, fn, "beta_fast")),
+                                    static_cast<float>(arg_float(args, 3, fn, "beta_slow")),
+                                    n == 5 ? static_cast<float>(arg_float(args, 4, fn, "inv_theta_log_scale")) : 0.f) != 0)
     throw Err{"ValueError", tvmb200_last_error()};
   TVMB200_FFI_END();
 }
@@ -1099,5 +1113,6 @@ TVMB200_EXPORT(compact_kv_copy, impl_compact_kv_copy)
 TVMB200_EXPORT(set_rope_params, impl_set_rope_params)
 TVMB200_EXPORT(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)
 TVMB200_EXPORT(set_rope_scaling, impl_set_rope_scaling)
+TVMB200_EXPORT(set_rope_scaling_yarn, impl_set_rope_scaling_yarn)
 TVMB200_EXPORT(launch_count, impl_launch_count)
 TVMB200_EXPORT(register_vm_builtins, impl_register_vm_builtins)

@@ -1167,7 +1167,8 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   const bool fuse_step = !plan && append_before_attn_ && num_depths_ == 1 && use_decode_kernel_[0] &&
                          is_chain_on_depths_[0] && !page_indices_[0].empty() && rope_mode_ != TVMB200_ROPE_INLINE && d == 128 &&
                          attn_kinds_[layer_id] != TVMB200_ATTN_MHA_SLIDING && !support_sw_ &&
-                         static_cast<int64_t>(v_qo_indptr_[0].size - 1) == n;
+                         static_cast<int64_t>(v_qo_indptr_[0].size - 1) == n &&
+                         (apply_rope == 0 || tvmb200_get_rope_scaling_kind() <= TVMB200_ROPE_SCALING_LLAMA3);
   if (append_before_attn_ && fuse_step) {
     trace_append();
   } else if (append_before_attn_) {

@@ -178,6 +178,100 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
   }
 }
 
+// f_split_rotary for the element-wise RoPE variants (gptj / llama4 / yarn, common.cuh RopeVariant): same CTA-per-token
+// layout, but the table holds one (cos, sin) per ELEMENT of the rotary range -- the two halves of a pair may rotate by
+// different angles (llama4, yarn) -- and gptj pairs neighbouring elements (2i, 2i+1) instead of the two halves.
+template <typename T>
+__global__ void __launch_bounds__(256)
+split_rotary_variant_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ position_map,
+                            uint4* __restrict__ q, uint4* __restrict__ k, uint4* __restrict__ v, int num_qo_heads,
+                            int num_kv_heads, int head_dim, int rotary_dim, float rope_scale, float rope_theta,
+                            const RopeVariant rv) {
+  extern __shared__ float2 cs[];  // [rotary_dim] (cos, sin)
+  const int64_t t = blockIdx.x;
+  const int row_vecs = head_dim / 8;
+  const int half_vecs = rotary_dim / 16;
+  const int fused_heads = num_qo_heads + 2 * num_kv_heads;
+  const float pos = static_cast<float>(position_map[t]) * rope_scale;
+  for (int d = threadIdx.x; d < rotary_dim; d += blockDim.x) {
+    float sn, c;
+    sincosf(rope_variant_angle(pos, d, rotary_dim, rope_theta, rv), &sn, &c);
+    cs[d] = make_float2(c, sn);
+  }
+  __syncthreads();
+  const uint4* src = qkv + t * fused_heads * row_vecs;
+  const bool interleaved = rv.kind == 2;
+  for (int w = threadIdx.x; w < fused_heads * row_vecs; w += blockDim.x) {
+    const int h = w / row_vecs;
+    const int j = w - h * row_vecs;
+    uint4* dst;
+    if (h < num_qo_heads) {
+      dst = q + (t * num_qo_heads + h) * row_vecs + j;
+    } else {
+      const int is_v = h >= num_qo_heads + num_kv_heads;
+      const int hh = h - num_qo_heads - is_v * num_kv_heads;
+      dst = (is_v ? v : k) + (t * num_kv_heads + hh) * row_vecs + j;
+    }
+    uint4 x = ldg_nc_v4(src + w);
+    if (h < num_qo_heads + num_kv_heads && j < 2 * half_vecs) {
+      const bool lower = j < half_vecs;
+      const T* xe = reinterpret_cast<const T*>(&x);
+      uint4 p = x;
+      if (!interleaved) p = ldg_nc_v4(src + (lower ? w + half_vecs : w - half_vecs));
+      const T* pe = reinterpret_cast<const T*>(&p);
+      uint4 o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = cs[j * 8 + e];
+        float partner;
+        if (interleaved)  // d even: -x[d + 1], d odd: x[d - 1]; negation done in dtype like the reference
+          partner = DT<T>::to_f((e & 1) ? xe[e - 1] : DT<T>::neg(xe[e + 1]));
+        else
+          partner = DT<T>::to_f(lower ? DT<T>::neg(pe[e]) : pe[e]);
+        oe[e] = DT<T>::from_f(rope_mix(f.x, DT<T>::to_f(xe[e]), f.y, partner));
+      }
+      x = o;
+    }
+    *dst = x;
+  }
+}
+
+// launch-time form of the process-wide variant: the yarn correction range depends on rotary_dim and theta
+static RopeVariant variant_for_launch(RopeVariant rv, int rotary_dim, float rope_theta) {
+  if (rv.kind == 5) {
+    const double itls = rv.inv_theta_log_scale > 0.f ? static_cast<double>(rv.inv_theta_log_scale)
+                                                     : 1.0 / (2.0 * std::log(static_cast<double>(rope_theta)));
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    double low = rotary_dim * std::log(rv.p1 / (rv.p2 * two_pi)) * itls;   // yarn_find_correction_range, :192-220
+    double high = rotary_dim * std::log(rv.p1 / (rv.p3 * two_pi)) * itls;
+    low = std::max(low, 0.0);
+    high = std::min(high, static_cast<double>(rotary_dim - 1));
+    if (low == high) high += 0.001;
+    rv.p1 = static_cast<float>(low);
+    rv.p2 = static_cast<float>(high - low);
+  }
+  return rv;
+}
+
+static int launch_split_rotary_variant(const void* qkv, const int32_t* position_map, void* q, void* k, void* v,
+                                       int64_t ntoken, int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_dim,
+                                       int32_t rotary_dim, float rope_scale, float rope_theta, int dtype, cudaStream_t st) {
+  const RopeVariant rv = variant_for_launch(rope_variant(), rotary_dim, rope_theta);
+  const size_t smem = static_cast<size_t>(rotary_dim) * sizeof(float2);
+  if (dtype == TVMB200_F16) {
+    split_rotary_variant_kernel<__half><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, rope_scale, rope_theta, rv);
+  } else {
+    split_rotary_variant_kernel<__nv_bfloat16><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
+        static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
+        static_cast<uint4*>(v), num_qo_heads, num_kv_heads, head_dim, rotary_dim, rope_scale, rope_theta, rv);
+  }
+  TVMB200_LAUNCH_OK();
+  return 0;
+}
+
 // (V,S) <- merge((V,S),(V',S')).  A block owns whole rows (row = n*H+h): thread = (row, 8-element
 // vector); S[row] is rewritten by the row's vector-0 thread after a block barrier so every thread of
 // the row has read the old value first.
@@ -305,6 +399,9 @@ extern "C" int tvmb200_split_rotary(const void* qkv, const int32_t* position_map
   const size_t smem = static_cast<size_t>(rotary_dim / 2) * sizeof(float2);
   const int apply = apply_rope > 0 ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (apply && rope_variant().kind != 0)
+    return launch_split_rotary_variant(qkv, position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim, rotary_dim,
+                                       rope_scale, rope_theta, dtype, st);
   if (dtype == TVMB200_F16) {
     split_rotary_kernel<__half, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
@@ -335,6 +432,13 @@ extern "C" int tvmb200_split_rotary_append(const void* qkv, const int32_t* q_rop
   const size_t smem = static_cast<size_t>(rotary_dim / 2) * sizeof(float2);
   const int apply = apply_rope > 0 ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (apply && rope_variant().kind != 0) {  // gptj / llama4 / yarn: the variant kernel, then the plain append
+    if (int rc = launch_split_rotary_variant(qkv, q_rope_position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim,
+                                             rotary_dim, rope_scale, rope_theta, dtype, st))
+      return rc;
+    return tvmb200_transpose_append(pages, k, v, append_position_map, ntoken, num_pages, num_kv_heads, page_size, head_dim,
+                                    dtype, stream);
+  }
   if (dtype == TVMB200_F16) {
     split_rotary_kernel<__half, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), q_rope_position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),

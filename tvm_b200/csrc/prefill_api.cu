@@ -4,7 +4,9 @@
 using namespace tvmb200;
 
 static int check_common(const char* name, int dtype, int head_dim, int num_qo_heads, int num_kv_heads,
-                        int batch_size) {
+                        int batch_size, int rotary_mode) {
+  if (rotary_mode == 1)
+    if (int rc = check_no_rope_variant(name)) return rc;
   TVMB200_CHECK(dtype == TVMB200_F16 || dtype == TVMB200_BF16, "%s: unsupported dtype %d", name, dtype);
   TVMB200_CHECK(head_dim == 128 || head_dim == 64, "%s: head_dim %d unsupported (64 or 128)", name, head_dim);
   TVMB200_CHECK(num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0,
@@ -40,7 +42,7 @@ extern "C" int tvmb200_attention_prefill_paged(
     int32_t head_dim, int sliding_window, int32_t layer_sliding_window_size, int causal,
     int rotary_mode, float rope_scale, float rope_theta, float sm_scale, int dtype,
     tvmb200_stream_t stream) {
-  if (int rc = check_common("attention_prefill", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size)) return rc;
+  if (int rc = check_common("attention_prefill", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size, rotary_mode)) return rc;
   TVMB200_CHECK(page_size == 16, "attention_prefill: page_size %d unsupported (16)", page_size);
   TVMB200_CHECK(rotary_mode == 0 || rotary_mode == 1, "attention_prefill: rotary_mode %d", rotary_mode);
   if (batch_size == 0 || total_q_len == 0) return 0;
@@ -72,7 +74,7 @@ extern "C" int tvmb200_attention_prefill_ragged(
     int32_t batch_size, int32_t total_q_len, int32_t total_kv_len, int32_t num_qo_heads,
     int32_t num_kv_heads, int32_t head_dim, int causal, int rotary_mode, float rope_scale,
     float rope_theta, float sm_scale, int dtype, tvmb200_stream_t stream) {
-  if (int rc = check_common("attention_prefill_ragged", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size)) return rc;
+  if (int rc = check_common("attention_prefill_ragged", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size, rotary_mode)) return rc;
   TVMB200_CHECK(rotary_mode == 0 || rotary_mode == 1, "attention_prefill_ragged: rotary_mode %d", rotary_mode);
   if (batch_size == 0 || total_q_len == 0) return 0;
   PrefillParams p;
@@ -94,7 +96,7 @@ extern "C" int tvmb200_attention_prefill_tree_ragged(
     float* lse, int32_t batch_size, int32_t total_q_len, int32_t total_kv_len, int32_t num_qo_heads,
     int32_t num_kv_heads, int32_t head_dim, int rotary_mode, float rope_scale, float rope_theta,
     float sm_scale, int dtype, tvmb200_stream_t stream) {
-  if (int rc = check_common("attention_prefill_with_tree_mask", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size)) return rc;
+  if (int rc = check_common("attention_prefill_with_tree_mask", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size, rotary_mode)) return rc;
   TVMB200_CHECK(rotary_mode == 0 || rotary_mode == 1, "attention_prefill_with_tree_mask: rotary_mode %d", rotary_mode);
   if (batch_size == 0 || total_q_len == 0) return 0;
   PrefillParams p;
@@ -117,7 +119,7 @@ extern "C" int tvmb200_attention_prefill_tree_paged(
     int32_t nnz_pages, int64_t num_pages, int32_t num_qo_heads, int32_t num_kv_heads, int32_t page_size,
     int32_t head_dim, int rotary_mode, float rope_scale, float rope_theta, float sm_scale,
     const int32_t* tree_order_indptr, const int32_t* tree_order, int dtype, tvmb200_stream_t stream) {
-  if (int rc = check_common("attention_prefill_with_tree_mask_paged_kv", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size)) return rc;
+  if (int rc = check_common("attention_prefill_with_tree_mask_paged_kv", dtype, head_dim, num_qo_heads, num_kv_heads, batch_size, rotary_mode)) return rc;
   TVMB200_CHECK(page_size == 16, "attention_prefill_with_tree_mask_paged_kv: page_size %d unsupported (16)", page_size);
   // the reference asserts this too (tree_attn.py:699, 930)
   TVMB200_CHECK(rotary_mode == 0, "Inline rotary mode is not supported in tree attention.");

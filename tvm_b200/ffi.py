@@ -23,7 +23,7 @@ TIR_NAMES = [
     "tree_attn_paged_kv", "merge_state_inplace", "fused_rope", "copy_single_page", "tir_kv_cache_debug_get_kv",
     "compact_kv_copy",
 ]
-STATE = ["set_rope_params", "set_rope_scaling", "set_layer_sliding_window_size", "launch_count", "register_vm_builtins"]
+STATE = ["set_rope_params", "set_rope_scaling", "set_rope_scaling_yarn", "set_layer_sliding_window_size", "launch_count", "register_vm_builtins"]
 
 _mod = None
 
