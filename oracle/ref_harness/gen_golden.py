@@ -296,6 +296,136 @@ def prog_random(seed):
     return p
 
 
+def prog_random_tree(seed):
+    """Randomised speculative-decoding program: prefill / decode steps interleaved with token-tree phases -- 1 to 3 rounds
+    of random trees over a random subset of the sequences (later rounds hang new nodes under any earlier node), then a
+    commit of a random root-to-node path (or of nothing, -1) per sequence."""
+    rng = np.random.default_rng(seed)
+    p = Program()
+    length = {}
+    for sid in range(5):
+        n = int(rng.integers(3, 50))
+        p.forward([(sid, n)])
+        length[sid] = n
+    for _ in range(14):
+        live = sorted(length)
+        k = int(rng.integers(1, len(live) + 1))
+        sel = sorted(int(x) for x in rng.choice(live, size=k, replace=False))
+        if rng.random() < 0.35:
+            batch = [(s_, 1) for s_ in sel] if rng.random() < 0.6 else [(s_, int(rng.integers(1, 9))) for s_ in sel]
+            p.forward(batch)
+            for s_, n in batch:
+                length[s_] += n
+            continue
+        rounds = int(rng.integers(1, 4))
+        trees = {s_: [] for s_ in sel}
+        for r in range(rounds):
+            lens = []
+            for s_ in sel:
+                t = trees[s_]
+                m = int(rng.integers(1, 7))
+                for _j in range(m):
+                    if not t:
+                        t.append(-1)
+                    elif r == 0 and rng.random() < 0.1:
+                        t.append(-1)                               # a second root, as in the reference's own test
+                    else:
+                        t.append(int(rng.integers(0, len(t))))
+                lens.append(m)
+            leaves = None
+            if r == rounds - 1:
+                # CommitAcceptedTokenTreeNodes pops `last append length - (depth + 1)` (paged_kv_cache.cc:1646-1650) and looks
+                # the path up in the LAST round's append_position_map: after several rounds only the first root (or
+                # nothing) is a path it handles; a single-round tree commits any root-to-node path
+                if rounds == 1:
+                    leaves = [int(rng.integers(-1, len(trees[s_]))) for s_ in sel]
+                else:
+                    leaves = [int(rng.integers(-1, 1)) for s_ in sel]
+            p.forward(list(zip(sel, lens)), trees=[trees[s_] for s_ in sel], leaves=leaves)
+            last_lens = lens
+        for s_, leaf, m_last in zip(sel, leaves, last_lens):
+            depth, node = 0, leaf
+            while node != -1:
+                depth += 1
+                node = trees[s_][node]
+            length[s_] += len(trees[s_]) - (m_last - depth)
+        if rng.random() < 0.3:
+            p.op(op="query")
+    p.dump_all({s_: min(n, 48) for s_, n in length.items()})
+    p.op(op="query")
+    return p
+
+
+def prog_random_sliding(seed):
+    """Randomised sliding-window program: sequences with random (window, sink) pairs, prefill chunks and many decode
+    steps (so that every window slides over several pages and pages are recycled), forks inside the sink, removals."""
+    rng = np.random.default_rng(seed)
+    p = Program()
+    length, window, sink = {}, {}, {}
+    next_id = 0
+
+    def new_seq():
+        nonlocal next_id
+        sid = next_id
+        next_id += 1
+        w = int(rng.integers(8, 60))
+        sk = int(rng.integers(0, w))
+        p.op(op="add", seq=sid)
+        p.op(op="enable_sw", seq=sid, window=w, sink=sk)
+        length[sid], window[sid], sink[sid] = 0, w, sk
+        return sid
+
+    for _ in range(4):
+        new_seq()
+    for _ in range(45):
+        live = sorted(length)
+        r = rng.random()
+        if r < 0.12 and len(live) < 8:
+            sid = new_seq()
+            n = int(rng.integers(1, 40))
+            p.forward([(sid, n)])
+            length[sid] += n
+        elif r < 0.20 and len(live) < 8:
+            cands = [s_ for s_ in live if 0 < length[s_] <= sink[s_]]
+            if cands:
+                parent = int(rng.choice(cands))
+                child = next_id
+                next_id += 1
+                pos = int(rng.integers(1, length[parent] + 1)) if rng.random() < 0.5 else -1
+                p.op(op="fork", parent=parent, child=child, pos=pos)
+                base = length[parent] if pos == -1 else pos
+                w = int(rng.integers(base + 2, base + 50))
+                sk = int(rng.integers(base, w))
+                p.op(op="enable_sw", seq=child, window=w, sink=sk)
+                length[child], window[child], sink[child] = base, w, sk
+                p.known.add(child)
+                n = int(rng.integers(1, 20))
+                p.forward([(child, n)])
+                length[child] += n
+        elif r < 0.85:
+            k = int(rng.integers(1, len(live) + 1))
+            sel = [int(x) for x in rng.choice(live, size=k, replace=False)]
+            if rng.random() < 0.75:
+                batch = [(s_, 1) for s_ in sel]
+            else:
+                batch = [(s_, int(rng.integers(1, 30))) for s_ in sel]
+            p.forward(batch)
+            for s_, n in batch:
+                length[s_] += n
+        elif len(live) > 2:
+            s_ = int(rng.choice(live))
+            p.op(op="remove", seq=s_)
+            del length[s_], window[s_], sink[s_]
+        if rng.random() < 0.15:
+            p.op(op="query")
+    for s_ in sorted(length):
+        n = min(length[s_], window[s_])
+        if n > 0:
+            p.op(op="debug_get_kv", seq=s_, start=0, end=n)
+    p.op(op="query")
+    return p
+
+
 def prog_shared_kv():
     """prefill, chunked prefill, decode and a fork, every step followed by a shared-KV query of the same layer."""
     p = Program()
@@ -335,6 +465,10 @@ def prog_self_cross_merge():
 
 SCENARIOS = {
     # name: (program builder, cache kwargs)
+    "random_tree_a": (lambda: prog_random_tree(21), dict(rope_mode=1)),
+    "random_tree_b": (lambda: prog_random_tree(22), dict(rope_mode=0, num_layers=2)),
+    "random_sliding_a": (lambda: prog_random_sliding(31), dict(rope_mode=2, support_sliding_window=True)),
+    "random_sliding_b": (lambda: prog_random_sliding(32), dict(rope_mode=1, support_sliding_window=True)),
     "layer_sliding": (prog_prefill_and_decode, dict(rope_mode=0, num_layers=2, attn_kinds=[3, 0], layer_sliding_window_size=20)),
     "layer_sliding_inline_rope": (prog_prefill_and_decode, dict(rope_mode=2, num_layers=2, attn_kinds=[0, 3],
                                                                 layer_sliding_window_size=35)),
