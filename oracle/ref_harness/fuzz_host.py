@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY -- live differential fuzzing of the host cache against the REFERENCE (no fixtures stored).
+
+    source /tmp/tvm_ref/env.sh && python oracle/ref_harness/fuzz_host.py [--seeds N] [--first S]
+
+For every seed, the three randomised program generators of gen_golden.py (plain: prefill / decode / fork / popn / remove;
+tree: 1-3 rounds of random token trees + commits; sliding: random windows + sinks, forks inside the sink) are run on the
+reference's own C++ PagedAttentionKVCacheObj (CPU TIR kernels) and, in the same process, on a planning-only tvm_b200 host
+cache (ctypes, no GPU): the callback sequence with every int32 array and scalar, the page counts and the query results
+must be identical.  With --oracle the captured callback traces are also re-executed by the NumPy oracle and compared with
+the reference's attention outputs.  Prints one line per program and a summary; exits non-zero on the first difference."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import gen_golden as gg  # noqa: E402
+
+KINDS = {
+    # name: (builder(seed), cache kwargs by seed parity)
+    "plain": (gg.prog_random, [dict(rope_mode=1), dict(rope_mode=0), dict(rope_mode=2)]),
+    "tree": (gg.prog_random_tree, [dict(rope_mode=1), dict(rope_mode=0)]),
+    "sliding": (gg.prog_random_sliding, [dict(rope_mode=2, support_sliding_window=True),
+                                         dict(rope_mode=1, support_sliding_window=True)]),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=20)
+    ap.add_argument("--first", type=int, default=1000)
+    ap.add_argument("--oracle", action="store_true", help="also re-execute the traces with the NumPy oracle")
+    a = ap.parse_args()
+    from tests.golden_replay import replay_meta
+
+    kernels = None  # the reference's CPU kernels do not depend on the rope mode / window flags that vary here
+    n_prog = n_ops = n_calls = 0
+    t0 = time.time()
+    for seed in range(a.first, a.first + a.seeds):
+        for kind, (builder, kws) in KINDS.items():
+            cfg = dict(gg.BASE)
+            cfg.update(kws[seed % len(kws)])
+            prog = builder(seed)
+            name = f"fuzz_{kind}_{seed}"
+            meta, arrays = gg.capture(name, prog, cfg, kernels=kernels)
+            kernels = gg.capture.last_kernels
+            replay_meta(name, meta, arrays, device=None)  # raises on the first differing array / scalar / count
+            if a.oracle:
+                check_oracle(name, meta, arrays)
+            calls = sum(len(r["trace"]) for r in meta["results"])
+            n_prog, n_ops, n_calls = n_prog + 1, n_ops + len(meta["ops"]), n_calls + calls
+            print(f"{name}: {len(meta['ops'])} ops, {calls} callbacks identical", flush=True)
+    print(f"OK: {n_prog} programs, {n_ops} cache operations, {n_calls} callbacks with every int32 array bit-identical "
+          f"({time.time() - t0:.0f} s)")
+
+
+def check_oracle(name, meta, z):
+    import numpy as np
+
+    from tests.golden_replay import qkv_for
+    from tests.test_oracle_golden import OracleMachine, _close
+
+    cfg = meta["config"]
+    m = OracleMachine(cfg)
+    L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
+    for idx, (op, res) in enumerate(zip(meta["ops"], meta["results"])):
+        if op["op"] == "clear":
+            m = OracleMachine(cfg)
+        elif op["op"] == "forward":
+            qkv = qkv_for(op["seed"], L, sum(op["lens"]), hq, hkv, d, cfg["dtype"])
+            outs, _ = m.run_forward(res["trace"], qkv, None)
+            for layer in range(L):
+                _close(f"{name} op {idx} layer {layer} O", outs[layer], z[f"o_{idx}"][layer].astype(np.float32))
+        else:
+            m.run_other(res["trace"])
+
+
+if __name__ == "__main__":
+    main()

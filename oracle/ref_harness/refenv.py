@@ -83,7 +83,7 @@ class RefCache:
 
     def __init__(self, num_layers=1, num_qo_heads=8, num_kv_heads=2, head_dim=128, dtype="float16", rope_mode=1,
                  support_sliding_window=False, reserved_nseq=32, max_total_seq=2048, prefill_chunk=512, page_size=16,
-                 rope_scale=1.0, rope_theta=1e4, layer_sliding_window_size=None, attn_kinds=None):
+                 rope_scale=1.0, rope_theta=1e4, layer_sliding_window_size=None, attn_kinds=None, kernels=None):
         self.cfg = dict(num_layers=num_layers, num_qo_heads=num_qo_heads, num_kv_heads=num_kv_heads,
                         head_dim=head_dim, dtype=dtype, rope_mode=int(rope_mode),
                         support_sliding_window=int(support_sliding_window), reserved_nseq=reserved_nseq,
@@ -92,13 +92,16 @@ class RefCache:
         self.dev = tvm.cpu()
         self.trace = []
         self._keep = []
-        pfs = kernel_primfuncs(num_layers, num_qo_heads, num_kv_heads, head_dim, dtype, rope_theta, rope_scale,
+        pfs = None if kernels is not None else kernel_primfuncs(num_layers, num_qo_heads, num_kv_heads, head_dim, dtype, rope_theta, rope_scale,
                                page_size, layer_sliding_window_size or 1024)
-        fns = {}
-        for name, pf in zip(CALLBACK_ORDER, pfs):
-            fn, _, _, mod = build_c(pf)
-            self._keep.append(mod)
-            fns[name] = self._wrap(name, fn)
+        # kernels: the compiled callbacks (raw_fns) of an earlier RefCache with the same shape configuration
+        if kernels is None:
+            kernels = {}
+            for name, pf in zip(CALLBACK_ORDER, pfs):
+                fn, _, _, mod = build_c(pf)
+                kernels[name] = (fn, mod)
+        self.raw_fns = kernels
+        fns = {name: self._wrap(name, fn) for name, (fn, _mod) in kernels.items()}
         self.fns = fns
         g = tvm.get_global_func
         self.f = {n: g("vm.builtin." + n) for n in [

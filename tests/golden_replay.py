@@ -78,6 +78,11 @@ def replay(name, device, on_forward=None, on_kv=None, on_shared=None, on_split=N
     on_shared(idx, outs, golden_os), on_split(idx, dict of device results, npz) and on_kv(idx, k, v, golden_k, golden_v)
     with device results when a device is used."""
     meta, z = load(name)
+    return replay_meta(name, meta, z, device, on_forward, on_kv, on_shared, on_split)
+
+
+def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=None, on_split=None):
+    """replay() on an already loaded (or freshly captured, oracle/ref_harness/fuzz_host.py) program."""
     cfg = meta["config"]
     cache = make_cache(cfg, device)
     cache.set_trace(True)
