@@ -235,13 +235,18 @@ def prog_tree_attn():
     return p
 
 
-def prog_random(seed):
+def prog_random(seed, shared=False, split=False):
     """Randomised differential scenario: a few hundred cache operations drawn at random -- prefill chunks, decode
     steps over random subsets, forks at random positions (also of forked sequences), popn (kept inside a sequence's own
     last block, as the reference requires), removals -- so that the host cache's page allocation, block tree, copy-on-
-    fork and aux-array construction are compared with the reference far off the hand-written paths."""
+    fork and aux-array construction are compared with the reference far off the hand-written paths.
+    shared: every forward also issues attention_with_shared_kv per layer; split: self_attention / cross_attention /
+    merge_attn_output_inplace steps (rolled back by popn) are mixed in."""
     rng = np.random.default_rng(seed)
     p = Program()
+    if shared:
+        fwd = p.forward
+        p.forward = lambda batch, **kw: fwd(batch, shared=True, **kw)
     length, tail = {}, {}     # seq -> total length, tokens appended since its last fork point / creation
     next_id = 0
     total = 0
@@ -289,6 +294,11 @@ def prog_random(seed):
             s_ = int(rng.choice(leaves))
             p.op(op="remove", seq=s_)
             del length[s_], tail[s_]
+        if split and length and rng.random() < 0.2 and total < cap - 200:
+            live = sorted(length)
+            k = int(rng.integers(1, min(len(live), 4) + 1))
+            sel = [int(x) for x in rng.choice(live, size=k, replace=False)]
+            p.forward_split([(s_, int(rng.integers(2, 30))) for s_ in sel])
         if rng.random() < 0.15:
             p.op(op="query")
     p.dump_all({s_: min(n, 40) for s_, n in length.items()})
@@ -362,6 +372,7 @@ def prog_random_sliding(seed):
     rng = np.random.default_rng(seed)
     p = Program()
     length, window, sink = {}, {}, {}
+    forked = set()
     next_id = 0
 
     def new_seq():
@@ -386,7 +397,11 @@ def prog_random_sliding(seed):
             p.forward([(sid, n)])
             length[sid] += n
         elif r < 0.20 and len(live) < 8:
-            cands = [s_ for s_ in live if 0 < length[s_] <= sink[s_]]
+            # a sliding-window sequence may sit on at most two blocks: beyond that the reference merges the trailing blocks
+            # into its last depth but keeps the LAST block's sink size / window offset for the merged page list
+            # (paged_kv_cache.cc:884-1100), so its own plan reads slots nobody wrote.  Hence: fork a sequence once, and
+            # never fork a child.
+            cands = [s_ for s_ in live if 0 < length[s_] <= sink[s_] and s_ not in forked]
             if cands:
                 parent = int(rng.choice(cands))
                 child = next_id
@@ -398,6 +413,7 @@ def prog_random_sliding(seed):
                     # ICHECK(block.seq_length >= block.sink_length) when that parent slides -- not a program it supports
                     pos = length[parent] - 1
                 p.op(op="fork", parent=parent, child=child, pos=pos)
+                forked.update((parent, child))
                 base = length[parent] if pos == -1 else pos
                 w = int(rng.integers(base + 2, base + 50))
                 sk = int(rng.integers(base, w))
@@ -527,8 +543,10 @@ def capture(name, prog, cfg, kernels=None):
 
     if cfg["attn_kinds"] is not None and any(k != 0 for k in cfg["attn_kinds"]):
         # DebugGetKV only takes all-MHA caches (paged_kv_cache.cc:1715-1717): the dump is replaced by the error check
+        dumped = [o["seq"] for o in prog.ops if o["op"] == "debug_get_kv"]   # sequences alive at the end of the program
         prog.ops = [o for o in prog.ops if o["op"] != "debug_get_kv"]
-        prog.ops.append({"op": "debug_get_kv_rejected", "seq": 0})
+        if dumped:
+            prog.ops.append({"op": "debug_get_kv_rejected", "seq": dumped[0]})
     rc = RefCache(**cfg, kernels=kernels)
     L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
     arrays = {}

@@ -29,7 +29,9 @@ class OracleMachine:
         self.dt = cfg["dtype"]
         L, hkv, d, ps = cfg["num_layers"], cfg["num_kv_heads"], cfg["head_dim"], cfg["page_size"]
         npages = (cfg["max_total_seq"] + ps - 1) // ps + 1 + (2 * cfg["reserved_nseq"] if cfg.get("support_sliding_window") else 0)
-        self.pages = [np.zeros((npages, 2, hkv, ps, d), np.float32) for _ in range(L)]
+        # NaN, not zero: a plan that reads a slot nobody appended to (as the reference's own plans do for sliding-window
+        # sequences spread over more than two blocks) must show up instead of comparing equal by luck
+        self.pages = [np.full((npages, 2, hkv, ps, d), np.nan, np.float32) for _ in range(L)]
         self.theta, self.scale = cfg["rope_theta"], cfg["rope_scale"]
 
     def attend(self, calls, layer, q, k, v):
