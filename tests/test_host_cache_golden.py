@@ -33,3 +33,110 @@ def test_error_behaviour(built_lib):
                           num_qo_heads=4, num_kv_heads=1, head_dim=128, device=None)
         c2.add_sequence(0)
         c2.begin_forward([0], [3], [-1, 2, 0])
+
+
+def _plan_cache(**kw):
+    from tvm_b200.kv_cache import PagedKVCache
+
+    cfg = dict(reserved_num_seqs=4, total_token_capacity=1024, prefill_chunk_size=512, num_layers=2, num_qo_heads=4,
+               num_kv_heads=1, head_dim=128, device=None)
+    cfg.update(kw)
+    return PagedKVCache(**cfg)
+
+
+def test_limits_and_preconditions_like_the_reference(built_lib):
+    """The reference's ICHECKs on the hot path (paged_kv_cache.cc:606-640, 772-830, 1566-1590, 1800-1870, 1404-1485),
+    with its messages: maximum tree size 256, tree shape, fork / popn / sliding-window preconditions, the split entries."""
+    from tvm_b200 import capi
+
+    E = capi.TvmB200Error
+    c = _plan_cache()
+    c.add_sequence(0)
+    c.begin_forward([0], [20])
+    c.attention_with_fused_qkv(0, 1.0, None, None)
+    c.end_forward()
+    # kTreeAttnMaxTreeSize = 256 (attn_utils.h:52): exactly 256 nodes pass, 257 do not
+    chain = list(range(-1, 255))
+    c.begin_forward([0], [256], chain)
+    c.commit_accepted_token_tree_nodes([0], [-1])
+    assert c.get_total_sequence_length() == 20
+    with pytest.raises(E, match="exceeds the maximum tree size limit 256"):
+        c.begin_forward([0], [257], list(range(-1, 256)))
+    c = _plan_cache()
+    c.add_sequence(0)
+    c.begin_forward([0], [20])
+    c.end_forward()
+    with pytest.raises(E, match="not smaller than"):
+        c.begin_forward([0], [3], [-1, 1, 0])
+    # a begin_forward that failed half-way leaves no batch: every consumer refuses it (this sequence used to crash)
+    with pytest.raises(E, match="did not complete"):
+        c.commit_accepted_token_tree_nodes([0], [0])
+    with pytest.raises(E, match="did not complete"):
+        c.attention_with_fused_qkv(0, 1.0, None, None)
+    c = _plan_cache()
+    c.add_sequence(0)
+    c.add_sequence(1)
+    c.begin_forward([0, 1], [20, 3])
+    c.end_forward()
+    with pytest.raises(E, match="already committed"):
+        c.commit_accepted_token_tree_nodes([0], [0])
+    with pytest.raises(E, match="is not sequence 0 of the last begin_forward"):
+        c.commit_accepted_token_tree_nodes([1], [-1])
+    with pytest.raises(E, match="3 sequences, but the last begin_forward had 2"):
+        c.commit_accepted_token_tree_nodes([0, 1, 1], [-1, -1, -1])
+    # a token tree that was not committed blocks the fork of its sequence
+    c2 = _plan_cache()
+    c2.add_sequence(0)
+    c2.begin_forward([0], [4], [-1, 0, 0, 1])
+    with pytest.raises(E, match="has not been committed|not been committed"):
+        c2.fork_sequence(0, 1, 2)
+    with pytest.raises(E, match="larger than or equals to the append length|Invalid tree index"):
+        c2.commit_accepted_token_tree_nodes([0], [4])
+    c2.commit_accepted_token_tree_nodes([0], [3])
+    assert c2.get_total_sequence_length() == 3          # the path 0 -> 1 -> 3
+    # fork / popn preconditions
+    with pytest.raises(E, match="should not exceed the total length of parent"):
+        c2.fork_sequence(0, 1, 9)
+    with pytest.raises(E, match="non-negative, or -1"):
+        c2.fork_sequence(0, 1, -2)
+    with pytest.raises(E, match="already in the KV cache"):
+        c2.fork_sequence(0, 0, 1)
+    with pytest.raises(E, match="cannot be negative"):
+        c2.popn(0, -1)
+    with pytest.raises(E):
+        c2.popn(0, 4)
+    with pytest.raises(E, match="Append with length 0 is not allowed"):
+        c2.begin_forward([0], [0])
+    with pytest.raises(E, match="more than prefill_chunk_size"):
+        c2.begin_forward([0], [513])
+    # sliding window
+    s = _plan_cache(support_sliding_window=True, rope_mode=2)
+    s.add_sequence(0)
+    with pytest.raises(E, match="should be less than the sliding window size"):
+        s.enable_sliding_window_for_seq(0, 8, 8)
+    with pytest.raises(E, match="should be positive"):
+        s.enable_sliding_window_for_seq(0, 0, 0)
+    with pytest.raises(E, match="non negative"):
+        s.enable_sliding_window_for_seq(0, 8, -1)
+    s.enable_sliding_window_for_seq(0, 24, 4)
+    with pytest.raises(E, match="cannot be enabled twice"):
+        s.enable_sliding_window_for_seq(0, 24, 4)
+    s.begin_forward([0], [40])
+    s.end_forward()
+    assert s.get_total_sequence_length() == 24          # the window slid
+    with pytest.raises(E, match="only can be forked within sink size|within sink size"):
+        s.fork_sequence(0, 1, 10)
+    with pytest.raises(E, match="Tree attention does not support sliding window"):
+        s.begin_forward([0], [2], [-1, 0])
+    # the split entries: rows must be the batch's append length, MHA layers only, layer ids inside the cache
+    m = _plan_cache(attn_kinds=[3, 0], layer_sliding_window_size=16, rope_mode=0)
+    m.add_sequence(0)
+    m.begin_forward([0], [5])
+    with pytest.raises(E, match="5 tokens|appends 5"):
+        m.self_attention(1, 1.0, 4, None, None, None, None)
+    with pytest.raises(E, match="not an MHA layer"):
+        m.cross_attention(0, 1.0, 5, None, None)
+    with pytest.raises(E, match="outside this cache's layers"):
+        m.attention_with_shared_kv(2, 1.0, 5, None, None, None)
+    m.self_attention(1, 1.0, 5, None, None, None, None)
+    m.end_forward()

@@ -123,6 +123,7 @@ class Cache {
                               int64_t num_heads, int64_t head_dim, cudaStream_t stream);
   void DebugGetKV(int64_t seq_id, int64_t start, int64_t end, void* k_out, void* v_out, cudaStream_t stream);
   void QueryPositions(const int32_t** ptr, int64_t* n, cudaStream_t stream) {
+    HCHECK(batch_valid_, "get_query_positions: call begin_forward first (the last one did not complete)");
     SyncAux(stream);
     *ptr = dev(v_q_rope_pos_);
     *n = v_q_rope_pos_.size;
@@ -163,6 +164,7 @@ class Cache {
 
   // ---- current batch ----
   bool dirty_ = false;
+  bool batch_valid_ = false;  // the last BeginForward ran to completion
   int64_t cur_batch_ = 0;
   std::vector<int64_t> cur_seq_ids_, cur_lens_;
   std::vector<bool> is_chain_on_depths_ = std::vector<bool>(kMaxBlockDepth, true);
@@ -454,6 +456,7 @@ void Cache::Clear() {
   blocks_.clear();
   free_blocks_.clear();
   dirty_ = false;
+  batch_valid_ = false;
 }
 
 void Cache::AddSequence(int64_t seq_id) {
@@ -763,6 +766,9 @@ void Cache::ConstructTokenTreeMask(const std::vector<Sequence*>& seqs, const int
 }
 
 void Cache::BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size) {
+  // a begin_forward that throws half-way (unknown sequence, cache full, invalid tree) leaves no usable batch: the
+  // attention / commit entries refuse to run on it instead of indexing half-built arrays
+  batch_valid_ = false;
   cur_batch_ = n;
   cur_seq_ids_.assign(seq_ids, seq_ids + n);
   cur_lens_.assign(lens, lens + n);
@@ -944,6 +950,7 @@ void Cache::BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, con
     }
   }
   BuildAuxViews();
+  batch_valid_ = true;
 }
 
 // layout of the merged buffer = order of SyncAuxArrayToDevice (paged_kv_cache.cc:2392-2512)
@@ -1128,6 +1135,7 @@ void Cache::AttentionInternal(int64_t layer_id, const void* q, const void* k, co
 }
 
 int64_t Cache::CheckLayer(int64_t layer_id) const {
+  HCHECK(batch_valid_, "no batch to attend over: call begin_forward first (the last one did not complete)");
   const int64_t local = layer_id - layer_begin_;
   HCHECK(local >= 0 && local < num_layers_, "layer_id %ld is outside this cache's layers [%ld, %ld)", (long)layer_id,
          (long)layer_begin_, (long)(layer_begin_ + num_layers_));
@@ -1238,10 +1246,17 @@ void Cache::MergeAttnOutputInplace(void* o_self, float* lse_self, const void* o_
 }
 
 void Cache::CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n) {
+  // the reference indexes cur_append_lengths_ / cur_seq_ids_ / append_position_map_host_ of the last BeginForward with
+  // the positions of seq_ids (paged_kv_cache.cc:1625-1650): the sequences must be that batch's, in its order
+  HCHECK(batch_valid_, "commit_accepted_token_tree_nodes: the last begin_forward did not complete");
+  HCHECK(n <= cur_batch_, "commit_accepted_token_tree_nodes: %d sequences, but the last begin_forward had %ld", n, (long)cur_batch_);
   std::vector<Sequence*> seqs;
   bool is_chain = true;
   for (int i = 0; i < n; ++i) {
+    HCHECK(seq_ids[i] == cur_seq_ids_[i], "commit_accepted_token_tree_nodes: sequence %ld at position %d is not sequence %ld "
+           "of the last begin_forward", (long)seq_ids[i], i, (long)cur_seq_ids_[i]);
     Sequence& s = Seq(seq_ids[i]);
+    HCHECK(s.tree_depth.size() == s.tree_parent.size(), "token tree of sequence %ld is incomplete", (long)seq_ids[i]);
     seqs.push_back(&s);
     is_chain = s.is_chain;
     HCHECK(leaves[i] == -1 || !s.committed, "The accepted nodes of sequence %ld are already committed.", (long)seq_ids[i]);
