@@ -62,7 +62,9 @@ TVMB200_API int tvmb200_cache_add_sequence(tvmb200_cache_t c, int64_t seq_id);
 TVMB200_API int tvmb200_cache_remove_sequence(tvmb200_cache_t c, int64_t seq_id);
 TVMB200_API int tvmb200_cache_fork_sequence(tvmb200_cache_t c, int64_t parent_seq_id, int64_t child_seq_id, int64_t fork_pos);
 TVMB200_API int tvmb200_cache_popn(tvmb200_cache_t c, int64_t seq_id, int32_t n);
-/*! \brief token_tree_parent_ptr may be NULL (no tree); otherwise it has sum(append_lengths) entries. */
+/*! \brief token_tree_parent_ptr may be NULL (no tree); otherwise it has sum(append_lengths) entries.  When the call
+ *  fails (unknown sequence, cache full, invalid tree) there is no current batch: the attention entries,
+ *  commit_accepted_token_tree_nodes and get_query_positions return an error until a begin_forward completes. */
 TVMB200_API int tvmb200_cache_begin_forward(tvmb200_cache_t c, const int64_t* seq_ids, const int64_t* append_lengths,
                                             int32_t batch_size, const int64_t* token_tree_parent_ptr, int32_t tree_size);
 TVMB200_API int tvmb200_cache_end_forward(tvmb200_cache_t c);
