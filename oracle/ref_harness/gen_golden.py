@@ -490,6 +490,10 @@ SCENARIOS = {
     "random_tree_b": (lambda: prog_random_tree(22), dict(rope_mode=0, num_layers=2)),
     "random_sliding_a": (lambda: prog_random_sliding(31), dict(rope_mode=2, support_sliding_window=True)),
     "random_sliding_b": (lambda: prog_random_sliding(32), dict(rope_mode=1, support_sliding_window=True)),
+    # a pipeline stage that owns layers [2, 4) of a 4-layer model (layer_indptr = [2, 4]): attention calls carry GLOBAL
+    # layer ids, attn_kinds has one entry per model layer (layer 2 plain, layer 3 sliding)
+    "layer_offset": (prog_shared_kv, dict(rope_mode=0, num_layers=2, layer_begin=2, attn_kinds=[3, 3, 0, 3],
+                                          layer_sliding_window_size=32)),
     "layer_sliding": (prog_prefill_and_decode, dict(rope_mode=0, num_layers=2, attn_kinds=[3, 0], layer_sliding_window_size=20)),
     "layer_sliding_inline_rope": (prog_prefill_and_decode, dict(rope_mode=2, num_layers=2, attn_kinds=[0, 3],
                                                                 layer_sliding_window_size=35)),
@@ -514,7 +518,7 @@ SCENARIOS = {
 }
 BASE = dict(num_layers=1, num_qo_heads=4, num_kv_heads=1, head_dim=128, dtype="float16", reserved_nseq=32,
             max_total_seq=2048, prefill_chunk=512, page_size=16, rope_scale=1.0, rope_theta=1e4,
-            layer_sliding_window_size=None, attn_kinds=None)
+            layer_sliding_window_size=None, attn_kinds=None, layer_begin=0)
 
 
 def q2_for(seed, num_layers, n, hq, d, dtype="float16"):
@@ -598,14 +602,14 @@ def capture(name, prog, cfg, kernels=None):
             shared_outs = []
             for layer in range(L):
                 o = tvm.runtime.empty((n, hq, d), cfg["dtype"], device=rc.dev)
-                rc.call("attention_kv_cache_attention_with_fused_qkv", layer, d ** -0.5,
+                rc.call("attention_kv_cache_attention_with_fused_qkv", cfg["layer_begin"] + layer, d ** -0.5,
                         tvm.runtime.tensor(qkv[layer], device=rc.dev), o)
                 outs.append(o.numpy())
                 if q2 is not None:
                     # rope is none or inline in these scenarios, so the step's raw k / v are the "current" k / v
                     assert cfg["rope_mode"] != 1
                     o2 = tvm.runtime.empty((n, hq, d), cfg["dtype"], device=rc.dev)
-                    rc.call("attention_kv_cache_attention_with_shared_kv", layer, d ** -0.5,
+                    rc.call("attention_kv_cache_attention_with_shared_kv", cfg["layer_begin"] + layer, d ** -0.5,
                             tvm.runtime.tensor(q2[layer], device=rc.dev),
                             tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq:hq + hkv]), device=rc.dev),
                             tvm.runtime.tensor(np.ascontiguousarray(qkv[layer][:, hq + hkv:]), device=rc.dev), o2)
@@ -630,8 +634,8 @@ def capture(name, prog, cfg, kernels=None):
                 # cross_attention leaves (o, lse) untouched when no sequence of the batch has a cached page
                 o_cross = tvm.runtime.tensor(np.zeros((n, hq, d), cfg["dtype"]), device=dev)
                 lse_cross = tvm.runtime.tensor(np.full((n, hq), -5e4, "float32"), device=dev)
-                rc.call("attention_kv_cache_self_attention", layer, d ** -0.5, q, kk, vv, o_self, lse_self)
-                rc.call("attention_kv_cache_cross_attention", layer, d ** -0.5, q, o_cross, lse_cross)
+                rc.call("attention_kv_cache_self_attention", cfg["layer_begin"] + layer, d ** -0.5, q, kk, vv, o_self, lse_self)
+                rc.call("attention_kv_cache_cross_attention", cfg["layer_begin"] + layer, d ** -0.5, q, o_cross, lse_cross)
                 selfs.append(o_self.numpy())
                 crosses.append(o_cross.numpy())
                 ret = rc.call("attention_kv_cache_merge_attn_output_inplace", o_self, lse_self, o_cross, lse_cross)

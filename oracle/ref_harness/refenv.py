@@ -83,7 +83,8 @@ class RefCache:
 
     def __init__(self, num_layers=1, num_qo_heads=8, num_kv_heads=2, head_dim=128, dtype="float16", rope_mode=1,
                  support_sliding_window=False, reserved_nseq=32, max_total_seq=2048, prefill_chunk=512, page_size=16,
-                 rope_scale=1.0, rope_theta=1e4, layer_sliding_window_size=None, attn_kinds=None, kernels=None):
+                 rope_scale=1.0, rope_theta=1e4, layer_sliding_window_size=None, attn_kinds=None, kernels=None,
+                 layer_begin=0):
         self.cfg = dict(num_layers=num_layers, num_qo_heads=num_qo_heads, num_kv_heads=num_kv_heads,
                         head_dim=head_dim, dtype=dtype, rope_mode=int(rope_mode),
                         support_sliding_window=int(support_sliding_window), reserved_nseq=reserved_nseq,
@@ -117,9 +118,9 @@ class RefCache:
         if layer_sliding_window_size is not None:
             cache_config.append(layer_sliding_window_size)
         if attn_kinds is None:
-            attn_kinds = [int(AttnKind.MHA)] * num_layers
+            attn_kinds = [int(AttnKind.MHA)] * (layer_begin + num_layers)
         self.cache = g("vm.builtin.paged_attention_kv_cache_create")(
-            tvm_ffi.Shape(cache_config), tvm_ffi.Shape([0, num_layers]), num_qo_heads, num_kv_heads, head_dim, head_dim,
+            tvm_ffi.Shape(cache_config), tvm_ffi.Shape([layer_begin, layer_begin + num_layers]), num_qo_heads, num_kv_heads, head_dim, head_dim,
             tvm_ffi.Shape(attn_kinds), False, int(rope_mode), rope_scale, rope_theta, None,
             tvm.runtime.empty((), dtype, device=self.dev),
             fns["transpose_append"], None, ["tirx", fns["prefill_ragged"]], ["tirx", fns["prefill"]],

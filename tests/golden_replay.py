@@ -50,7 +50,8 @@ def make_cache(cfg, device):
                         num_qo_heads=cfg["num_qo_heads"], num_kv_heads=cfg["num_kv_heads"], head_dim=cfg["head_dim"],
                         rope_mode=cfg["rope_mode"], rotary_scale=cfg["rope_scale"], rotary_theta=cfg["rope_theta"],
                         dtype=cfg["dtype"], device=device, attn_kinds=cfg.get("attn_kinds"),
-                        layer_sliding_window_size=cfg.get("layer_sliding_window_size"))
+                        layer_sliding_window_size=cfg.get("layer_sliding_window_size"),
+                        layer_id_begin_offset=cfg.get("layer_begin", 0))
 
 
 def q2_for(seed, num_layers, n, hq, d, dtype="float16"):
@@ -87,6 +88,7 @@ def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=No
     cache = make_cache(cfg, device)
     cache.set_trace(True)
     L, hq, hkv, d = cfg["num_layers"], cfg["num_qo_heads"], cfg["num_kv_heads"], cfg["head_dim"]
+    lb = cfg.get("layer_begin", 0)  # attention calls carry global layer ids
     for idx, (op, res) in enumerate(zip(meta["ops"], meta["results"])):
         k = op["op"]
         where = f"{name} op {idx} {op}"
@@ -143,9 +145,9 @@ def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=No
             shared = bool(op.get("shared"))
             if device is None:
                 for layer in range(L):
-                    cache.attention_with_fused_qkv(layer, d ** -0.5, None, None)
+                    cache.attention_with_fused_qkv(lb + layer, d ** -0.5, None, None)
                     if shared:
-                        cache.attention_with_shared_kv(layer, d ** -0.5, n, None, None, None)
+                        cache.attention_with_shared_kv(lb + layer, d ** -0.5, n, None, None, None)
             else:
                 import torch
 
@@ -155,11 +157,11 @@ def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=No
                 for layer in range(L):
                     tq = torch.from_numpy(qkv[layer]).cuda()
                     o = torch.full((n, hq, d), float("nan"), dtype=tq.dtype, device="cuda")
-                    cache.attention_with_fused_qkv(layer, d ** -0.5, tq, o)
+                    cache.attention_with_fused_qkv(lb + layer, d ** -0.5, tq, o)
                     outs.append(o)
                     if shared:
                         o2 = torch.full((n, hq, d), float("nan"), dtype=tq.dtype, device="cuda")
-                        cache.attention_with_shared_kv(layer, d ** -0.5, torch.from_numpy(q2[layer]).cuda(),
+                        cache.attention_with_shared_kv(lb + layer, d ** -0.5, torch.from_numpy(q2[layer]).cuda(),
                                                        tq[:, hq:hq + hkv].contiguous(), tq[:, hq + hkv:].contiguous(), o2)
                         shared_outs.append(o2)
                 torch.cuda.synchronize()
@@ -174,8 +176,8 @@ def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=No
             n = sum(op["lens"])
             if device is None:
                 for layer in range(L):
-                    cache.self_attention(layer, d ** -0.5, n, None, None, None, None)
-                    cache.cross_attention(layer, d ** -0.5, n, None, None)
+                    cache.self_attention(lb + layer, d ** -0.5, n, None, None, None, None)
+                    cache.cross_attention(lb + layer, d ** -0.5, n, None, None)
                     cache.merge_attn_output_inplace(n, None, None, None)
             else:
                 import torch
@@ -188,8 +190,8 @@ def replay_meta(name, meta, z, device, on_forward=None, on_kv=None, on_shared=No
                     o_self = torch.zeros((n, hq, d), dtype=tq.dtype, device="cuda")
                     lse_self = torch.full((n, hq), -5e4, dtype=torch.float32, device="cuda")
                     o_cross, lse_cross = torch.zeros_like(o_self), torch.full_like(lse_self, -5e4)
-                    cache.self_attention(layer, d ** -0.5, q, kk, vv, o_self, lse_self)
-                    cache.cross_attention(layer, d ** -0.5, q, o_cross, lse_cross)
+                    cache.self_attention(lb + layer, d ** -0.5, q, kk, vv, o_self, lse_self)
+                    cache.cross_attention(lb + layer, d ** -0.5, q, o_cross, lse_cross)
                     got["oself"].append(o_self.clone())
                     got["ocross"].append(o_cross.clone())
                     ro, rl = cache.merge_attn_output_inplace(o_self, lse_self, o_cross, lse_cross)
