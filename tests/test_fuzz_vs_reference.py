@@ -21,3 +21,13 @@ def test_random_programs_match_the_reference_live(built_lib):
     tail = "\n".join(line for line in (r.stdout + r.stderr).splitlines() if "arm_aprofile" not in line)[-3000:]
     assert r.returncode == 0, f"first seed {seed}:\n{tail}"
     assert "OK: 10 programs" in r.stdout, tail
+
+
+@pytest.mark.skipif(not (ENV.exists() and Path("/root/reference").exists()), reason="no reference build in this container")
+def test_library_loads_in_the_reference_runtime(built_lib):
+    """INTEGRATION.md routes A / A2 inside the reference's own process (vendored tvm-ffi, libtvm_runtime, its vm.builtin
+    registrations present): oracle/ref_harness/load_in_reference_runtime.py."""
+    r = subprocess.run(["bash", "-c", f"source {ENV} && {sys.executable} oracle/ref_harness/load_in_reference_runtime.py"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    tail = "\n".join(line for line in (r.stdout + r.stderr).splitlines() if "arm_aprofile" not in line)[-3000:]
+    assert r.returncode == 0 and "reference runtime ok" in r.stdout, tail
