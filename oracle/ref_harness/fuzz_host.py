@@ -27,6 +27,8 @@ KINDS = {
     # name: (builder(seed), cache kwargs by seed parity)
     "plain": (gg.prog_random, [dict(rope_mode=1), dict(rope_mode=0), dict(rope_mode=2)]),
     "tree": (gg.prog_random_tree, [dict(rope_mode=1), dict(rope_mode=0)]),
+    # token trees on sequences that fork and disappear between the phases
+    "tree_forks": (lambda seed: gg.prog_random_tree(seed, forks=True), [dict(rope_mode=0), dict(rope_mode=1)]),
     "sliding": (gg.prog_random_sliding, [dict(rope_mode=2, support_sliding_window=True),
                                          dict(rope_mode=1, support_sliding_window=True)]),
     # attention_with_shared_kv behind every fused call + self / cross / merge steps (rope none or inline: the step's raw
@@ -42,6 +44,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=20)
     ap.add_argument("--first", type=int, default=1000)
+    ap.add_argument("--only", default="", help="comma-separated generator names")
     ap.add_argument("--oracle", action="store_true", help="also re-execute the traces with the NumPy oracle")
     a = ap.parse_args()
     from tests.golden_replay import replay_meta
@@ -51,6 +54,8 @@ def main():
     t0 = time.time()
     for seed in range(a.first, a.first + a.seeds):
         for kind, (builder, kws) in KINDS.items():
+            if a.only and kind not in a.only.split(","):
+                continue
             cfg = dict(gg.BASE)
             cfg.update(kws[seed % len(kws)])
             prog = builder(seed)

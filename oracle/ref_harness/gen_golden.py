@@ -306,7 +306,7 @@ def prog_random(seed, shared=False, split=False):
     return p
 
 
-def prog_random_tree(seed):
+def prog_random_tree(seed, forks=False):
     """Randomised speculative-decoding program: prefill / decode steps interleaved with token-tree phases -- 1 to 3 rounds
     of random trees over a random subset of the sequences (later rounds hang new nodes under any earlier node), then a
     commit of a random root-to-node path (or of nothing, -1) per sequence."""
@@ -317,8 +317,23 @@ def prog_random_tree(seed):
         n = int(rng.integers(3, 50))
         p.forward([(sid, n)])
         length[sid] = n
+    next_id = 5
     for _ in range(14):
         live = sorted(length)
+        if forks and rng.random() < 0.25 and len(live) < 9:
+            # between tree phases every sequence is committed: fork one (at a random position or its end), or drop one
+            parent = int(rng.choice(live))
+            pos = int(rng.integers(1, length[parent] + 1)) if rng.random() < 0.6 else -1
+            n = int(rng.integers(1, 12))
+            p.forward([((next_id, parent, pos), n)])
+            length[next_id] = (length[parent] if pos == -1 else pos) + n
+            next_id += 1
+            continue
+        if forks and rng.random() < 0.08 and len(live) > 3:
+            s_ = int(rng.choice(live))
+            p.op(op="remove", seq=s_)
+            del length[s_]
+            continue
         k = int(rng.integers(1, len(live) + 1))
         sel = sorted(int(x) for x in rng.choice(live, size=k, replace=False))
         if rng.random() < 0.35:
