@@ -1,6 +1,7 @@
 """The C-ABI library loads without a GPU and exports every symbol declared in include/*.h, plus the tvm-ffi packed
 functions under the reference's callback names.  No compute call is made here."""
 import ctypes
+import re
 
 import pytest
 
@@ -48,3 +49,39 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(capi, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(capi.TvmB200Error, match="no CPU fallback"):
         capi.lib()
+
+
+def test_packed_functions_validate_like_the_tir_binders(built_lib):
+    """The generated TIR binders of the reference check argument count, kind, dtype and shape before anything runs
+    (src/tirx/transform/tvm_ffi_binder.cc:704-807); the packed functions do the same, ahead of the device check -- so this
+    runs without a GPU."""
+    import torch
+
+    from tvm_b200 import ffi
+
+    m = ffi.module()
+    f16 = lambda *s: torch.zeros(s, dtype=torch.float16)  # noqa: E731
+    i32 = lambda *s: torch.zeros(s, dtype=torch.int32)  # noqa: E731
+    f32 = lambda *s: torch.zeros(s, dtype=torch.float32)  # noqa: E731
+    pages = f16(2, 2, 1, 16, 128)
+    q, o, lse = f16(2, 4, 128), f16(2, 4, 128), f32(2, 4)
+    dec = (q, pages, i32(3), i32(2), i32(2), i32(2), i32(2), o, lse)
+    cases = [
+        (TypeError, "expects 4 arguments, got 3", "f_transpose_append", (pages, f16(3, 1, 128), f16(3, 1, 128))),
+        (TypeError, "must be a Tensor", "f_transpose_append", (pages, f16(3, 1, 128), f16(3, 1, 128), 5)),
+        (ValueError, "dtype mismatch: k_data vs pages", "f_transpose_append", (pages, f32(3, 1, 128), f16(3, 1, 128), i32(3))),
+        (ValueError, "position_map must be int32", "f_transpose_append", (pages, f16(3, 1, 128), f16(3, 1, 128), f32(3))),
+        (ValueError, "shape mismatch", "f_transpose_append", (pages, f16(3, 1, 64), f16(3, 1, 128), i32(3))),
+        (TypeError, "expects 13 arguments, got 12", "f_attention_decode", dec + (0, 1.0, 1e4)),
+        (ValueError, "lse must be float32", "f_attention_decode", dec[:8] + (f16(2, 4), 0, 1.0, 1e4, 0.08)),
+        (TypeError, "rotary_mode) must be an int", "f_attention_decode", dec + ("x", 1.0, 1e4, 0.08)),
+        (ValueError, "shape mismatch", "f_merge_inplace", (o, lse, o, f32(2, 5))),
+        (ValueError, "rope_ext_factors (longrope", "f_split_rotary",
+         (f16(2, 6, 128), i32(2), f16(2, 4, 128), f16(2, 1, 128), f16(2, 1, 128), f32(128))),
+        # everything valid: the device check is what is left
+        (ValueError, "no CPU fallback", "f_attention_decode", dec + (0, 1.0, 1e4, 0.08)),
+        (ValueError, "no CPU fallback", "f_split_rotary", (f16(2, 6, 128), i32(2), f16(2, 4, 128), f16(2, 1, 128), f16(2, 1, 128), 1)),
+    ]
+    for exc, fragment, name, args in cases:
+        with pytest.raises(exc, match=re.escape(fragment)):
+            m[name](*args)

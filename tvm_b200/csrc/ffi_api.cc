@@ -303,6 +303,9 @@ int impl_fused_rope(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   }
   Tensor qkv = arg_tensor(args, 0, fn, "qkv"), pm = arg_tensor(args, 1, fn, "position_map"),
          q = arg_tensor(args, 2, fn, "q"), k = arg_tensor(args, 3, fn, "k"), v = arg_tensor(args, 4, fn, "v");
+  // the longrope flavour of the reference PrimFunc takes `ext_factors` (a tensor) here (position_embedding.py:567-667)
+  if (args[5].type_index == kTVMFFITensor || args[5].type_index == kTVMFFIDLTensorPtr)
+    throw Err{"ValueError", fmt("%s: rope_ext_factors (longrope, fused_rope_longrope_scaling) is not supported", fn)};
   const int64_t apply_rope = arg_int(args, 5, fn, "apply_rope");
   expect_ndim(qkv, 3, fn, "qkv");
   expect_ndim(q, 3, fn, "q");
