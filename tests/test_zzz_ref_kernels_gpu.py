@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import cpu_ref
+from tests.golden_replay import late_scenario_names
+from tests.test_cache_gpu_golden import run_scenario
 from tests.test_ref_kernels import _ragged_inputs, ref_merge, ref_ragged_prefill
 from tests.util import assert_close, to_dev, to_np
 
@@ -87,3 +89,10 @@ def test_ragged_prefill_and_merge_vs_the_reference_kernels(built_lib, ref_mod, r
     torch.cuda.synchronize()
     assert_close("merge V", to_np(dv), mv)
     assert_close("merge S", to_np(ds), ms)
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+@pytest.mark.parametrize("name", late_scenario_names())
+def test_late_scenario_matches_reference(built_lib, name, impl):
+    """Fixtures captured from the reference after the last GPU session of the round (tests/golden_replay.py)."""
+    run_scenario(name, impl)
