@@ -31,8 +31,7 @@ def base_scenario_names():
     return [n for n in scenario_names() if n in BASE_SCENARIOS]
 
 
-# fixtures added after the round's last GPU session: replayed on the GPU by the last test file (tests/test_zzz_*), so
-# that a surprise there cannot hide the results of the files that have already run on a B200
+# fixtures added late in the round: replayed on the GPU by the last test file (tests/test_zzz_*)
 LATE_SCENARIOS = ("layer_offset",)
 
 

@@ -94,5 +94,5 @@ def test_ragged_prefill_and_merge_vs_the_reference_kernels(built_lib, ref_mod, r
 @pytest.mark.parametrize("impl", [0, 2])
 @pytest.mark.parametrize("name", late_scenario_names())
 def test_late_scenario_matches_reference(built_lib, name, impl):
-    """Fixtures captured from the reference after the last GPU session of the round (tests/golden_replay.py)."""
+    """Fixtures captured from the reference late in the round (tests/golden_replay.py::LATE_SCENARIOS)."""
     run_scenario(name, impl)
