@@ -27,6 +27,8 @@ KINDS = {
     # name: (builder(seed), cache kwargs by seed parity)
     "plain": (gg.prog_random, [dict(rope_mode=1), dict(rope_mode=0), dict(rope_mode=2)]),
     "tree": (gg.prog_random_tree, [dict(rope_mode=1), dict(rope_mode=0)]),
+    # popn across fork points (the sequence is re-created as a fork of itself)
+    "deep_popn": (lambda seed: gg.prog_random(seed, deep_popn=True), [dict(rope_mode=1), dict(rope_mode=2)]),
     # token trees on sequences that fork and disappear between the phases
     "tree_forks": (lambda seed: gg.prog_random_tree(seed, forks=True), [dict(rope_mode=0), dict(rope_mode=1)]),
     "sliding": (gg.prog_random_sliding, [dict(rope_mode=2, support_sliding_window=True),

@@ -235,12 +235,13 @@ def prog_tree_attn():
     return p
 
 
-def prog_random(seed, shared=False, split=False):
+def prog_random(seed, shared=False, split=False, deep_popn=False):
     """Randomised differential scenario: a few hundred cache operations drawn at random -- prefill chunks, decode
     steps over random subsets, forks at random positions (also of forked sequences), popn (kept inside a sequence's own
     last block, as the reference requires), removals -- so that the host cache's page allocation, block tree, copy-on-
     fork and aux-array construction are compared with the reference far off the hand-written paths.
-    shared: every forward also issues attention_with_shared_kv per layer; split: self_attention / cross_attention /
+    deep_popn: popn may cut into blocks shared with other sequences.  shared: every forward also issues
+    attention_with_shared_kv per layer; split: self_attention / cross_attention /
     merge_attn_output_inplace steps (rolled back by popn) are mixed in."""
     rng = np.random.default_rng(seed)
     p = Program()
@@ -282,6 +283,15 @@ def prog_random(seed, shared=False, split=False):
                 length[s_] += n
                 tail[s_] += n
                 total += n
+        elif r < 0.90 and live and deep_popn:
+            # pop across fork points: the reference re-creates the sequence as a fork of itself at the shorter length
+            # (PopN, paged_kv_cache.cc:803-860)
+            s_ = int(rng.choice(live))
+            if length[s_] > 1:
+                n = int(rng.integers(1, length[s_]))
+                p.op(op="popn", seq=s_, n=n)
+                length[s_] -= n
+                tail[s_] = max(tail[s_] - n, 0)
         elif r < 0.90 and live:
             s_ = int(rng.choice(live))
             if tail[s_] > 1:
