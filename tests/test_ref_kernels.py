@@ -78,3 +78,144 @@ def test_ref_ragged_prefill_and_merge_match_oracle(rotary_mode):
     wv, ws = ok.merge_state_inplace(o.copy(), lse.copy(), o2, lse2, "float16")
     np.testing.assert_allclose(mv, wv, atol=2e-3, rtol=1e-2)
     np.testing.assert_allclose(ms, ws, atol=2e-3, rtol=1e-2)
+
+
+# ---- the remaining attention kernels of the reference at the Llama-3-8B head shape ---------------------------------
+HQ, HKV, D, THETA, SM = 32, 8, 128, 5e5, 128 ** -0.5
+
+
+def _t(a):
+    import torch
+
+    a = np.asarray(a)
+    return torch.from_numpy(np.ascontiguousarray(a.astype(np.float16) if a.dtype in (np.float32, np.float64) else a))
+
+
+def _out(n):
+    import torch
+
+    return torch.zeros((n, HQ, D), dtype=torch.float16), torch.zeros((n, HQ), dtype=torch.float32)
+
+
+def _need_ref():
+    mod = cpu_ref._ref_module("float16", HQ, HKV, D)
+    if mod is None:
+        pytest.skip("oracle/_ref not built (needs the reference build, see oracle/ref_harness/)")
+    try:
+        mod["batch_prefill_paged_kv_cpu"]
+    except Exception:
+        pytest.skip("oracle/_ref holds the decode-step kernels only (re-run oracle/ref_harness/emit_ref_kernels.py)")
+    return mod
+
+
+def _dfs_mask(parents):
+    """(dfs_order, subtree_end) rows as ConstructTokenTreeMask emits them (paged_kv_cache.cc:1900-1918)."""
+    n = len(parents)
+    children, roots = [[] for _ in range(n)], []
+    for i, p in enumerate(parents):
+        (roots if p < 0 else children[p]).append(i)
+    order, end, cnt = [0] * n, [0] * n, [0]
+
+    def visit(u):
+        order[u] = cnt[0]
+        cnt[0] += 1
+        for c in children[u]:
+            visit(c)
+        end[u] = cnt[0]
+
+    for r in roots:
+        visit(r)
+    return np.array([[order[i], end[i]] for i in range(n)], np.int32)
+
+
+def _paged_case(rng, q_lens, kv_lens, sliding=None):
+    from tests.util import make_paged_cache, rand16
+
+    B = len(q_lens)
+    qi = np.zeros(B + 1, np.int32)
+    qi[1:] = np.cumsum(q_lens)
+    c = make_paged_cache(rng, kv_lens, HKV, D, "float16", sliding=sliding)
+    q = rand16(rng, (int(qi[-1]), HQ, D), "float16")
+    kofs = rng.integers(0, 30, B).astype(np.int32)
+    vis = list(kv_lens) if sliding is None else [L - s[0] + s[1] for L, s in zip(kv_lens, sliding)]
+    qpos = np.concatenate([kofs[b] + vis[b] + np.arange(q_lens[b]) for b in range(B)]).astype(np.int32)
+    return c, q, qi, kofs, qpos
+
+
+@pytest.mark.parametrize("causal,rotary_mode", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_ref_paged_prefill_matches_oracle(causal, rotary_mode):
+    mod = _need_ref()
+    rng = np.random.default_rng(21)
+    q_lens, kv_lens = [3, 17, 40], [20, 100, 333]
+    if causal:  # the query rows are the last q_len cached tokens
+        kv_lens = [a + b for a, b in zip(kv_lens, q_lens)]
+    c, q, qi, kofs, qpos = _paged_case(rng, q_lens, kv_lens)
+    if causal:
+        qpos = np.concatenate([kofs[b] + kv_lens[b] - q_lens[b] + np.arange(q_lens[b]) for b in range(3)]).astype(np.int32)
+    o, lse = _out(q.shape[0])
+    mod["batch_prefill_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                      _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, causal, rotary_mode, 1.0, THETA, SM)
+    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
+                                        causal, rotary_mode, 1.0, THETA, SM, "float16")
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("rotary_mode", [0, 1])
+def test_ref_sliding_window_decode_and_prefill_match_oracle(rotary_mode):
+    """The `_sliding_window` flavours: length_info [3, B] = (last_page_len, sliding_window_offset, sink_size)."""
+    mod = _need_ref()
+    rng = np.random.default_rng(22)
+    kv_slots, sliding = [70, 300, 40], [(37, 4), (16, 16), (0, 0)]
+    c, q, qi, kofs, qpos = _paged_case(rng, [1, 1, 1], kv_slots, sliding)
+    qpos = (qpos - 1).astype(np.int32)   # decode: the query is the last visible token
+    o, lse = _out(3)
+    mod["batch_decode_paged_kv_sliding_window_cpu"](_t(q), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                                    _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, rotary_mode, 1.0,
+                                                    THETA, SM)
+    wo, wl = ok.attention_decode(q, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
+                                 rotary_mode, 1.0, THETA, SM, "float16")
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    c, q, qi, kofs, qpos = _paged_case(rng, [5, 9, 2], kv_slots, sliding)
+    o, lse = _out(q.shape[0])
+    # emit_ref_kernels.py builds this flavour with the reference's default layer window (1024): wider than these caches
+    mod["batch_prefill_paged_kv_sliding_window_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]),
+                                                     _t(c["page_values"]), _t(c["length_info"]), _t(kofs), _t(qpos), o, lse,
+                                                     0, rotary_mode, 1.0, THETA, SM)
+    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
+                                        0, rotary_mode, 1.0, THETA, SM, "float16", sliding_window_size=1024)
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+
+
+def test_ref_tree_attention_matches_oracle():
+    """tree_attn_cpu (ragged, the new tokens among themselves) and tree_attn_with_paged_kv_cache_cpu (the tree occupies the
+    trailing columns of the cached KV), token trees given as (dfs order, subtree end) rows."""
+    from tests.util import rand16
+
+    mod = _need_ref()
+    rng = np.random.default_rng(23)
+    trees = [[-1, 0, 0, 1], [(k - 1) // 2 if k else -1 for k in range(15)], [-1, 0, 1, -1, 3, 3, 0]]
+    masks = np.concatenate([_dfs_mask(t) for t in trees])
+    lens = [len(t) for t in trees]
+    ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(ip[-1])
+    q, k, v = (rand16(rng, (n, h, D), "float16") for h in (HQ, HKV, HKV))
+    qpos = np.concatenate([30 + np.arange(x) for x in lens]).astype(np.int32)
+    o, lse = _out(n)
+    mod["batch_tree_attn_cpu"](_t(q), _t(ip), _t(k), _t(v), _t(ip), _t(qpos), _t(ip), _t(masks), o, lse, 0, 1.0, THETA, SM)
+    wo, wl = ok.attention_prefill_ragged(q, ip, k, v, ip, qpos, None, 0, 0, 1.0, THETA, SM, "float16", mn_indptr=ip,
+                                         tree_mask=masks)
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    # paged: the cached KV of each sequence ends with its tree
+    kv_lens = [x + extra for x, extra in zip(lens, (20, 200, 0))]
+    c, q, qi, kofs, qpos = _paged_case(rng, lens, kv_lens)
+    o, lse = _out(n)
+    mod["tree_attn_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                  _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, 0, 1.0, THETA, SM, _t(ip), _t(masks))
+    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
+                                        0, 0, 1.0, THETA, SM, "float16", tree_indptr=ip, tree_order=masks)
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
