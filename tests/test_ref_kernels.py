@@ -219,3 +219,37 @@ def test_ref_tree_attention_matches_oracle():
                                         0, 0, 1.0, THETA, SM, "float16", tree_indptr=ip, tree_order=masks)
     np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
     np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+
+
+def test_ref_empty_and_boundary_lengths_match_oracle():
+    """Edge cases against the reference's own kernels: sequences with no cached KV (O = 0, lse = -5e4), KV lengths around
+    the page size, sequences with no query rows, a one-token ragged prefill."""
+    mod = _need_ref()
+    rng = np.random.default_rng(24)
+    kv = [0, 1, 15, 16, 17, 32, 33, 0]
+    c, q, qi, kofs, qpos = _paged_case(rng, [1] * len(kv), kv)
+    qpos = np.maximum(qpos - 1, 0).astype(np.int32)
+    o, lse = _out(len(kv))
+    mod["batch_decode_paged_kv_cpu"](_t(q), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]), _t(c["length_info"]),
+                                     _t(kofs), _t(qpos), o, lse, 0, 1.0, THETA, SM)
+    wo, wl = ok.attention_decode(q, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos, 0, 1.0,
+                                 THETA, SM, "float16")
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    assert (lse.numpy()[[0, 7]] == -5e4).all() and (o.float().numpy()[[0, 7]] == 0).all()
+    q_lens, kv_lens = [3, 0, 5, 2], [0, 20, 16, 1]
+    c, q, qi, kofs, qpos = _paged_case(rng, q_lens, kv_lens)
+    o, lse = _out(q.shape[0])
+    mod["batch_prefill_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                      _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, 0, 0, 1.0, THETA, SM)
+    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
+                                        0, 0, 1.0, THETA, SM, "float16")
+    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    assert (lse.numpy()[:3] == -5e4).all()
+    inp = _ragged_inputs(seed=6, lens=(1, 0, 16, 17))
+    o, lse = ref_ragged_prefill(mod, inp, 1)
+    wo, wl = ok.attention_prefill_ragged(inp["q"], inp["ip"], inp["k"], inp["v"], inp["ip"], inp["qpos"], inp["kofs"], 1, 1, 1.0,
+                                         THETA, SM, "float16")
+    np.testing.assert_allclose(o, wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse, wl, atol=2e-3, rtol=1e-2)
