@@ -142,9 +142,9 @@ def _paged_case(rng, q_lens, kv_lens, sliding=None):
     return c, q, qi, kofs, qpos
 
 
-@pytest.mark.parametrize("causal,rotary_mode", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_ref_paged_prefill_matches_oracle(causal, rotary_mode):
-    mod = _need_ref()
+# Each case_* runs one of the reference's compiled kernels on seeded inputs and returns (inputs, O, LSE); the CPU tests
+# below compare the oracle with them, tests/test_zzz_ref_kernels_gpu.py compares the CUDA kernels with them.
+def case_paged_prefill(mod, causal, rotary_mode):
     rng = np.random.default_rng(21)
     q_lens, kv_lens = [3, 17, 40], [20, 100, 333]
     if causal:  # the query rows are the last q_len cached tokens
@@ -155,70 +155,107 @@ def test_ref_paged_prefill_matches_oracle(causal, rotary_mode):
     o, lse = _out(q.shape[0])
     mod["batch_prefill_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
                                       _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, causal, rotary_mode, 1.0, THETA, SM)
-    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
-                                        causal, rotary_mode, 1.0, THETA, SM, "float16")
-    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
-    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    return dict(c=c, q=q, qi=qi, kofs=kofs, qpos=qpos), o.float().numpy(), lse.numpy()
+
+
+SLIDING_SLOTS, SLIDING = [70, 300, 40], [(37, 4), (16, 16), (0, 0)]   # (sliding_window_offset, sink_size) per sequence
+
+
+def case_sliding_decode(mod, rotary_mode):
+    rng = np.random.default_rng(22)
+    c, q, qi, kofs, qpos = _paged_case(rng, [1, 1, 1], SLIDING_SLOTS, SLIDING)
+    qpos = (qpos - 1).astype(np.int32)   # decode: the query is the last visible token
+    o, lse = _out(3)
+    mod["batch_decode_paged_kv_sliding_window_cpu"](_t(q), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                                    _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, rotary_mode, 1.0,
+                                                    THETA, SM)
+    return dict(c=c, q=q, qi=qi, kofs=kofs, qpos=qpos), o.float().numpy(), lse.numpy()
+
+
+def case_sliding_prefill(mod, rotary_mode):
+    rng = np.random.default_rng(25)
+    c, q, qi, kofs, qpos = _paged_case(rng, [5, 9, 2], SLIDING_SLOTS, SLIDING)
+    o, lse = _out(q.shape[0])
+    # emit_ref_kernels.py builds this flavour with the reference's default layer window (1024): wider than these caches
+    mod["batch_prefill_paged_kv_sliding_window_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]),
+                                                     _t(c["page_values"]), _t(c["length_info"]), _t(kofs), _t(qpos), o, lse,
+                                                     0, rotary_mode, 1.0, THETA, SM)
+    return dict(c=c, q=q, qi=qi, kofs=kofs, qpos=qpos), o.float().numpy(), lse.numpy()
+
+
+TREES = [[-1, 0, 0, 1], [(k - 1) // 2 if k else -1 for k in range(15)], [-1, 0, 1, -1, 3, 3, 0]]
+
+
+def _tree_arrays():
+    masks = np.concatenate([_dfs_mask(t) for t in TREES])
+    lens = [len(t) for t in TREES]
+    return masks, lens, np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+
+
+def case_tree_ragged(mod):
+    """tree_attn_cpu: the new tokens among themselves, token trees given as (dfs order, subtree end) rows."""
+    from tests.util import rand16
+
+    rng = np.random.default_rng(23)
+    masks, lens, ip = _tree_arrays()
+    n = int(ip[-1])
+    q, k, v = (rand16(rng, (n, h, D), "float16") for h in (HQ, HKV, HKV))
+    qpos = np.concatenate([30 + np.arange(x) for x in lens]).astype(np.int32)
+    o, lse = _out(n)
+    mod["batch_tree_attn_cpu"](_t(q), _t(ip), _t(k), _t(v), _t(ip), _t(qpos), _t(ip), _t(masks), o, lse, 0, 1.0, THETA, SM)
+    return dict(q=q, k=k, v=v, ip=ip, qpos=qpos, masks=masks), o.float().numpy(), lse.numpy()
+
+
+def case_tree_paged(mod):
+    """tree_attn_with_paged_kv_cache_cpu: the tree occupies the trailing columns of each sequence's cached KV."""
+    rng = np.random.default_rng(26)
+    masks, lens, ip = _tree_arrays()
+    kv_lens = [x + extra for x, extra in zip(lens, (20, 200, 0))]
+    c, q, qi, kofs, qpos = _paged_case(rng, lens, kv_lens)
+    o, lse = _out(q.shape[0])
+    mod["tree_attn_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
+                                  _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, 0, 1.0, THETA, SM, _t(ip), _t(masks))
+    return dict(c=c, q=q, qi=qi, kofs=kofs, qpos=qpos, ip=ip, masks=masks), o.float().numpy(), lse.numpy()
+
+
+def _same(o, lse, wo, wl):
+    np.testing.assert_allclose(o, wo, atol=2e-3, rtol=1e-2)
+    np.testing.assert_allclose(lse, wl, atol=2e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("causal,rotary_mode", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_ref_paged_prefill_matches_oracle(causal, rotary_mode):
+    x, o, lse = case_paged_prefill(_need_ref(), causal, rotary_mode)
+    c = x["c"]
+    _same(o, lse, *ok.attention_prefill_paged(x["q"], x["qi"], c["pages"], c["page_indptr"], c["page_values"], c["length_info"],
+                                             x["kofs"], x["qpos"], causal, rotary_mode, 1.0, THETA, SM, "float16"))
 
 
 @pytest.mark.parametrize("rotary_mode", [0, 1])
 def test_ref_sliding_window_decode_and_prefill_match_oracle(rotary_mode):
     """The `_sliding_window` flavours: length_info [3, B] = (last_page_len, sliding_window_offset, sink_size)."""
     mod = _need_ref()
-    rng = np.random.default_rng(22)
-    kv_slots, sliding = [70, 300, 40], [(37, 4), (16, 16), (0, 0)]
-    c, q, qi, kofs, qpos = _paged_case(rng, [1, 1, 1], kv_slots, sliding)
-    qpos = (qpos - 1).astype(np.int32)   # decode: the query is the last visible token
-    o, lse = _out(3)
-    mod["batch_decode_paged_kv_sliding_window_cpu"](_t(q), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
-                                                    _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, rotary_mode, 1.0,
-                                                    THETA, SM)
-    wo, wl = ok.attention_decode(q, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
-                                 rotary_mode, 1.0, THETA, SM, "float16")
-    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
-    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
-    c, q, qi, kofs, qpos = _paged_case(rng, [5, 9, 2], kv_slots, sliding)
-    o, lse = _out(q.shape[0])
-    # emit_ref_kernels.py builds this flavour with the reference's default layer window (1024): wider than these caches
-    mod["batch_prefill_paged_kv_sliding_window_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]),
-                                                     _t(c["page_values"]), _t(c["length_info"]), _t(kofs), _t(qpos), o, lse,
-                                                     0, rotary_mode, 1.0, THETA, SM)
-    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
-                                        0, rotary_mode, 1.0, THETA, SM, "float16", sliding_window_size=1024)
-    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
-    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    x, o, lse = case_sliding_decode(mod, rotary_mode)
+    c = x["c"]
+    _same(o, lse, *ok.attention_decode(x["q"], c["pages"], c["page_indptr"], c["page_values"], c["length_info"], x["kofs"],
+                                      x["qpos"], rotary_mode, 1.0, THETA, SM, "float16"))
+    x, o, lse = case_sliding_prefill(mod, rotary_mode)
+    c = x["c"]
+    _same(o, lse, *ok.attention_prefill_paged(x["q"], x["qi"], c["pages"], c["page_indptr"], c["page_values"], c["length_info"],
+                                             x["kofs"], x["qpos"], 0, rotary_mode, 1.0, THETA, SM, "float16",
+                                             sliding_window_size=1024))
 
 
 def test_ref_tree_attention_matches_oracle():
-    """tree_attn_cpu (ragged, the new tokens among themselves) and tree_attn_with_paged_kv_cache_cpu (the tree occupies the
-    trailing columns of the cached KV), token trees given as (dfs order, subtree end) rows."""
-    from tests.util import rand16
-
     mod = _need_ref()
-    rng = np.random.default_rng(23)
-    trees = [[-1, 0, 0, 1], [(k - 1) // 2 if k else -1 for k in range(15)], [-1, 0, 1, -1, 3, 3, 0]]
-    masks = np.concatenate([_dfs_mask(t) for t in trees])
-    lens = [len(t) for t in trees]
-    ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    n = int(ip[-1])
-    q, k, v = (rand16(rng, (n, h, D), "float16") for h in (HQ, HKV, HKV))
-    qpos = np.concatenate([30 + np.arange(x) for x in lens]).astype(np.int32)
-    o, lse = _out(n)
-    mod["batch_tree_attn_cpu"](_t(q), _t(ip), _t(k), _t(v), _t(ip), _t(qpos), _t(ip), _t(masks), o, lse, 0, 1.0, THETA, SM)
-    wo, wl = ok.attention_prefill_ragged(q, ip, k, v, ip, qpos, None, 0, 0, 1.0, THETA, SM, "float16", mn_indptr=ip,
-                                         tree_mask=masks)
-    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
-    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
-    # paged: the cached KV of each sequence ends with its tree
-    kv_lens = [x + extra for x, extra in zip(lens, (20, 200, 0))]
-    c, q, qi, kofs, qpos = _paged_case(rng, lens, kv_lens)
-    o, lse = _out(n)
-    mod["tree_attn_paged_kv_cpu"](_t(q), _t(qi), _t(c["pages"]), _t(c["page_indptr"]), _t(c["page_values"]),
-                                  _t(c["length_info"]), _t(kofs), _t(qpos), o, lse, 0, 1.0, THETA, SM, _t(ip), _t(masks))
-    wo, wl = ok.attention_prefill_paged(q, qi, c["pages"], c["page_indptr"], c["page_values"], c["length_info"], kofs, qpos,
-                                        0, 0, 1.0, THETA, SM, "float16", tree_indptr=ip, tree_order=masks)
-    np.testing.assert_allclose(o.float().numpy(), wo, atol=2e-3, rtol=1e-2)
-    np.testing.assert_allclose(lse.numpy(), wl, atol=2e-3, rtol=1e-2)
+    x, o, lse = case_tree_ragged(mod)
+    _same(o, lse, *ok.attention_prefill_ragged(x["q"], x["ip"], x["k"], x["v"], x["ip"], x["qpos"], None, 0, 0, 1.0, THETA, SM,
+                                              "float16", mn_indptr=x["ip"], tree_mask=x["masks"]))
+    x, o, lse = case_tree_paged(mod)
+    c = x["c"]
+    _same(o, lse, *ok.attention_prefill_paged(x["q"], x["qi"], c["pages"], c["page_indptr"], c["page_values"], c["length_info"],
+                                             x["kofs"], x["qpos"], 0, 0, 1.0, THETA, SM, "float16", tree_indptr=x["ip"],
+                                             tree_order=x["masks"]))
 
 
 def test_ref_empty_and_boundary_lengths_match_oracle():
