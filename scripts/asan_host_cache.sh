@@ -4,6 +4,8 @@
 # planning-only caches and then runs 240 random programs (scripts/asan_fuzz_host_cache.py).  libstdc++ is preloaded next
 # to libasan so that ASan's __cxa_throw interceptor finds the real function inside a Python process.
 # Round 1 result: 36 tests + 240 programs, no report.  Remove tvm_b200/lib/*_asan* afterwards.
+# The same recipe with TVMB200_LIB_SUFFIX=_ubsan, -fsanitize=undefined -fno-sanitize-recover=undefined and libubsan preloaded
+# (UndefinedBehaviorSanitizer) was run as well: no report either.
 set -e
 cd "$(dirname "$0")/.."
 export TVMB200_LIB_SUFFIX=_asan
