@@ -17,4 +17,6 @@ export ASAN_OPTIONS=detect_leaks=0:halt_on_error=1:log_path=/tmp/asan_report
 rm -f /tmp/asan_report*
 LD_PRELOAD="$ASAN $STD" python -m pytest tests/test_host_cache_golden.py tests/test_zz_fuzz_gpu.py -q -m "not gpu" -x -s -p no:cacheprovider
 LD_PRELOAD="$ASAN $STD" PYTHONPATH=oracle/ref_harness python scripts/asan_fuzz_host_cache.py
+# the tvm-ffi boundary (argument marshalling of the packed functions and of the vm.builtin entries), CPU part
+LD_PRELOAD="$ASAN $STD" python -m pytest tests/test_library_symbols.py tests/test_vm_builtins.py tests/test_rope_variant_angle.py -q -m "not gpu" -s -p no:cacheprovider
 ls /tmp/asan_report* 2>/dev/null && { echo "ASan reports found"; exit 1; } || echo "no ASan report"
