@@ -140,3 +140,28 @@ def test_limits_and_preconditions_like_the_reference(built_lib):
         m.attention_with_shared_kv(2, 1.0, 5, None, None, None)
     m.self_attention(1, 1.0, 5, None, None, None, None)
     m.end_forward()
+
+
+def test_batch_beyond_reserved_num_seqs_is_refused_not_overrun(built_lib):
+    """The merged aux buffer is sized for reserved_num_seqs sequences (as the reference's is, attn_utils.h:817-1052): a batch
+    that needs more is a loud error, checked before every write into the staging buffer."""
+    from tvm_b200 import capi
+
+    for sliding in (False, True):
+        c = _plan_cache(reserved_num_seqs=1, total_token_capacity=4800, prefill_chunk_size=300, num_layers=1,
+                        support_sliding_window=sliding, rope_mode=2)
+        for i in range(300):
+            c.add_sequence(i)
+        with pytest.raises(capi.TvmB200Error, match="auxiliary buffer overflow"):
+            c.begin_forward(list(range(300)), [1] * 300)
+        with pytest.raises(capi.TvmB200Error, match="did not complete"):
+            c.attention_with_fused_qkv(0, 1.0, None, None)
+        c.begin_forward([0], [1])           # the cache stays usable
+        c.attention_with_fused_qkv(0, 1.0, None, None)
+        c.end_forward()
+    ok_ = _plan_cache(reserved_num_seqs=300, total_token_capacity=4800, prefill_chunk_size=300, num_layers=1)
+    for i in range(300):
+        ok_.add_sequence(i)
+    ok_.begin_forward(list(range(300)), [1] * 300)
+    ok_.attention_with_fused_qkv(0, 1.0, None, None)
+    ok_.end_forward()

@@ -268,8 +268,16 @@ class Cache {
                               const std::vector<std::vector<int32_t>>& trailing);
   void CopySinglePage(int32_t src, int32_t tgt, int64_t len);
   void CompactKVCopy();
+  // the staging buffer is sized for reserved_num_seqs sequences (like the reference's merged aux buffer,
+  // attn_utils.h:817-1052); a batch beyond that is refused before anything is written past its end
+  void StageRoom(int64_t n) const {
+    HCHECK(stage_off_ + (n + 3) / 4 * 4 <= static_cast<int64_t>(stage_.size()),
+           "auxiliary buffer overflow: the batch needs more than the %ld int32 reserved for reserved_num_seqs = %ld",
+           (long)stage_.size(), (long)reserved_seqs_);
+  }
   View Put(const IVec& v) {
     View r;
+    StageRoom(static_cast<int64_t>(v.size()));
     r.offset = stage_off_;
     r.size = static_cast<int64_t>(v.size());
     if (!v.empty()) std::memcpy(stage_.data() + stage_off_, v.data(), v.size() * 4);
@@ -279,6 +287,7 @@ class Cache {
   View Put3(const IVec& a, const IVec& b, const IVec& c) {
     View r;
     const int64_t n = static_cast<int64_t>(a.size());
+    StageRoom(3 * n);
     r.offset = stage_off_;
     r.size = 3 * n;
     r.rows = 3;
