@@ -1,7 +1,16 @@
+"""Random programs on planning-only host caches (no GPU, no reference): the loop of tests/test_zz_fuzz_gpu.py::_run for 40
+seeds x 6 generators.  Meant to run with a sanitizer-instrumented library (scripts/asan_host_cache.sh); it also checks, via the
+NaN-initialised oracle pages, that no plan reads a slot nobody appended to."""
 import sys
-sys.path.insert(0, "/root/repo")
-import tests.test_zz_fuzz_gpu as T
-import gen_golden as gg
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle" / "ref_harness"))
+
+import gen_golden as gg  # noqa: E402
+import tests.test_zz_fuzz_gpu as T  # noqa: E402
+
 T.CASES += [("deep_popn", lambda s: gg.prog_random(s, deep_popn=True), dict(rope_mode=1)),
             ("tree_forks", lambda s: gg.prog_random_tree(s, forks=True), dict(rope_mode=0))]
 n = 0
@@ -10,9 +19,7 @@ for seed in range(30000, 30040):
         try:
             T._run(kind, seed, None)
         except AssertionError as e:
-            if "unwritten" in str(e) or "n_fwd" in str(e) or not str(e):
-                pass   # layer-sliding NaN rows of the oracle / short programs: not a host matter
-            else:
+            if str(e):          # a bare `assert n_fwd > 10 ...` (a short program) is not a host matter
                 raise
         n += 1
-print("asan fuzz ok:", n, "programs")
+print("sanitizer fuzz ok:", n, "programs")
