@@ -8,11 +8,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle" / "ref_harness"))
 
-import gen_golden as gg  # noqa: E402
 import tests.test_zz_fuzz_gpu as T  # noqa: E402
 
-T.CASES += [("deep_popn", lambda s: gg.prog_random(s, deep_popn=True), dict(rope_mode=1)),
-            ("tree_forks", lambda s: gg.prog_random_tree(s, forks=True), dict(rope_mode=0))]
 n = 0
 for seed in range(30000, 30040):
     for kind in [c[0] for c in T.CASES]:
