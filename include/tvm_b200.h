@@ -52,10 +52,33 @@ TVMB200_API const char* tvmb200_version(void);
 TVMB200_API int64_t tvmb200_launch_count(void);
 
 /*!
- * \brief Pre-size the per-device split-KV workspace (partial O / LSE).  Optional: the workspace grows
- *        on demand, but growing calls cudaMalloc, which must not happen inside CUDA-graph capture.
+ * \brief Kernel-set context = what the reference compiles INTO one set of PrimFuncs (the `rope_scaling` dict, the
+ *  rotary_dim / theta / scale of fused_rope, `layer_sliding_window_size`; kv_cache.py:690-736) plus the device scratch
+ *  the launches need (split-KV partials, the work counter of the persistent prefill kernel, the block ticket of the
+ *  peer gather), keyed by (device, stream).  The reference builds one kernel set per model; here a process holds
+ *    - one DEFAULT context, used by every entry point below and by the `__tvm_ffi_*` module symbols,
+ *    - one context per host cache (tvm_b200_cache.h), created from the settings current at its creation,
+ *    - any number made with tvmb200_context_create (tvm-ffi closures bound to one: `bind_context`).
+ *  tvmb200_context_enter(c) makes `c` the calling thread's current context -- the setters below and every launch on
+ *  this thread then use it -- and returns the previous one (NULL = default); pass that back to leave the scope.
+ *  Launches of different contexts, or of one context on different streams, never share scratch, so they may run
+ *  concurrently on one device.  A new context copies the settings of the creator's current one.
+ */
+typedef struct tvmb200_context_s* tvmb200_context_t;
+TVMB200_API int tvmb200_context_create(tvmb200_context_t* out);
+TVMB200_API void tvmb200_context_retain(tvmb200_context_t c);
+/*! \brief drops one reference; the last one frees the context's device scratch. */
+TVMB200_API void tvmb200_context_release(tvmb200_context_t c);
+TVMB200_API tvmb200_context_t tvmb200_context_enter(tvmb200_context_t c);
+
+/*!
+ * \brief Pre-size the split-KV workspace (partial O / LSE) of the current context for launches on (device, stream);
+ *        tvmb200_reserve_workspace = the NULL stream.  Optional: the workspace starts at 32 MiB, which covers every
+ *        decode shape up to batch 256 x 64 heads, and grows on demand, but growing calls cudaMalloc, which must not
+ *        happen inside CUDA-graph capture.
  */
 TVMB200_API int tvmb200_reserve_workspace(int device_id, int64_t bytes);
+TVMB200_API int tvmb200_reserve_workspace_stream(int device_id, int64_t bytes, tvmb200_stream_t stream);
 
 /*!
  * \brief Per-layer sliding window size compiled into the reference's `*_sliding_window` prefill
@@ -67,7 +90,8 @@ TVMB200_API void tvmb200_set_layer_sliding_window_size(int32_t size);
 /*!
  * \brief RoPE frequency scaling the reference compiles into every PrimFunc that rotates (`rope_scaling` dict ->
  *  switch_rope_freq_func, position_embedding.py:257-299: fused_rope and the inline-RoPE paths of the attention kernels,
- *  _kernel_common.py:115-127).  A loaded library needs it as state, for every call made afterwards in this process:
+ *  _kernel_common.py:115-127).  A loaded library needs it as state of the calling thread's current context (the
+ *  default context unless tvmb200_context_enter was used), for every call made afterwards with that context:
  *    TVMB200_ROPE_SCALING_NONE   rope_freq_default
  *    TVMB200_ROPE_SCALING_LLAMA3 rope_freq_llama3 (position_embedding.py:130-160; Llama-3.1: factor 8, low 1, high 4,
  *                                original_max_position_embeddings 8192) -- tvmb200_split_rotary[_append], rotary_mode = 1

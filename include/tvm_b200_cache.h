@@ -63,7 +63,8 @@ TVMB200_API int tvmb200_cache_remove_sequence(tvmb200_cache_t c, int64_t seq_id)
 TVMB200_API int tvmb200_cache_fork_sequence(tvmb200_cache_t c, int64_t parent_seq_id, int64_t child_seq_id, int64_t fork_pos);
 TVMB200_API int tvmb200_cache_popn(tvmb200_cache_t c, int64_t seq_id, int32_t n);
 /*! \brief token_tree_parent_ptr may be NULL (no tree); otherwise it has sum(append_lengths) entries.  When the call
- *  fails (unknown sequence, cache full, invalid tree) there is no current batch: the attention entries,
+ *  fails (unknown sequence, cache full, invalid tree, empty batch) the cache is left exactly as it was before the call
+ *  (sequence lengths, pages, free-page stack) and there is no current batch: the attention entries,
  *  commit_accepted_token_tree_nodes and get_query_positions return an error until a begin_forward completes. */
 TVMB200_API int tvmb200_cache_begin_forward(tvmb200_cache_t c, const int64_t* seq_ids, const int64_t* append_lengths,
                                             int32_t batch_size, const int64_t* token_tree_parent_ptr, int32_t tree_size);
@@ -139,6 +140,12 @@ TVMB200_API int tvmb200_cache_debug_get_kv(tvmb200_cache_t c, int64_t seq_id, in
 TVMB200_API int tvmb200_register_vm_builtins(int allow_override);
 
 /* ---- introspection (parity tests, integration glue) ---- */
+/*! \brief out6 = {num_qo_heads, num_kv_heads, head_dim, dtype, num_layers, layer_id_begin_offset}. */
+TVMB200_API int tvmb200_cache_shape(tvmb200_cache_t c, int64_t* out6);
+/*! \brief The cache's own kernel-set context (borrowed; valid while the cache lives).  It starts as a copy of the
+ *  settings current at tvmb200_cache_create; tvmb200_context_enter(ctx) + tvmb200_set_rope_scaling(...) changes
+ *  them for this cache only. */
+TVMB200_API int tvmb200_cache_context(tvmb200_cache_t c, tvmb200_context_t* out);
 /*! \brief device pointer of pages_[local_layer]: [num_total_pages, 2, Hkv, page, D]. */
 TVMB200_API int tvmb200_cache_pages(tvmb200_cache_t c, int64_t local_layer, void** dev_ptr, int64_t* num_total_pages);
 /*! \brief Start (1) / stop (0) recording the callback sequence with every int32 array and scalar argument. */

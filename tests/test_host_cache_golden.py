@@ -144,24 +144,90 @@ def test_limits_and_preconditions_like_the_reference(built_lib):
 
 def test_batch_beyond_reserved_num_seqs_is_refused_not_overrun(built_lib):
     """The merged aux buffer is sized for reserved_num_seqs sequences (as the reference's is, attn_utils.h:817-1052): a batch
-    that needs more is a loud error, checked before every write into the staging buffer."""
+    that needs more is a loud error, checked before every write into the staging buffer, and -- begin_forward being
+    transactional -- the refused batch leaves lengths and free pages untouched."""
     from tvm_b200 import capi
 
+    N = 1200
     for sliding in (False, True):
-        c = _plan_cache(reserved_num_seqs=1, total_token_capacity=4800, prefill_chunk_size=300, num_layers=1,
+        c = _plan_cache(reserved_num_seqs=1, total_token_capacity=16 * N, prefill_chunk_size=N, num_layers=1,
                         support_sliding_window=sliding, rope_mode=2)
-        for i in range(300):
+        for i in range(N):
             c.add_sequence(i)
+        free0 = c.get_num_available_pages()
         with pytest.raises(capi.TvmB200Error, match="auxiliary buffer overflow"):
-            c.begin_forward(list(range(300)), [1] * 300)
+            c.begin_forward(list(range(N)), [1] * N)
+        assert c.get_total_sequence_length() == 0 and c.get_num_available_pages() == free0
         with pytest.raises(capi.TvmB200Error, match="did not complete"):
             c.attention_with_fused_qkv(0, 1.0, None, None)
         c.begin_forward([0], [1])           # the cache stays usable
         c.attention_with_fused_qkv(0, 1.0, None, None)
         c.end_forward()
-    ok_ = _plan_cache(reserved_num_seqs=300, total_token_capacity=4800, prefill_chunk_size=300, num_layers=1)
-    for i in range(300):
+    ok_ = _plan_cache(reserved_num_seqs=N, total_token_capacity=16 * N, prefill_chunk_size=N, num_layers=1)
+    for i in range(N):
         ok_.add_sequence(i)
-    ok_.begin_forward(list(range(300)), [1] * 300)
+    ok_.begin_forward(list(range(N)), [1] * N)
     ok_.attention_with_fused_qkv(0, 1.0, None, None)
     ok_.end_forward()
+
+
+def test_full_prefill_chunk_is_accepted(built_lib):
+    """a batch with total_append == prefill_chunk_size must fit the merged aux buffer (the two
+    kv-transfer regions BuildAuxViews skips are budgeted too)."""
+    for chunk in (512, 8192):
+        c = _plan_cache(reserved_num_seqs=4, total_token_capacity=32768, prefill_chunk_size=chunk, num_layers=1)
+        c.add_sequence(0)
+        c.begin_forward([0], [chunk])
+        c.attention_with_fused_qkv(0, 1.0, None, None)
+        c.end_forward()
+        assert c.get_total_sequence_length() == chunk
+        c.add_sequence(1)
+        c.add_sequence(2)
+        c.begin_forward([1, 2], [chunk // 2, chunk - chunk // 2])
+        c.attention_with_fused_qkv(0, 1.0, None, None)
+        c.end_forward()
+
+
+def test_failed_begin_forward_rolls_back(built_lib):
+    """a begin_forward that throws leaves sequence lengths, block lengths and the free-page stack
+    exactly as they were; popn / remove / fork afterwards behave as if the call had never happened."""
+    from tvm_b200 import capi
+
+    E = capi.TvmB200Error
+    for sliding in (False, True):
+        c = _plan_cache(reserved_num_seqs=4, total_token_capacity=64, prefill_chunk_size=64, num_layers=1,
+                        support_sliding_window=sliding, rope_mode=2 if sliding else 1)
+        twin = _plan_cache(reserved_num_seqs=4, total_token_capacity=64, prefill_chunk_size=64, num_layers=1,
+                           support_sliding_window=sliding, rope_mode=2 if sliding else 1)
+        for m in (c, twin):
+            m.add_sequence(0)
+            m.add_sequence(1)
+            m.begin_forward([0, 1], [20, 30])
+            m.attention_with_fused_qkv(0, 1.0, None, None)
+            m.end_forward()
+        state0 = (c.get_total_sequence_length(), c.get_num_available_pages())
+        with pytest.raises(E, match="cannot be found"):      # seq 0 would have been lengthened before seq 7 is looked up
+            c.begin_forward([0, 7], [3, 3])
+        assert (c.get_total_sequence_length(), c.get_num_available_pages()) == state0
+        with pytest.raises(E, match="full|prefill_chunk_size|No page"):  # seq 0 gets pages, seq 1 cannot
+            c.begin_forward([0, 1], [10, 60])
+        assert (c.get_total_sequence_length(), c.get_num_available_pages()) == state0
+        with pytest.raises(E, match="empty"):
+            c.begin_forward([], [])
+        with pytest.raises(E, match="Invalid token tree|does not support"):
+            c.begin_forward([0, 1], [2, 2], [-1, 0, -1, 5])
+        assert (c.get_total_sequence_length(), c.get_num_available_pages()) == state0
+        # from here on both caches must plan identically
+        for m in (c, twin):
+            m.set_trace(True)
+            m.fork_sequence(0, 2, 17)
+            m.begin_forward([0, 2, 1], [1, 2, 1])
+            m.attention_with_fused_qkv(0, 1.0, None, None)
+            m.end_forward()
+            m.popn(1, 5)
+            m.remove_sequence(0)
+            m.begin_forward([2, 1], [1, 1])
+            m.attention_with_fused_qkv(0, 1.0, None, None)
+            m.end_forward()
+        assert c.take_trace() == twin.take_trace()
+        assert c.get_num_available_pages() == twin.get_num_available_pages()

@@ -85,3 +85,60 @@ def test_packed_functions_validate_like_the_tir_binders(built_lib):
     for exc, fragment, name, args in cases:
         with pytest.raises(exc, match=re.escape(fragment)):
             m[name](*args)
+
+
+LLAMA31 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+           "original_max_position_embeddings": 8192}
+
+
+def test_contexts_keep_their_own_rope_scaling(built_lib):
+    """A kernel-set context carries what the reference compiles into one set of PrimFuncs (include/tvm_b200.h): the
+    setters act on the calling thread's current context; a host cache snapshots the settings current at its creation."""
+    from tvm_b200 import capi
+    from tvm_b200.kv_cache import PagedKVCache
+
+    L = capi.lib()
+    kind = lambda: int(L.tvmb200_get_rope_scaling_kind())  # noqa: E731
+    capi.set_rope_scaling(None)
+    ctx = capi.Context()
+    with ctx:
+        capi.set_rope_scaling(LLAMA31)
+        assert kind() == 1
+        inner = capi.Context()            # a new context copies its creator's current settings
+    assert kind() == 0                    # the default context never saw it
+    with inner:
+        assert kind() == 1
+    try:
+        capi.set_rope_scaling({"rope_type": "gptj"})
+        cache = PagedKVCache(reserved_num_seqs=2, total_token_capacity=64, prefill_chunk_size=16, num_layers=1,
+                             num_qo_heads=4, num_kv_heads=1, head_dim=128, device=None)
+    finally:
+        capi.set_rope_scaling(None)
+    with cache.context():
+        assert kind() == 2                # the cache kept the scaling that was current when it was created
+        capi.set_rope_scaling(LLAMA31)    # ... and can be given its own
+    with cache.context():
+        assert kind() == 1
+    assert kind() == 0
+
+
+def test_kernel_set_binds_packed_functions_to_a_context(built_lib):
+    import torch
+
+    from tvm_b200 import ffi
+
+    a = ffi.KernelSet(rope_theta=5e5, rope_scaling=LLAMA31)
+    b = ffi.KernelSet()
+    assert set(a.callbacks()) == set(ffi.CALLBACKS)
+    with pytest.raises(ValueError, match="exports no packed function"):
+        a["f_no_such_thing"]
+    with pytest.raises(Exception, match="not supported"):
+        ffi.KernelSet(rope_scaling={"rope_type": "longrope"})
+    # bound functions validate exactly like the module symbols
+    with pytest.raises(TypeError, match="expects 4 arguments, got 1"):
+        b["f_transpose_append"](torch.zeros(1))
+    if not torch.cuda.is_available():
+        f16 = lambda *s: torch.zeros(s, dtype=torch.float16)  # noqa: E731
+        with pytest.raises(ValueError, match="no CPU fallback"):
+            a["f_split_rotary"](f16(2, 6, 128), torch.zeros(2, dtype=torch.int32), f16(2, 4, 128), f16(2, 1, 128), f16(2, 1, 128), 1)
+    del a, b  # releases the contexts (last reference frees their scratch)

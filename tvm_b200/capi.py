@@ -46,6 +46,14 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_version.restype = c_char_p
     L.tvmb200_launch_count.restype = c_int64
     L.tvmb200_reserve_workspace.argtypes = [c_int, c_int64]
+    L.tvmb200_reserve_workspace_stream.argtypes = [c_int, c_int64, c_void_p]
+    L.tvmb200_context_create.argtypes = [ctypes.POINTER(c_void_p)]
+    L.tvmb200_context_retain.argtypes = [c_void_p]
+    L.tvmb200_context_retain.restype = None
+    L.tvmb200_context_release.argtypes = [c_void_p]
+    L.tvmb200_context_release.restype = None
+    L.tvmb200_context_enter.argtypes = [c_void_p]
+    L.tvmb200_context_enter.restype = c_void_p
     L.tvmb200_set_layer_sliding_window_size.argtypes = [c_int32]
     L.tvmb200_set_layer_sliding_window_size.restype = None
     L.tvmb200_set_prefill_impl.argtypes = [c_int]
@@ -82,6 +90,33 @@ def lib() -> ctypes.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise TvmB200Error(lib().tvmb200_last_error().decode())
+
+
+class Context:
+    """A kernel-set context of include/tvm_b200.h (rope scaling, layer window, device scratch).  `with ctx:` makes it
+    the calling thread's current context: setters and launches inside the block use it."""
+
+    def __init__(self, handle=None, owned=True):
+        if handle is None:
+            h = c_void_p()
+            _check(lib().tvmb200_context_create(ctypes.byref(h)))
+            handle = h.value
+        self.handle, self._owned, self._prev = handle, owned, []
+
+    def __enter__(self):
+        self._prev.append(lib().tvmb200_context_enter(c_void_p(self.handle)))
+        return self
+
+    def __exit__(self, *exc):
+        lib().tvmb200_context_enter(c_void_p(self._prev.pop()))
+        return False
+
+    def __del__(self):
+        if self._owned and self.handle:
+            try:
+                lib().tvmb200_context_release(c_void_p(self.handle))
+            except Exception:  # interpreter shutdown
+                pass
 
 
 def set_prefill_impl(impl: int) -> None:

@@ -10,7 +10,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/tvm_b200.h"
 
@@ -45,8 +48,10 @@ extern std::atomic<int64_t> g_launch_count;
 
 int num_sms();  // SM count of the current device (cached)
 
-// per-device scratch used by split-KV decode (partial O / LSE / chunk offsets)
-int get_workspace(int64_t bytes, void** out);
+// scratch of the current context for launches on (current device, stream): split-KV partials (O / LSE / chunk
+// offsets) and two zeroed int32 counters ([0] prefill work queue, [64] peer-gather ticket); see Context below
+int get_workspace(int64_t bytes, cudaStream_t st, void** out);
+int get_counters(cudaStream_t st, int32_t** out);
 int32_t layer_sliding_window_size();
 
 // TMA tensor maps (decode.cu): 2-D [rows][cols] with box [box_rows][64], cached by (base, shape); 3-D uncached
@@ -249,7 +254,7 @@ struct RopeScaling {
   int kind;
   float inv_factor, alpha, beta;  // llama3: 1/factor, orig_max_pos / (2 pi (high - low)), low / (high - low)
 };
-RopeScaling rope_scaling();  // current process-wide setting (core.cu)
+RopeScaling rope_scaling();  // setting of the calling thread's current context (core.cu)
 
 // The denominator the rotation angle is divided by: freq = pos * scale / rope_denominator(d).
 //   default: theta^((2d mod rd)/rd)                                  (position_embedding.py:63)
@@ -278,7 +283,8 @@ struct RopeVariant {
   //         become (low, high - low) of the correction range for the launch's rotary_dim and theta
   float inv_theta_log_scale;  // yarn; 0 = 1 / (2 ln theta) taken at launch (kv_cache.py:355-366)
 };
-RopeVariant rope_variant();  // current process-wide setting (core.cu)
+RopeVariant rope_variant();  // setting of the calling thread's current context (core.cu)
+
 int check_no_rope_variant(const char* who);  // error (non-zero) when a variant is active (core.cu)
 
 // host: the stored form of kind 2 / 3 from the numbers of the reference's rope_scaling dict (llama3-style arguments)
@@ -367,5 +373,37 @@ __device__ __forceinline__ void block_exclusive_scan(int* s, int n, int* tmp) {
   if (tid == 0) s[n] = tmp[32];
   __syncthreads();
 }
+
+// What the reference compiles into one kernel set + the device scratch its launches need (core.cu).
+struct Context {
+  struct Scratch {
+    void* ws = nullptr;
+    int64_t ws_bytes = 0;
+    int32_t* counters = nullptr;
+  };
+  std::mutex mu_;
+  RopeScaling rs = {0, 1.0f, 0.0f, 0.0f};
+  RopeVariant rv = {0, 0.f, 0.f, 0.f, 0.f, 0.f};
+  std::atomic<int32_t> layer_sws{1024};
+  // what the 6-argument (reference) form of fused_rope uses (position_embedding.py:444-452 bakes them in)
+  float rope_theta = 10000.0f, rope_scale = 1.0f;
+  int rotary_dim = 0;
+  std::map<std::pair<int, uintptr_t>, Scratch> scratch_;  // (device, stream) -> scratch
+  std::atomic<int> refs{1};
+  ~Context();
+};
+Context* default_context();
+Context* current_context();                  // the scope entered on this thread, else the default context
+Context* enter_context(Context* c);          // returns the previous scope (nullptr = default); not RAII
+struct ContextScope {
+  explicit ContextScope(Context* c);
+  ~ContextScope();
+  Context* prev_;
+};
+int context_set_rope_scaling(Context* c, int32_t kind, float factor, float low_freq_factor, float high_freq_factor,
+                             float original_max_position_embeddings);
+int context_set_rope_scaling_yarn(Context* c, float factor, float original_max_position_embeddings, float beta_fast,
+                                  float beta_slow, float inv_theta_log_scale);
+void context_copy_settings(Context* dst, Context* src);
 
 }  // namespace tvmb200

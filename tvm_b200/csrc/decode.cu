@@ -773,7 +773,7 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   const int64_t lse_bytes = (max_chunks * num_qo_heads * 4 + 255) / 256 * 256;
   const int64_t o_bytes = max_chunks * num_qo_heads * head_dim * 4;
   void* ws = nullptr;
-  if (int rc = get_workspace(off_bytes + lse_bytes + o_bytes, &ws)) return rc;
+  if (int rc = get_workspace(off_bytes + lse_bytes + o_bytes, st, &ws)) return rc;
 
   DecodeParams p;
   p.q = q;
@@ -854,23 +854,8 @@ extern "C" int tvmb200_attention_decode_fused_qkv(const void* qkv, const int32_t
                       rope_scale, rope_theta, sm_scale, dtype, stream, pg, qkv, append_position_map, apply_rope > 0 ? 1 : 0);
 }
 
-static int get_done_counter(int32_t** out) {
-  static int32_t* counters[64];
-  static std::mutex mu;
-  int dev = 0;
-  TVMB200_CUDA(cudaGetDevice(&dev));
-  TVMB200_CHECK(dev >= 0 && dev < 64, "device id %d out of range", dev);
-  std::lock_guard<std::mutex> lk(mu);
-  if (!counters[dev]) {
-    TVMB200_CUDA(cudaMalloc(&counters[dev], 256));
-    TVMB200_CUDA(cudaMemset(counters[dev], 0, 256));
-  }
-  *out = counters[dev];
-  return 0;
-}
-
 static int fill_peer_gather(PeerGather* pg, void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
-                            int32_t rank, uint32_t epoch, int32_t num_qo_heads) {
+                            int32_t rank, uint32_t epoch, int32_t num_qo_heads, tvmb200_stream_t stream) {
   TVMB200_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "attention_decode_gather: world %d / rank %d (1..8 ranks of one box)", world, rank);
   TVMB200_CHECK(peer_outputs != nullptr && peer_flags != nullptr, "attention_decode_gather: peer pointer arrays are null");
   pg->n = world;
@@ -883,7 +868,11 @@ static int fill_peer_gather(PeerGather* pg, void* const* peer_outputs, uint32_t*
     pg->out[i] = peer_outputs[i];
     pg->flags[i] = peer_flags[i];
   }
-  return get_done_counter(&pg->done);
+  // block ticket of this (context, device, stream): zero between launches
+  int32_t* counters = nullptr;
+  if (int rc = get_counters(static_cast<cudaStream_t>(stream), &counters)) return rc;
+  pg->done = counters + 64;
+  return 0;
 }
 
 extern "C" int tvmb200_attention_decode_gather(const void* q, const void* pages, const int32_t* page_indptr,
@@ -896,7 +885,7 @@ extern "C" int tvmb200_attention_decode_gather(const void* q, const void* pages,
                                                void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
                                                int32_t rank, uint32_t epoch, tvmb200_stream_t stream) {
   PeerGather pg = {};
-  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads)) return rc;
+  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads, stream)) return rc;
   if (batch_size <= 0) return 0;
   return decode_entry(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
                       batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window,
@@ -914,7 +903,7 @@ extern "C" int tvmb200_attention_decode_fused_qkv_gather(
   TVMB200_CHECK(qkv != nullptr && append_position_map != nullptr && pages != nullptr, "attention_decode_fused_qkv_gather: null argument");
   TVMB200_CHECK(!sliding_window, "attention_decode_fused_qkv_gather: per-sequence sliding windows append after the attention; use the separate calls");
   PeerGather pg = {};
-  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads)) return rc;
+  if (int rc = fill_peer_gather(&pg, peer_outputs, peer_flags, world, rank, epoch, num_qo_heads, stream)) return rc;
   if (batch_size <= 0) return 0;
   return decode_entry(nullptr, pages, page_indptr, page_values, length_info, k_rope_pos_offset, q_rope_position, output, lse,
                       batch_size, nnz_pages, num_pages, num_qo_heads, num_kv_heads, page_size, head_dim, sliding_window, 0,

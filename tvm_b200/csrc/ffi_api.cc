@@ -17,15 +17,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tvm_b200.h"
 #include "../../include/tvm_b200_cache.h"
-
-namespace tvmb200 {
-int32_t layer_sliding_window_size();
-}
+#include "common.cuh"
 
 namespace {
 
@@ -108,6 +108,17 @@ double arg_float(const TVMFFIAny* args, int i, const char* fn, const char* name)
   if (a.type_index == kTVMFFIFloat) return a.v_float64;
   if (a.type_index == kTVMFFIInt || a.type_index == kTVMFFIBool) return static_cast<double>(a.v_int64);
   throw Err{"TypeError", fmt("%s: argument %d (%s) must be a float, got type index %d", fn, i, name, a.type_index)};
+}
+
+std::string arg_str(const TVMFFIAny* args, int i, const char* fn, const char* name) {
+  const TVMFFIAny& a = args[i];
+  if (a.type_index == kTVMFFIRawStr) return a.v_c_str;
+  if (a.type_index == kTVMFFISmallStr) return std::string(a.v_bytes, a.small_str_len);
+  if (a.type_index == kTVMFFIStr) {
+    const TVMFFIByteArray* b = TVMFFIBytesGetByteArrayPtr(a.v_obj);
+    return std::string(b->data, b->size);
+  }
+  throw Err{"TypeError", fmt("%s: argument %d (%s) must be a string, got type index %d", fn, i, name, a.type_index)};
 }
 
 void expect_nargs(int got, int want, const char* fn) {
@@ -285,17 +296,16 @@ int impl_compact_kv_copy(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   TVMB200_FFI_END();
 }
 
-// (qkv, position_map, q, k, v, apply_rope)     rope theta/scale are module state (see set_rope_params)
-float g_rope_theta = 10000.0f, g_rope_scale = 1.0f;
-int g_rotary_dim = 0;
+// (qkv, position_map, q, k, v, apply_rope)     rope theta/scale/rotary_dim are context state (see set_rope_params)
 int impl_fused_rope(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   static const char* fn = "fused_rope";
   TVMB200_FFI_BEGIN();
   // 6 arguments = the reference signature (theta/scale/rotary_dim from module state);
   // 9 arguments = explicit (..., apply_rope, rope_theta, rope_scale, rotary_dim) used by our own host
   if (n != 6 && n != 9) throw Err{"TypeError", fmt("%s expects 6 (or 9) arguments, got %d", fn, n)};
-  float theta = g_rope_theta, scale = g_rope_scale;
-  int rotary_dim = g_rotary_dim;
+  tvmb200::Context* ctx = tvmb200::current_context();
+  float theta = ctx->rope_theta, scale = ctx->rope_scale;
+  int rotary_dim = ctx->rotary_dim;
   if (n == 9) {
     theta = static_cast<float>(arg_float(args, 6, fn, "rope_theta"));
     scale = static_cast<float>(arg_float(args, 7, fn, "rope_scale"));
@@ -331,14 +341,15 @@ int impl_fused_rope(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
 }
 
 // (theta, scale[, rotary_dim]) -- the reference bakes these into the fused_rope PrimFunc when it is
-// built (position_embedding.py:444-452); a loaded .so needs them as state.
+// built (position_embedding.py:444-452); a loaded .so needs them as state of the (current / bound) context.
 int impl_set_rope_params(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   static const char* fn = "set_rope_params";
   TVMB200_FFI_BEGIN();
   if (n != 2 && n != 3) throw Err{"TypeError", "set_rope_params expects (theta, scale[, rotary_dim])"};
-  g_rope_theta = static_cast<float>(arg_float(args, 0, fn, "theta"));
-  g_rope_scale = static_cast<float>(arg_float(args, 1, fn, "scale"));
-  g_rotary_dim = n == 3 ? static_cast<int>(arg_int(args, 2, fn, "rotary_dim")) : 0;
+  tvmb200::Context* ctx = tvmb200::current_context();
+  ctx->rope_theta = static_cast<float>(arg_float(args, 0, fn, "theta"));
+  ctx->rope_scale = static_cast<float>(arg_float(args, 1, fn, "scale"));
+  ctx->rotary_dim = n == 3 ? static_cast<int>(arg_int(args, 2, fn, "rotary_dim")) : 0;
   TVMB200_FFI_END();
 }
 
@@ -637,15 +648,41 @@ int impl_launch_count(const TVMFFIAny*, int32_t, TVMFFIAny* result) {
 // `vm.builtin.paged_attention_kv_cache_create` and the `vm.builtin.kv_state_*` / `attention_kv_cache_*` functions BY
 // NAME (src/runtime/vm/kv_state.cc:33-116, paged_kv_cache.cc:2535-2639; callers python/tvm/relax/frontend/nn/llm/
 // kv_cache.py:124-351); register_vm_builtins() re-registers those names onto tvm_b200's cache (kv_cache_host.cc), so the
-// unmodified model runs on the sm_100a kernels.  The cache travels through the VM registers as an opaque pointer; the
-// callback arguments of the constructor (13..27) are accepted and ignored.  Unsupported entries (MLA, disaggregation) are
-// registered too and raise.
+// unmodified model runs on the sm_100a kernels.  The cache travels through the VM registers as a ref-counted ffi object
+// (destroyed with its last reference); the callback arguments of the constructor (13..27) are accepted and ignored.
+// Unsupported entries (MLA, disaggregation) are registered too and raise.
 // =====================================================================================================
+// The cache travels through the VM registers as a tvm-ffi Function object whose resource handle is the cache and
+// whose deleter destroys it -- a ref-counted ffi Object, like the reference's PagedAttentionKVCacheObj, made with
+// nothing but the tvm-ffi C API.  Live handles are kept in a table (object -> cache), so any other Function passed
+// where a cache is expected is refused.  A raw opaque pointer (the C ABI's tvmb200_cache_t) is accepted as well.
+std::mutex g_handles_mu;
+std::unordered_map<void*, tvmb200_cache_t> g_handles;
+
+int cache_handle_call(void* self, const TVMFFIAny*, int32_t, TVMFFIAny* result) {
+  result->type_index = kTVMFFIOpaquePtr;  // calling the handle returns the raw tvmb200_cache_t
+  result->zero_padding = 0;
+  result->v_ptr = self;
+  return 0;
+}
+void cache_handle_delete(void* self) {
+  {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    for (auto it = g_handles.begin(); it != g_handles.end();)
+      it = it->second == self ? g_handles.erase(it) : std::next(it);
+  }
+  tvmb200_cache_destroy(static_cast<tvmb200_cache_t>(self));
+}
+
 tvmb200_cache_t arg_cache(const TVMFFIAny* args, int i, const char* fn) {
-  if (args[i].type_index != kTVMFFIOpaquePtr || args[i].v_ptr == nullptr)
-    throw Err{"TypeError", fmt("%s: argument %d must be the cache returned by vm.builtin.paged_attention_kv_cache_create "
-                               "of tvm_b200 (got type index %d)", fn, i, args[i].type_index)};
-  return static_cast<tvmb200_cache_t>(args[i].v_ptr);
+  if (args[i].type_index == kTVMFFIOpaquePtr && args[i].v_ptr != nullptr) return static_cast<tvmb200_cache_t>(args[i].v_ptr);
+  if (args[i].type_index == kTVMFFIFunction) {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    auto it = g_handles.find(args[i].v_obj);
+    if (it != g_handles.end()) return it->second;
+  }
+  throw Err{"TypeError", fmt("%s: argument %d must be the cache returned by vm.builtin.paged_attention_kv_cache_create "
+                             "of tvm_b200 (got type index %d)", fn, i, args[i].type_index)};
 }
 
 struct ShapeView {
@@ -687,7 +724,11 @@ int vm_create(void*, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   if (n != 28 && n != 29) throw Err{"TypeError", fmt("%s expects 28 or 29 arguments, got %d", fn, n)};
   const ShapeView cfg = arg_shape(args, 0, fn, "cache_config"), li = arg_shape(args, 1, fn, "layer_indptr");
   if (cfg.size != 5 && cfg.size != 6) throw Err{"ValueError", fmt("%s: cache_config must have 5 or 6 entries", fn)};
-  if (li.size < 2) throw Err{"ValueError", fmt("%s: layer_indptr needs at least two entries", fn)};
+  // the reference picks layer_indptr[group .. group + 1] of the calling Disco worker's pipeline group
+  // (paged_kv_cache.cc:2541-2551); there is no Disco worker here, so only a single stage slice can be meant
+  if (li.size != 2)
+    throw Err{"ValueError", fmt("%s: layer_indptr has %ld entries; tvm_b200 serves one pipeline stage per cache -- pass "
+                                "this worker's [begin, end) pair", fn, (long)li.size)};
   const int64_t hq = arg_int(args, 2, fn, "num_qo_heads"), hkv = arg_int(args, 3, fn, "num_kv_heads");
   const int64_t d_qk = arg_int(args, 4, fn, "qk_head_dim"), d_v = arg_int(args, 5, fn, "v_head_dim");
   if (d_qk != d_v) throw Err{"ValueError", fmt("%s: qk_head_dim %ld != v_head_dim %ld (MLA is outside this hot path)", fn, (long)d_qk, (long)d_v)};
@@ -719,11 +760,27 @@ int vm_create(void*, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   c.rotary_theta = arg_float(args, 10, fn, "rotary_theta");
   c.dtype = kv_dtype(init, fn, "init");
   c.device_id = init.t->device.device_id;
+  // arguments 13..27 (the compiled callbacks) are not used: the cache drives tvm_b200's own kernels.  What the
+  // reference compiled INTO them -- rope_scaling, rotary_dim -- is taken from the calling thread's current kernel-set
+  // context (tvmb200_set_rope_scaling / the `set_rope_scaling` packed function) at this moment and stays with this
+  // cache, so two models with different scalings can live in one process.
+  typedef int (*PFN_Create)(void*, TVMFFISafeCallType, void (*)(void*), TVMFFIObjectHandle*);
+  static PFN_Create create = reinterpret_cast<PFN_Create>(ffi_sym("TVMFFIFunctionCreate"));
+  if (!create) throw Err{"RuntimeError", "libtvm_ffi.so (TVMFFIFunctionCreate) is not loaded"};
   tvmb200_cache_t cache = nullptr;
   cache_rc(tvmb200_cache_create(&c, &cache));
-  result->type_index = kTVMFFIOpaquePtr;
+  TVMFFIObjectHandle h = nullptr;
+  if (create(cache, cache_handle_call, cache_handle_delete, &h) != 0) {
+    tvmb200_cache_destroy(cache);
+    return -1;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    g_handles[h] = cache;
+  }
+  result->type_index = kTVMFFIFunction;
   result->zero_padding = 0;
-  result->v_ptr = cache;
+  result->v_obj = static_cast<TVMFFIObject*>(h);
   TVMB200_VM_END();
 }
 
@@ -887,6 +944,26 @@ int vm_debug_get_kv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
   TVMB200_VM_NONE();
   TVMB200_VM_END();
 }
+struct CacheShape {
+  int64_t hq, hkv, d, dtype;
+};
+CacheShape cache_shape(tvmb200_cache_t c) {
+  int64_t v[6];
+  cache_rc(tvmb200_cache_shape(c, v));
+  return CacheShape{v[0], v[1], v[2], v[3]};
+}
+void expect_cache_dtype(const Tensor& t, const CacheShape& cs, const char* fn, const char* name) {
+  if (kv_dtype(t, fn, name) != cs.dtype)
+    throw Err{"ValueError", fmt("%s: %s has a different dtype than the cache's pages (%s)", fn, name,
+                                cs.dtype == TVMB200_F16 ? "float16" : "bfloat16")};
+}
+// q / o style tensor [n, heads, head_dim] of the cache's dtype
+void expect_cache_heads(const Tensor& t, const CacheShape& cs, int64_t heads, const char* fn, const char* name) {
+  expect_cache_dtype(t, cs, fn, name);
+  if (t.shape(1) != heads || t.shape(2) != cs.d)
+    throw Err{"ValueError", fmt("%s: %s must be [n, %ld, %ld] for this cache, got [%ld, %ld, %ld]", fn, name, (long)heads,
+                                (long)cs.d, (long)t.shape(0), (long)t.shape(1), (long)t.shape(2))};
+}
 int vm_attention_with_fused_qkv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
   static const char* fn = "vm.builtin.attention_kv_cache_attention_with_fused_qkv";
   TVMB200_VM_BEGIN();
@@ -895,8 +972,18 @@ int vm_attention_with_fused_qkv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny*
   if (qkv.t->device.device_type != kDLCUDA || o.t->device.device_type != kDLCUDA)
     throw Err{"ValueError", fmt("%s: qkv_data / o_data must be CUDA tensors (there is no CPU fallback)", fn)};
   if (qkv.ndim() != 3 || o.ndim() != 3) throw Err{"ValueError", fmt("%s: qkv_data and o_data must be 3-D", fn)};
-  (void)kv_dtype(qkv, fn, "qkv_data");
-  cache_rc(tvmb200_cache_attention_with_fused_qkv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+  tvmb200_cache_t c = arg_cache(a, 0, fn);
+  // the reference's checks (paged_kv_cache.cc:1303-1335): dtype of the pages, head counts, head_dim, o vs qkv
+  const CacheShape cs = cache_shape(c);
+  expect_cache_dtype(qkv, cs, fn, "qkv_data");
+  expect_cache_dtype(o, cs, fn, "o_data");
+  if (qkv.shape(1) != cs.hq + 2 * cs.hkv || o.shape(1) != cs.hq || qkv.shape(2) != cs.d || o.shape(2) != cs.d ||
+      o.shape(0) != qkv.shape(0))
+    throw Err{"ValueError", fmt("%s: qkv_data must be [n, %ld, %ld] and o_data [n, %ld, %ld] for this cache, got [%ld, %ld, %ld] "
+                                "and [%ld, %ld, %ld]", fn, (long)(cs.hq + 2 * cs.hkv), (long)cs.d, (long)cs.hq, (long)cs.d,
+                                (long)qkv.shape(0), (long)qkv.shape(1), (long)qkv.shape(2), (long)o.shape(0), (long)o.shape(1),
+                                (long)o.shape(2))};
+  cache_rc(tvmb200_cache_attention_with_fused_qkv(c, arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
                                                   qkv.data, o.data, qkv.shape(0), env_stream(qkv.t->device.device_id)));
   TVMB200_VM_NONE();
   TVMB200_VM_END();
@@ -926,7 +1013,13 @@ int vm_self_attention(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
   expect_lse(lse, q, fn, "lse_data");
   if (k.shape(0) != q.shape(0) || v.shape(0) != q.shape(0) || o.shape(0) != q.shape(0))
     throw Err{"ValueError", fmt("%s: q / k / v / o must have the same number of rows", fn)};
-  cache_rc(tvmb200_cache_self_attention(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+  tvmb200_cache_t c = arg_cache(a, 0, fn);
+  const CacheShape cs = cache_shape(c);
+  expect_cache_heads(q, cs, cs.hq, fn, "q_data");
+  expect_cache_heads(k, cs, cs.hkv, fn, "k_data");
+  expect_cache_heads(v, cs, cs.hkv, fn, "v_data");
+  expect_cache_heads(o, cs, cs.hq, fn, "o_data");
+  cache_rc(tvmb200_cache_self_attention(c, arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
                                         q.data, k.data, v.data, o.data, static_cast<float*>(lse.data), q.shape(0),
                                         env_stream(q.t->device.device_id)));
   TVMB200_VM_NONE();
@@ -941,7 +1034,11 @@ int vm_cross_attention(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) 
   expect_cuda_3d(o, fn, "o_data");
   expect_lse(lse, q, fn, "lse_data");
   if (o.shape(0) != q.shape(0)) throw Err{"ValueError", fmt("%s: q and o must have the same number of rows", fn)};
-  cache_rc(tvmb200_cache_cross_attention(arg_cache(a, 0, fn), arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
+  tvmb200_cache_t c = arg_cache(a, 0, fn);
+  const CacheShape cs = cache_shape(c);
+  expect_cache_heads(q, cs, cs.hq, fn, "q_data");
+  expect_cache_heads(o, cs, cs.hq, fn, "o_data");
+  cache_rc(tvmb200_cache_cross_attention(c, arg_int(a, 1, fn, "layer_id"), arg_float(a, 2, fn, "sm_scale"),
                                          q.data, o.data, static_cast<float*>(lse.data), q.shape(0),
                                          env_stream(q.t->device.device_id)));
   TVMB200_VM_NONE();
@@ -959,7 +1056,13 @@ int vm_attention_with_shared_kv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny*
   expect_cuda_3d(o, fn, "o_data");
   if (k.shape(0) != q.shape(0) || v.shape(0) != q.shape(0) || o.shape(0) != q.shape(0))
     throw Err{"ValueError", fmt("%s: q / current_k / current_v / o must have the same number of rows", fn)};
-  cache_rc(tvmb200_cache_attention_with_shared_kv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "source_layer_id"),
+  tvmb200_cache_t c = arg_cache(a, 0, fn);
+  const CacheShape cs = cache_shape(c);
+  expect_cache_heads(q, cs, cs.hq, fn, "q_data");
+  expect_cache_heads(k, cs, cs.hkv, fn, "current_k_data");
+  expect_cache_heads(v, cs, cs.hkv, fn, "current_v_data");
+  expect_cache_heads(o, cs, cs.hq, fn, "o_data");
+  cache_rc(tvmb200_cache_attention_with_shared_kv(c, arg_int(a, 1, fn, "source_layer_id"),
                                                   arg_float(a, 2, fn, "sm_scale"), q.data, k.data, v.data, o.data, q.shape(0),
                                                   env_stream(q.t->device.device_id)));
   TVMB200_VM_NONE();
@@ -1074,7 +1177,120 @@ extern "C" int tvmb200_register_vm_builtins(int allow_override) {
   return count;
 }
 
+// role names used by the reference cache constructor (paged_kv_cache.cc:2573-2603), the global_symbols of the reference
+// PrimFuncs they replace, and the state the reference bakes in at TIR build time
+#define TVMB200_CALLBACKS(X)                                                  \
+  X(f_transpose_append, impl_transpose_append)                                \
+  X(f_attention_decode, impl_decode)                                          \
+  X(f_attention_decode_sliding_window, impl_decode)                           \
+  X(f_attention_prefill, impl_prefill_paged)                                  \
+  X(f_attention_prefill_sliding_window, impl_prefill_paged)                   \
+  X(f_attention_prefill_ragged, impl_prefill_ragged)                          \
+  X(f_attention_prefill_with_tree_mask, impl_tree_ragged)                     \
+  X(f_attention_prefill_with_tree_mask_paged_kv, impl_tree_paged)             \
+  X(f_merge_inplace, impl_merge_state_inplace)                                \
+  X(f_split_rotary, impl_fused_rope)                                          \
+  X(f_copy_single_page, impl_copy_single_page)                                \
+  X(f_debug_get_kv, impl_debug_get_kv)                                        \
+  X(f_compact_copy, impl_compact_kv_copy)                                     \
+  X(tir_kv_cache_transpose_append, impl_transpose_append)                     \
+  X(batch_decode_paged_kv, impl_decode)                                       \
+  X(batch_decode_paged_kv_sliding_window, impl_decode)                        \
+  X(batch_prefill_paged_kv, impl_prefill_paged)                               \
+  X(batch_prefill_paged_kv_sliding_window, impl_prefill_paged)                \
+  X(batch_prefill_ragged_kv, impl_prefill_ragged)                             \
+  X(batch_tree_attn, impl_tree_ragged)                                        \
+  X(tree_attn_paged_kv, impl_tree_paged)                                      \
+  X(merge_state_inplace, impl_merge_state_inplace)                            \
+  X(fused_rope, impl_fused_rope)                                              \
+  X(copy_single_page, impl_copy_single_page)                                  \
+  X(tir_kv_cache_debug_get_kv, impl_debug_get_kv)                             \
+  X(compact_kv_copy, impl_compact_kv_copy)                                    \
+  X(set_rope_params, impl_set_rope_params)                                    \
+  X(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)        \
+  X(set_rope_scaling, impl_set_rope_scaling)                                  \
+  X(set_rope_scaling_yarn, impl_set_rope_scaling_yarn)                        \
+  X(launch_count, impl_launch_count)                                          \
+  X(register_vm_builtins, impl_register_vm_builtins)
+
 namespace {
+
+// ---- kernel-set contexts for the packed path --------------------------------------------------------------------
+// The module symbols above run in the DEFAULT context.  The reference compiles one kernel set per model (rope_scaling,
+// rotary_dim, layer window baked in); the equivalent here is a context plus closures bound to it:
+//   ctx = context_create()                                   (opaque pointer; context_release(ctx) when done)
+//   bind_context(ctx, "set_rope_scaling")(1, 8.0, 1.0, 4.0, 8192)
+//   f_decode = bind_context(ctx, "f_attention_decode")       (an ffi Function that holds a reference on ctx)
+// Two models with different rope scalings, or two streams, then never share settings or scratch.
+typedef int (*ImplFn)(const TVMFFIAny*, int32_t, TVMFFIAny*);
+struct Bound {
+  tvmb200_context_t ctx;
+  ImplFn impl;
+};
+int bound_call(void* self, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  Bound* b = static_cast<Bound*>(self);
+  tvmb200::ContextScope scope(reinterpret_cast<tvmb200::Context*>(b->ctx));
+  return b->impl(args, n, result);
+}
+void bound_delete(void* self) {
+  Bound* b = static_cast<Bound*>(self);
+  tvmb200_context_release(b->ctx);
+  delete b;
+}
+ImplFn find_impl(const std::string& name) {
+#define X(sym, impl) \
+  if (name == #sym) return impl;
+  TVMB200_CALLBACKS(X)
+#undef X
+  return nullptr;
+}
+tvmb200_context_t arg_context(const TVMFFIAny* args, int i, const char* fn) {
+  if (args[i].type_index != kTVMFFIOpaquePtr || args[i].v_ptr == nullptr)
+    throw Err{"TypeError", fmt("%s: argument %d must be a context made by context_create", fn, i)};
+  return static_cast<tvmb200_context_t>(args[i].v_ptr);
+}
+int impl_context_create(const TVMFFIAny*, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "context_create";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 0, fn);
+  tvmb200_context_t c = nullptr;
+  check_rc(tvmb200_context_create(&c));
+  result->type_index = kTVMFFIOpaquePtr;
+  result->zero_padding = 0;
+  result->v_ptr = c;
+  TVMB200_VM_END();
+}
+int impl_context_release(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "context_release";
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 1, fn);
+  tvmb200_context_release(arg_context(args, 0, fn));
+  TVMB200_FFI_END();
+}
+int impl_bind_context(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "bind_context";
+  typedef int (*PFN_Create)(void*, TVMFFISafeCallType, void (*)(void*), TVMFFIObjectHandle*);
+  static PFN_Create create = reinterpret_cast<PFN_Create>(ffi_sym("TVMFFIFunctionCreate"));
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 2, fn);
+  if (!create) throw Err{"RuntimeError", "libtvm_ffi.so (TVMFFIFunctionCreate) is not loaded"};
+  tvmb200_context_t ctx = arg_context(args, 0, fn);
+  const std::string name = arg_str(args, 1, fn, "name");
+  ImplFn impl = find_impl(name);
+  if (!impl) throw Err{"ValueError", fmt("%s: tvm_b200 exports no packed function named \"%s\"", fn, name.c_str())};
+  Bound* b = new Bound{ctx, impl};
+  tvmb200_context_retain(ctx);
+  TVMFFIObjectHandle h = nullptr;
+  if (create(b, bound_call, bound_delete, &h) != 0) {
+    bound_delete(b);
+    return -1;
+  }
+  result->type_index = kTVMFFIFunction;
+  result->zero_padding = 0;
+  result->v_obj = static_cast<TVMFFIObject*>(h);
+  TVMB200_VM_END();
+}
+
 }  // namespace
 
 #define TVMB200_EXPORT(name, impl)                                                                      \
@@ -1084,38 +1300,7 @@ namespace {
     return impl(args, num_args, result);                                                                \
   }
 
-// role names used by the reference cache constructor (paged_kv_cache.cc:2573-2603) ...
-TVMB200_EXPORT(f_transpose_append, impl_transpose_append)
-TVMB200_EXPORT(f_attention_decode, impl_decode)
-TVMB200_EXPORT(f_attention_decode_sliding_window, impl_decode)
-TVMB200_EXPORT(f_attention_prefill, impl_prefill_paged)
-TVMB200_EXPORT(f_attention_prefill_sliding_window, impl_prefill_paged)
-TVMB200_EXPORT(f_attention_prefill_ragged, impl_prefill_ragged)
-TVMB200_EXPORT(f_attention_prefill_with_tree_mask, impl_tree_ragged)
-TVMB200_EXPORT(f_attention_prefill_with_tree_mask_paged_kv, impl_tree_paged)
-TVMB200_EXPORT(f_merge_inplace, impl_merge_state_inplace)
-TVMB200_EXPORT(f_split_rotary, impl_fused_rope)
-TVMB200_EXPORT(f_copy_single_page, impl_copy_single_page)
-TVMB200_EXPORT(f_debug_get_kv, impl_debug_get_kv)
-TVMB200_EXPORT(f_compact_copy, impl_compact_kv_copy)
-// ... and the global_symbols of the reference PrimFuncs they replace
-TVMB200_EXPORT(tir_kv_cache_transpose_append, impl_transpose_append)
-TVMB200_EXPORT(batch_decode_paged_kv, impl_decode)
-TVMB200_EXPORT(batch_decode_paged_kv_sliding_window, impl_decode)
-TVMB200_EXPORT(batch_prefill_paged_kv, impl_prefill_paged)
-TVMB200_EXPORT(batch_prefill_paged_kv_sliding_window, impl_prefill_paged)
-TVMB200_EXPORT(batch_prefill_ragged_kv, impl_prefill_ragged)
-TVMB200_EXPORT(batch_tree_attn, impl_tree_ragged)
-TVMB200_EXPORT(tree_attn_paged_kv, impl_tree_paged)
-TVMB200_EXPORT(merge_state_inplace, impl_merge_state_inplace)
-TVMB200_EXPORT(fused_rope, impl_fused_rope)
-TVMB200_EXPORT(copy_single_page, impl_copy_single_page)
-TVMB200_EXPORT(tir_kv_cache_debug_get_kv, impl_debug_get_kv)
-TVMB200_EXPORT(compact_kv_copy, impl_compact_kv_copy)
-// module state the reference bakes in at TIR build time
-TVMB200_EXPORT(set_rope_params, impl_set_rope_params)
-TVMB200_EXPORT(set_layer_sliding_window_size, impl_set_layer_sliding_window_size)
-TVMB200_EXPORT(set_rope_scaling, impl_set_rope_scaling)
-TVMB200_EXPORT(set_rope_scaling_yarn, impl_set_rope_scaling_yarn)
-TVMB200_EXPORT(launch_count, impl_launch_count)
-TVMB200_EXPORT(register_vm_builtins, impl_register_vm_builtins)
+TVMB200_CALLBACKS(TVMB200_EXPORT)
+TVMB200_EXPORT(context_create, impl_context_create)
+TVMB200_EXPORT(context_release, impl_context_release)
+TVMB200_EXPORT(bind_context, impl_bind_context)

@@ -99,6 +99,7 @@ class Cache {
   void PopN(int64_t seq_id, int32_t n);
   void EnableSlidingWindowForSeq(int64_t seq_id, int32_t window, int32_t sink);
   void BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size);
+  void BeginForwardImpl(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size);
   void EndForward() {}
   void CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n);
   bool Empty() const {
@@ -133,6 +134,15 @@ class Cache {
     *np = num_total_pages_;
     return pages_.empty() ? nullptr : pages_[layer];
   }
+  void Shape(int64_t* out) const {
+    out[0] = num_qo_heads_;
+    out[1] = num_kv_heads_;
+    out[2] = head_dim_;
+    out[3] = dtype_;
+    out[4] = num_layers_;
+    out[5] = layer_begin_;
+  }
+  tvmb200_context_t Context() const { return ctx_; }
   void SetTrace(bool on) {
     tracing_ = on;
     trace_.clear();
@@ -155,6 +165,8 @@ class Cache {
   double rotary_scale_, rotary_theta_;
   int dtype_, device_;
   size_t esize_ = 2;
+  // this cache's kernel-set context (tvm_b200.h): the rope scaling / layer window current at creation, own scratch
+  tvmb200_context_t ctx_ = nullptr;
 
   // ---- page / block / sequence state ----
   std::vector<int32_t> free_pages_;
@@ -389,13 +401,21 @@ Cache::Cache(const tvmb200_cache_config& c)
   num_total_pages_ = (c.total_token_capacity + page_size_ - 1) / page_size_ + 1;
   if (c.support_sliding_window) num_total_pages_ += reserved_seqs_ * 2;
   Clear();
+  HCHECK(tvmb200_context_create(&ctx_) == 0, "%s", tvmb200_last_error());
+  {
+    tvmb200_context_t prev = tvmb200_context_enter(ctx_);
+    tvmb200_set_layer_sliding_window_size(static_cast<int32_t>(layer_sws_));
+    tvmb200_context_enter(prev);
+  }
 
   // worst-case size of the merged aux buffer (the reference allocates a flat 32 Mi-element buffer, attn_utils.h:825)
   auto al = [](int64_t n) { return (n + 3) / 4 * 4; };
   int64_t per_depth = 2 * al(reserved_seqs_ + 1) + 2 * al(reserved_seqs_ + 1) + 2 * al(num_total_pages_) +
                       2 * al(3 * reserved_seqs_) + 2 * al(reserved_seqs_) + al(kMaxTreeSize * 2 * reserved_seqs_) +
                       al(reserved_seqs_ + 1);
-  aux_capacity_ = al(prefill_chunk_) * 2 + al(reserved_seqs_ + 1) + al(reserved_seqs_) + kMaxBlockDepth * per_depth + 64;
+  // q_rope_position + append_position maps, plus the two prefill_chunk-sized regions BuildAuxViews skips to keep the
+  // reference's byte offsets (its kv-transfer maps)
+  aux_capacity_ = al(prefill_chunk_) * 4 + al(reserved_seqs_ + 1) + al(reserved_seqs_) + kMaxBlockDepth * per_depth + 64;
   stage_.assign(aux_capacity_, 0);
 
   if (!planning_only()) {
@@ -433,6 +453,11 @@ Cache::Cache(const tvmb200_cache_config& c)
 }
 
 Cache::~Cache() {
+  if (!planning_only()) {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+  }
+  tvmb200_context_release(ctx_);
   if (planning_only()) return;
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
@@ -774,10 +799,73 @@ void Cache::ConstructTokenTreeMask(const std::vector<Sequence*>& seqs, const int
   }
 }
 
+// BeginForward is transactional: when it throws (unknown sequence, cache full, aux overflow, invalid tree) every
+// sequence length, block, page list and the free-page stack are restored to what they were before the call, so the
+// cache stays usable; there is just no current batch (the attention / commit entries refuse to run until a
+// begin_forward completes).  The reference is not transactional (its errors are fatal ICHECKs).
 void Cache::BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size) {
-  // a begin_forward that throws half-way (unknown sequence, cache full, invalid tree) leaves no usable batch: the
-  // attention / commit entries refuse to run on it instead of indexing half-built arrays
   batch_valid_ = false;
+  HCHECK(n > 0, "begin_forward: the batch is empty");
+  for (int i = 0; i < n; ++i) {
+    Seq(seq_ids[i]);
+    HCHECK(lens[i] > 0, "Append with length 0 is not allowed.");
+    for (int j = 0; j < i; ++j) HCHECK(seq_ids[j] != seq_ids[i], "begin_forward: sequence %ld appears twice in the batch", (long)seq_ids[i]);
+  }
+  // snapshot of what the call may mutate: the batch's Sequence records and their last blocks, the free-page stack
+  struct Saved {
+    int64_t id;
+    Sequence seq;
+    int32_t block;
+    Block blk;
+  };
+  std::vector<Saved> saved;
+  saved.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    const Sequence& s = seq_map_.at(seq_ids[i]);
+    saved.push_back(Saved{seq_ids[i], s, s.last_block_idx, Block()});
+    // a decode step of a plain sequence can only push pages onto its last block: remember the scalars and the page
+    // count; a sliding-window sequence may also drop pages from the middle, so keep the list
+    const Block& b = blocks_[s.last_block_idx];
+    Block& kb = saved.back().blk;
+    kb.seq_length = b.seq_length;
+    kb.start_pos = b.start_pos;
+    kb.sink_length = b.sink_length;
+    kb.sliding_window_offset = b.sliding_window_offset;
+    kb.parent_idx = b.parent_idx;
+    kb.external_ref_cnt = static_cast<int>(b.page_ids.size());  // (re-used field: the page count before the call)
+    if (s.sliding_window_size != -1) kb.page_ids = b.page_ids;
+  }
+  const std::vector<int32_t> free_before = support_sw_ ? free_pages_ : std::vector<int32_t>();
+  const size_t free_size_before = free_pages_.size();
+  try {
+    BeginForwardImpl(seq_ids, lens, n, tree, tree_size);
+  } catch (...) {
+    for (auto it = saved.rbegin(); it != saved.rend(); ++it) {  // reverse: pages go back in the order they came
+      const Saved& sv = *it;
+      seq_map_.at(sv.id) = sv.seq;
+      Block& b = blocks_[sv.block];
+      const size_t pages_before = static_cast<size_t>(sv.blk.external_ref_cnt);
+      if (sv.seq.sliding_window_size != -1) {
+        b.page_ids = sv.blk.page_ids;
+      } else {
+        // pages were handed out from the back of the free stack in push order: give them back in reverse
+        while (b.page_ids.size() > pages_before) {
+          if (!support_sw_ && b.page_ids.back() != kTempPageId) free_pages_.push_back(b.page_ids.back());
+          b.page_ids.pop_back();
+        }
+      }
+      b.seq_length = sv.blk.seq_length;
+      b.start_pos = sv.blk.start_pos;
+      b.sink_length = sv.blk.sink_length;
+      b.sliding_window_offset = sv.blk.sliding_window_offset;
+    }
+    if (support_sw_) free_pages_ = free_before;
+    if (free_pages_.size() != free_size_before) fail("begin_forward rollback lost pages (%zu != %zu)", free_pages_.size(), free_size_before);
+    throw;
+  }
+}
+
+void Cache::BeginForwardImpl(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size) {
   cur_batch_ = n;
   cur_seq_ids_.assign(seq_ids, seq_ids + n);
   cur_lens_.assign(lens, lens + n);
@@ -1386,7 +1474,17 @@ struct tvmb200_cache_s {
   std::unique_ptr<Cache> impl;
 };
 
+// every entry runs with the cache's own kernel-set context current on the calling thread
+struct CacheScope {
+  explicit CacheScope(tvmb200_context_t c) : prev(tvmb200_context_enter(c)) {}
+  ~CacheScope() { tvmb200_context_enter(prev); }
+  tvmb200_context_t prev;
+};
 #define CACHE_API_BEGIN() try {
+#define CACHE_API_BEGIN_C(c)                                                     \
+  try {                                                                          \
+    if (!(c)) throw std::runtime_error("null cache handle");                     \
+    CacheScope scope__((c)->impl->Context());
 #define CACHE_API_END()                                   \
   return 0;                                               \
   }                                                       \
@@ -1409,65 +1507,67 @@ int tvmb200_cache_create(const tvmb200_cache_config* cfg, tvmb200_cache_t* out) 
   CACHE_API_END();
 }
 void tvmb200_cache_destroy(tvmb200_cache_t c) { delete c; }
-int tvmb200_cache_clear(tvmb200_cache_t c) { CACHE_API_BEGIN(); c->impl->Clear(); CACHE_API_END(); }
-int tvmb200_cache_add_sequence(tvmb200_cache_t c, int64_t s) { CACHE_API_BEGIN(); c->impl->AddSequence(s); CACHE_API_END(); }
-int tvmb200_cache_remove_sequence(tvmb200_cache_t c, int64_t s) { CACHE_API_BEGIN(); c->impl->RemoveSequence(s); CACHE_API_END(); }
+int tvmb200_cache_clear(tvmb200_cache_t c) { CACHE_API_BEGIN_C(c); c->impl->Clear(); CACHE_API_END(); }
+int tvmb200_cache_add_sequence(tvmb200_cache_t c, int64_t s) { CACHE_API_BEGIN_C(c); c->impl->AddSequence(s); CACHE_API_END(); }
+int tvmb200_cache_remove_sequence(tvmb200_cache_t c, int64_t s) { CACHE_API_BEGIN_C(c); c->impl->RemoveSequence(s); CACHE_API_END(); }
 int tvmb200_cache_fork_sequence(tvmb200_cache_t c, int64_t p, int64_t ch, int64_t pos) {
-  CACHE_API_BEGIN(); c->impl->ForkSequence(p, ch, pos); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->ForkSequence(p, ch, pos); CACHE_API_END();
 }
-int tvmb200_cache_popn(tvmb200_cache_t c, int64_t s, int32_t n) { CACHE_API_BEGIN(); c->impl->PopN(s, n); CACHE_API_END(); }
+int tvmb200_cache_popn(tvmb200_cache_t c, int64_t s, int32_t n) { CACHE_API_BEGIN_C(c); c->impl->PopN(s, n); CACHE_API_END(); }
 int tvmb200_cache_begin_forward(tvmb200_cache_t c, const int64_t* seq_ids, const int64_t* lens, int32_t n,
                                 const int64_t* tree, int32_t tree_size) {
-  CACHE_API_BEGIN(); c->impl->BeginForward(seq_ids, lens, n, tree, tree_size); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->BeginForward(seq_ids, lens, n, tree, tree_size); CACHE_API_END();
 }
-int tvmb200_cache_end_forward(tvmb200_cache_t c) { CACHE_API_BEGIN(); c->impl->EndForward(); CACHE_API_END(); }
+int tvmb200_cache_end_forward(tvmb200_cache_t c) { CACHE_API_BEGIN_C(c); c->impl->EndForward(); CACHE_API_END(); }
 int tvmb200_cache_enable_sliding_window_for_seq(tvmb200_cache_t c, int64_t s, int32_t w, int32_t sink) {
-  CACHE_API_BEGIN(); c->impl->EnableSlidingWindowForSeq(s, w, sink); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->EnableSlidingWindowForSeq(s, w, sink); CACHE_API_END();
 }
 int tvmb200_cache_commit_accepted_token_tree_nodes(tvmb200_cache_t c, const int64_t* s, const int64_t* l, int32_t n) {
-  CACHE_API_BEGIN(); c->impl->CommitAcceptedTokenTreeNodes(s, l, n); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->CommitAcceptedTokenTreeNodes(s, l, n); CACHE_API_END();
 }
-int tvmb200_cache_empty(tvmb200_cache_t c, int32_t* out) { CACHE_API_BEGIN(); *out = c->impl->Empty(); CACHE_API_END(); }
+int tvmb200_cache_empty(tvmb200_cache_t c, int32_t* out) { CACHE_API_BEGIN_C(c); *out = c->impl->Empty(); CACHE_API_END(); }
 int tvmb200_cache_get_num_available_pages(tvmb200_cache_t c, int32_t* out) {
-  CACHE_API_BEGIN(); *out = c->impl->NumAvailablePages(); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); *out = c->impl->NumAvailablePages(); CACHE_API_END();
 }
 int tvmb200_cache_get_total_sequence_length(tvmb200_cache_t c, int32_t* out) {
-  CACHE_API_BEGIN(); *out = c->impl->TotalSequenceLength(); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); *out = c->impl->TotalSequenceLength(); CACHE_API_END();
 }
 int tvmb200_cache_get_query_positions(tvmb200_cache_t c, const int32_t** p, int64_t* n, tvmb200_stream_t st) {
-  CACHE_API_BEGIN(); c->impl->QueryPositions(p, n, static_cast<cudaStream_t>(st)); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->QueryPositions(p, n, static_cast<cudaStream_t>(st)); CACHE_API_END();
 }
 int tvmb200_cache_attention_with_fused_qkv(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* qkv, void* o,
                                            int64_t rows, tvmb200_stream_t st) {
-  CACHE_API_BEGIN(); c->impl->AttentionWithFusedQKV(layer, sm_scale, qkv, o, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->AttentionWithFusedQKV(layer, sm_scale, qkv, o, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
 }
 int tvmb200_cache_self_attention(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* q, const void* k,
                                  const void* v, void* o, float* lse, int64_t rows, tvmb200_stream_t st) {
-  CACHE_API_BEGIN(); c->impl->SelfAttention(layer, sm_scale, q, k, v, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->SelfAttention(layer, sm_scale, q, k, v, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
 }
 int tvmb200_cache_cross_attention(tvmb200_cache_t c, int64_t layer, double sm_scale, const void* q, void* o, float* lse,
                                   int64_t rows, tvmb200_stream_t st) {
-  CACHE_API_BEGIN(); c->impl->CrossAttention(layer, sm_scale, q, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->CrossAttention(layer, sm_scale, q, o, lse, rows, static_cast<cudaStream_t>(st)); CACHE_API_END();
 }
 int tvmb200_cache_attention_with_shared_kv(tvmb200_cache_t c, int64_t source_layer, double sm_scale, const void* q,
                                            const void* cur_k, const void* cur_v, void* o, int64_t rows, tvmb200_stream_t st) {
-  CACHE_API_BEGIN();
+  CACHE_API_BEGIN_C(c);
   c->impl->AttentionWithSharedKV(source_layer, sm_scale, q, cur_k, cur_v, o, rows, static_cast<cudaStream_t>(st));
   CACHE_API_END();
 }
 int tvmb200_cache_merge_attn_output_inplace(tvmb200_cache_t c, void* o_self, float* lse_self, const void* o_cross,
                                             const float* lse_cross, int64_t n, int64_t num_heads, int64_t head_dim,
                                             tvmb200_stream_t st) {
-  CACHE_API_BEGIN();
+  CACHE_API_BEGIN_C(c);
   c->impl->MergeAttnOutputInplace(o_self, lse_self, o_cross, lse_cross, n, num_heads, head_dim, static_cast<cudaStream_t>(st));
   CACHE_API_END();
 }
 int tvmb200_cache_debug_get_kv(tvmb200_cache_t c, int64_t s, int64_t a, int64_t b, void* k, void* v, tvmb200_stream_t st) {
-  CACHE_API_BEGIN(); c->impl->DebugGetKV(s, a, b, k, v, static_cast<cudaStream_t>(st)); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); c->impl->DebugGetKV(s, a, b, k, v, static_cast<cudaStream_t>(st)); CACHE_API_END();
 }
 int tvmb200_cache_pages(tvmb200_cache_t c, int64_t layer, void** p, int64_t* np) {
-  CACHE_API_BEGIN(); *p = c->impl->Pages(layer, np); CACHE_API_END();
+  CACHE_API_BEGIN_C(c); *p = c->impl->Pages(layer, np); CACHE_API_END();
 }
-int tvmb200_cache_set_trace(tvmb200_cache_t c, int32_t on) { CACHE_API_BEGIN(); c->impl->SetTrace(on != 0); CACHE_API_END(); }
-int tvmb200_cache_take_trace(tvmb200_cache_t c, const char** json) { CACHE_API_BEGIN(); *json = c->impl->TakeTrace(); CACHE_API_END(); }
+int tvmb200_cache_shape(tvmb200_cache_t c, int64_t* out6) { CACHE_API_BEGIN_C(c); c->impl->Shape(out6); CACHE_API_END(); }
+int tvmb200_cache_context(tvmb200_cache_t c, tvmb200_context_t* out) { CACHE_API_BEGIN_C(c); *out = c->impl->Context(); CACHE_API_END(); }
+int tvmb200_cache_set_trace(tvmb200_cache_t c, int32_t on) { CACHE_API_BEGIN_C(c); c->impl->SetTrace(on != 0); CACHE_API_END(); }
+int tvmb200_cache_take_trace(tvmb200_cache_t c, const char** json) { CACHE_API_BEGIN_C(c); *json = c->impl->TakeTrace(); CACHE_API_END(); }
 }

@@ -650,22 +650,6 @@ bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head
   return static_cast<int64_t>(total_q_len) * g >= 2048;
 }
 
-// device-wide work counter of the persistent kernel (one int per device; the kernel leaves it at zero)
-static int get_work_counter(int** out) {
-  static int* counters[64];
-  static std::mutex mu;
-  int dev = 0;
-  TVMB200_CUDA(cudaGetDevice(&dev));
-  TVMB200_CHECK(dev >= 0 && dev < 64, "device id %d out of range", dev);
-  std::lock_guard<std::mutex> lk(mu);
-  if (!counters[dev]) {
-    TVMB200_CUDA(cudaMalloc(&counters[dev], 256));
-    TVMB200_CUDA(cudaMemset(counters[dev], 0, 256));
-  }
-  *out = counters[dev];
-  return 0;
-}
-
 template <typename T, typename PT, bool PAGED>
 static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          int total_q_len, cudaStream_t st) {
@@ -680,8 +664,9 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   const uint32_t idesc_qk = tc05::make_idesc(fa, fa, 0, 0, kRows, kKV);
   // V is converted to the P format in shared memory when the two differ (bf16 inputs, fp16 P)
   const uint32_t idesc_pv = tc05::make_idesc(fp, fp, 0, 1, kRows, kD);
-  int* counter = nullptr;
-  if (int rc = get_work_counter(&counter)) return rc;
+  // work-queue counter of this (context, device, stream)
+  int32_t* counter = nullptr;
+  if (int rc = get_counters(st, &counter)) return rc;
   // the kernel resets the counter with its last fetch; the memset only matters after an aborted launch
   TVMB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv, counter);

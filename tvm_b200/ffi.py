@@ -24,6 +24,7 @@ TIR_NAMES = [
     "compact_kv_copy",
 ]
 STATE = ["set_rope_params", "set_rope_scaling", "set_rope_scaling_yarn", "set_layer_sliding_window_size", "launch_count", "register_vm_builtins"]
+CONTEXT = ["context_create", "context_release", "bind_context"]
 
 _mod = None
 
@@ -55,3 +56,55 @@ def register_globals(prefix: str = "tvm_b200.") -> None:
     m = module()
     for name in CALLBACKS + STATE:
         tvm_ffi.register_global_func(prefix + name, m[name], override=True)
+
+
+class KernelSet:
+    """One kernel set = the 13 callbacks (plus their TIR-named twins) bound to their own context, the counterpart of the
+    reference compiling its PrimFuncs with a `rope_scaling` dict, `rotary_dim`, `rope_theta` / `rope_scale` and
+    `layer_sliding_window_size` baked in (kv_cache.py:690-736).  Two kernel sets never share settings or device
+    scratch, so two models -- or two streams -- can use the library concurrently in one process.
+
+        ks = KernelSet(rope_theta=5e5, rope_scaling={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0,
+                                                      "high_freq_factor": 4.0, "original_max_position_embeddings": 8192})
+        ks["f_attention_decode"](q, pages, ...)
+    """
+
+    def __init__(self, rope_theta: float = 1e4, rope_scale: float = 1.0, rotary_dim: int = 0, rope_scaling: dict | None = None,
+                 layer_sliding_window_size: int = 1024):
+        m = module()
+        self._release = m["context_release"]
+        self._ctx = m["context_create"]()
+        self._bind = m["bind_context"]
+        self._fns = {}
+        self["set_rope_params"](float(rope_theta), float(rope_scale), int(rotary_dim))
+        self["set_layer_sliding_window_size"](int(layer_sliding_window_size))
+        rs = dict(rope_scaling or {})
+        kind = rs.get("rope_type", rs.get("type", "default"))
+        if kind in ("default", None, "none"):
+            self["set_rope_scaling"](0, 1.0, 0.0, 0.0, 0.0)
+        elif kind in ("llama3", "llama4", "gptj"):
+            code = {"llama3": 1, "gptj": 2, "llama4": 3}[kind]
+            self["set_rope_scaling"](code, float(rs.get("factor", 1.0)), float(rs.get("low_freq_factor", 0.0)),
+                                     float(rs.get("high_freq_factor", 0.0)),
+                                     float(rs.get("original_max_position_embeddings", 0.0)))
+        elif kind == "yarn":
+            self["set_rope_scaling_yarn"](float(rs["factor"]), float(rs["original_max_position_embeddings"]),
+                                          float(rs.get("beta_fast", 32.0)), float(rs.get("beta_slow", 1.0)),
+                                          float(rs.get("inv_theta_log_scale", 0.0)))
+        else:
+            raise capi.TvmB200Error(f"rope_scaling type {kind!r} is not supported (default, llama3, gptj, llama4, yarn)")
+
+    def __getitem__(self, name: str):
+        f = self._fns.get(name)
+        if f is None:
+            f = self._fns[name] = self._bind(self._ctx, name)
+        return f
+
+    def callbacks(self) -> dict:
+        return {n: self[n] for n in CALLBACKS}
+
+    def __del__(self):
+        try:
+            self._release(self._ctx)
+        except Exception:  # interpreter shutdown
+            pass

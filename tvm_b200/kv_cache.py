@@ -68,6 +68,8 @@ def _lib():
         L.tvmb200_cache_merge_attn_output_inplace.argtypes = [P, P, P, P, P, I64, I64, I64, P]
         L.tvmb200_cache_debug_get_kv.argtypes = [P, I64, I64, I64, P, P, P]
         L.tvmb200_cache_pages.argtypes = [P, I64, POINTER(P), POINTER(I64)]
+        L.tvmb200_cache_shape.argtypes = [P, POINTER(I64)]
+        L.tvmb200_cache_context.argtypes = [P, POINTER(P)]
         L.tvmb200_cache_set_trace.argtypes = [P, I32]
         L.tvmb200_cache_take_trace.argtypes = [P, POINTER(c_char_p)]
         _bound = True
@@ -242,6 +244,13 @@ class PagedKVCache:
         return ptr.value, n.value
 
     # ---- introspection ----
+    def context(self) -> "capi.Context":
+        """The cache's own kernel-set context: `with cache.context(): capi.lib().tvmb200_set_rope_scaling(...)` changes
+        the rope scaling of this cache only (it starts as a copy of the settings current when the cache was created)."""
+        h = c_void_p()
+        capi._check(_lib().tvmb200_cache_context(self._h, byref(h)))
+        return capi.Context(h.value, owned=False)
+
     def pages_ptr(self, local_layer=0):
         ptr, n = c_void_p(), c_int64()
         capi._check(_lib().tvmb200_cache_pages(self._h, local_layer, byref(ptr), byref(n)))
