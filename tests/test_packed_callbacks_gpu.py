@@ -83,9 +83,9 @@ def env(mod):
     import tvm_ffi
 
     s = torch.cuda.Stream()
+    arena = Arena(s)                   # (its constructor synchronises the device)
     with torch.cuda.stream(s):
         torch.cuda._sleep(20_000_000)  # ~10 ms: uploads and kernels queued behind it are ordered by the stream alone
-    arena = Arena(s)
 
     class Env:
         pass
@@ -397,9 +397,9 @@ def test_stale_input_proves_the_stream_matters(mod):
     import tvm_ffi
 
     s = torch.cuda.Stream()
+    arena = Arena(s, nbytes=8 << 20)
     with torch.cuda.stream(s):
         torch.cuda._sleep(400_000_000)  # ~0.2 s
-    arena = Arena(s, nbytes=8 << 20)
     rng = np.random.default_rng(9)
     v = rand16(rng, (64, HQ, D), "float16")
     s_ = np.zeros((64, HQ), np.float32)
