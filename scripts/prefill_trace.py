@@ -33,14 +33,13 @@ if mode == "tile":
     # softmax warpgroup t owns Q tile t; stamps indexed by half-step s = 2j+h
     print("role 1+t = softmax warpgroup of Q tile t, index s: [0] wait S, [1] S ready, [2] ld done, [3] P arrive")
     print("role 0 = MMA warp, index s: [3t+1] P ready seen, [3t+2] PV(+QK) issued.   times in clk from the first stamp")
-    print("role 0 also: [3t] QK_t(j) issue time at index s = 2j")
     print("  s | T0: Swait   ld  comp  arrive@ | T1: Swait   ld  comp  arrive@ | MMA t0: seen@ issued@ (dur) | t1: seen@ issued@ (dur)")
     for s in range(64):
         a, b, m = rel[1, s], rel[2, s], rel[0, s]
         if a[3] < 0 and b[3] < 0:
             break
         print(f"{s:3d} | {a[1]-a[0]:6d} {a[2]-a[1]:5d} {a[3]-a[2]:5d} {a[3]:8d} | {b[1]-b[0]:6d} {b[2]-b[1]:5d} {b[3]-b[2]:5d} {b[3]:8d} |"
-              f" {m[1]:7d} {m[2]:7d} ({m[2]-m[1]:4d}) | {m[4]:7d} {m[5]:7d} ({m[5]-m[4]:4d}) | QK0@ {m[0]:7d} QK1@ {m[3]:7d} | S0rdy@ {a[1]:7d} S1rdy@ {b[1]:7d}"
+              f" {m[1]:7d} {m[2]:7d} ({m[2]-m[1]:4d}) | {m[4]:7d} {m[5]:7d} ({m[5]-m[4]:4d})"
               f" || T0 phases: max {a[4]-a[2]:4d} exp {a[5]-a[4]:4d} st+lo {a[6]-a[5]:4d} wait_st+arrive {a[3]-a[6]:4d}"
               f" | T1: max {b[4]-b[2]:4d} exp {b[5]-b[4]:4d} st+lo {b[6]-b[5]:4d} wait_st+arrive {b[3]-b[6]:4d}")
 else:

@@ -125,7 +125,10 @@ def test_our_kernels_vs_the_references_gpu_tir_kernels(built_lib, dtype):
     # ---- fused_rope + append ----
     n = 70
     qkv = rand16(rng, (n, HQ + 2 * HKV, D), dtype)
-    pos = rng.integers(0, 30000, n).astype(np.int32)
+    # positions < 4096: the rotation angle pos / theta^(2d/D) is an fp32 number, and at position 30000 one ulp of it is
+    # 2e-3 rad -- the reference's GPU code and ours (and the reference's own CPU code) then differ by ~1e-2 on |x| ~ 4
+    # purely through the order of the fp32 operations; below 4096 every side agrees to one ulp of the 16-bit output
+    pos = rng.integers(0, 4096, n).astype(np.int32)
     P = 40
     pages0 = rand16(rng, (P, 2, HKV, 16, D), dtype)
     slots = rng.permutation(P * 16)[:n].astype(np.int32)

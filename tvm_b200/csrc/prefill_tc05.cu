@@ -13,24 +13,19 @@
 //               _prefill_kernels.py:318-324) once per item, K_j / V_j tiles of 128 KV rows through a 4-slot ring
 //               (ragged: one 3-D box per 64-col half; paged: eight 16-row page boxes per half, page ids looked up by
 //               the producer lanes).  The next item's Q / K / V loads start while the current item finishes.
-//   warp 1      MMA issuer (one elected thread).  Per Q tile t and KV tile j: S = Q_t K_j^T as eight N = 128 SS MMAs
-//               (K-major operands) into the ONE S region both tiles share, and O_t += P_t V_j as two groups of four TS
-//               MMAs (P read from TMEM, V an MN-major shared-memory operand), one group per 64-column half of P as soon
-//               as that half is ready.  N = 128 is deliberate: an SS-mode MMA never takes fewer than ~64 clk
-//               (scripts/umma_bench.cu: 63 clk at N = 64, 67 at N = 128, 128 at N = 256), so 64-column QK steps run the
-//               tensor pipe at half rate.  The issuer is a small event loop over both tiles (non-blocking mbarrier
-//               polls): PV_t(s) goes out when P_t(s) is ready; QK_t(j+1) goes out when the S region is free, K_{j+1}
-//               has landed and PV_t(j, lower half) has been issued -- i.e. about half a softmax tile before warpgroup
-//               t will ask for it, NOT after PV_t(j) as in a layout where P aliases S.
-//   warps 2, 3  TMEM allocation (512 columns: [0,128) S shared by both tiles, [128,192) P_0, [192,256) P_1 -- fp16, one
-//               32-column half per 64 KV columns --, [256,384) O_0, [384,512) O_1) and, for bf16 inputs, conversion of
-//               every V tile to fp16 in shared memory, so that P can be fp16 (kind::f16 wants one format for A and B).
-//               S lives in TMEM only between the QK^T and the warpgroup's tcgen05.ld (the softmax keeps all 128 values
-//               in registers), so ONE region serves both tiles, and P has columns of its own: the next QK^T of a tile
-//               no longer waits for the PV that reads its P.  r1 aliased P onto S, which chained softmax(j) -> PV(j) ->
-//               QK(j+1) -> softmax(j+1) on every tile: each warpgroup idled ~1100 clk per KV tile (60 % tensor duty).
+//   warp 1      MMA issuer (one elected thread).  Per Q tile t and KV tile j: S_t = Q_t K_j^T as eight N = 128 SS
+//               MMAs (K-major operands) into the tile's 128-column S region, and O_t += P_t V_j as two groups of
+//               four TS MMAs (P read from TMEM, V an MN-major shared-memory operand), one group per 64-column half
+//               of P as soon as that half is ready.  N = 128 is deliberate: an SS-mode MMA never takes fewer than
+//               ~64 clk (scripts/umma_bench.cu: 63 clk at N = 64, 67 at N = 128, 128 at N = 256), so 64-column QK
+//               steps run the tensor pipe at half rate.  P arrives in a fixed order -- (t0, lower half), (t0, upper),
+//               (t1, lower), (t1, upper) -- and QK_t(j+1) is issued right behind the upper-half PV of tile t, so one
+//               Q tile's PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
+//   warps 2, 3  TMEM allocation (512 columns: S_0, S_1 of 128 columns each, O_0, O_1 of 128; P aliases the first 32
+//               columns of the S half it was computed from) and, for bf16 inputs, conversion of every V tile to fp16 in
+//               shared memory, so that P can be fp16 (kind::f16 wants one format for A and B).
 //   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: one thread per row; per KV tile: tcgen05.ld the 128
-//               S values and hand the S region back, mask (diagonal / tail tiles only), ONE row maximum and LAZY rescale decision (O in TMEM is
+//               S values, mask (diagonal / tail tiles only), ONE row maximum and LAZY rescale decision (O in TMEM is
 //               only rescaled when the max grows by more than 2^8), then per 64-column half exp2 (4 of 16 pairs on
 //               the FMA pipe), pack to fp16, tcgen05.st P, arrive.  Each tile stops at its own last visible step
 //               under a causal mask.  The same threads normalise and store O / LSE at the end of an item.
@@ -57,10 +52,6 @@ constexpr int kTileBytes = 2 * kHalfBytes; // 32 KiB
 constexpr int kSlots = 4;                  // K/V ring
 constexpr int kThreads = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
-#ifndef TVMB200_POLL_NS
-#define TVMB200_POLL_NS 64
-#endif
-constexpr uint32_t kPollNs = TVMB200_POLL_NS;  // upper bound of one park of the MMA issuer's event loop
 // P is always fp16 (11 bits; the reference keeps P in fp32): kind::f16 UMMA needs A and B in one format, so for bf16
 // inputs the V tile is converted to fp16 in shared memory by two otherwise idle warps (exact for |v| in [2^-14, 65504],
 // saturating above).  The first tcgen05 versions kept P in bf16 and added a second PV pass with the rounding residual
@@ -82,14 +73,12 @@ struct SmemLayout {
   static constexpr int item = bars + 280;     // int[2]: work-item ring filled by the producer warp
   static constexpr int scan = bars + 288;
 };
-// P_READY / PV_DONE: one barrier per (tile, P half) = index 2 t + h; S_FULL per tile; S_FREE: the warpgroup that owns
-// the S region's content has it in registers.  The kernel is persistent, so every barrier is used across work items:
-// each role keeps running use counts and waits for parity (count & 1).
+// S_FULL / P_READY / PV_DONE: one barrier per (tile, S half) = index 2 t + h.  The kernel is persistent, so every
+// barrier is used across work items: each role keeps running use counts and waits for parity (count & 1).
 enum Bar {
-  Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, S_FREE = 11, P_READY = 13, PV_DONE = 17, Q_EMPTY = 21, ITEM_FULL = 22,
+  Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, Q_EMPTY = 21, ITEM_FULL = 22,
   ITEM_EMPTY = 24, V_CONV = 26, NUM_BARS = 30
 };
-constexpr uint32_t kTmemS = 0, kTmemP = 128, kTmemO = 256;  // TMEM columns: S (shared), P_t = 128 + 64 t, O_t = 256 + 128 t
 
 #ifdef TVMB200_TRACE
 // tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot];
@@ -207,10 +196,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(bar(KV_EMPTY + i), 1);
       mbar_init(bar(V_CONV + i), 2);
     }
-    mbar_init(bar(S_FREE), kRows);
     for (int t = 0; t < 2; ++t) {
-      mbar_init(bar(S_FULL + t), 1);
       for (int h = 0; h < 2; ++h) {
+        mbar_init(bar(S_FULL + 2 * t + h), 1);
         mbar_init(bar(P_READY + 2 * t + h), kRows);
         mbar_init(bar(PV_DONE + 2 * t + h), 1);
       }
@@ -291,11 +279,11 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t kmaj_hi = static_cast<uint32_t>(dkm >> 32), kmaj_lo = static_cast<uint32_t>(dkm);
       const uint32_t mnmaj_hi = static_cast<uint32_t>(dmn >> 32), mnmaj_lo = static_cast<uint32_t>(dmn);
       const uint32_t q_lo = kmaj_lo + (sq >> 4), k_lo = kmaj_lo + (skv >> 4), v_lo = mnmaj_lo + (skv >> 4);
-      // S[0:128) = Q_t x (K tile in `kslot`)^T, one N = 128 MMA per 16-wide slice of the head dim
+      // S_t[0:128) = Q_t x (K tile in `kslot`)^T, one N = 128 MMA per 16-wide slice of the head dim
       auto issue_qk = [&](int t, uint32_t kslot) {
         const uint32_t a0 = q_lo + ((t * kTileBytes) >> 4);
         const uint32_t b0 = k_lo + ((kslot * kTileBytes) >> 4);
-        const uint32_t d = tmem + kTmemS;
+        const uint32_t d = tmem + t * 128;
 #pragma unroll
         for (int s = 0; s < kD / 16; ++s) {
           const uint32_t off = ((s >> 2) * kHalfBytes + (s & 3) * 32) >> 4;
@@ -304,8 +292,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       };
       auto issue_pv = [&](int t, uint32_t vslot, int half, bool acc) {
         const uint32_t b0 = v_lo + ((vslot * kTileBytes + half * (kStep * 128)) >> 4);
-        const uint32_t p0 = tmem + kTmemP + t * 64 + half * 32;
-        const uint32_t d = tmem + kTmemO + t * 128;
+        const uint32_t p0 = tmem + t * 128 + half * kStep;
+        const uint32_t d = tmem + 256 + t * 128;
 #pragma unroll
         for (int s = 0; s < kStep / 16; ++s) {
           // A = P_t[:, 16s .. 16s+15] = 8 packed columns; B = V rows 16s.. (MN-major: LBO = next 64-col half)
@@ -313,8 +301,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
       };
       uint32_t fill = 0, n_q = 0;
-      uint32_t n_qk = 0;                      // QK^T groups issued so far (all items): S_FREE completes once per group
-      uint32_t n_p[2][2] = {{0, 0}, {0, 0}};  // PVs issued so far per (tile, half) = completions of P_READY consumed
+      uint32_t n_p[2][2] = {{0, 0}, {0, 0}};  // real (tile, half) steps issued so far = completions of P_READY waited
       for (int k = 0;; ++k) {
         const int islot = k & 1;
         mbar_wait(bar(ITEM_FULL + islot), (k >> 1) & 1);
@@ -327,103 +314,76 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
         const int n_kv = it.n_kv;
         if (n_kv == 0) continue;
-        const int ns[2] = {it.ns0, it.ns1};                         // 64-column steps per tile
-        const int nk[2] = {(it.ns0 + 1) >> 1, (it.ns1 + 1) >> 1};   // KV tiles per tile
+        auto ns = [&](int t) { return t ? it.ns1 : it.ns0; };
         mbar_wait(bar(Q_FULL), n_q & 1);
         ++n_q;
-        int qk_j[2] = {0, 0};   // next KV tile whose QK^T is to be issued, per Q tile
-        int pv_s[2] = {0, 0};   // next 64-column step whose PV is to be issued, per Q tile
-        bool tail_zeroed = false;
-        // every K_j / V_j slot is handed back once its last reader has been issued (tcgen05.commit covers everything
-        // this thread issued before it)
-        auto k_done = [&](int j) { return (nk[0] <= j || qk_j[0] > j) && (nk[1] <= j || qk_j[1] > j); };
-        // of the (at most two) 64-column steps of tile u that read V_j: how many exist / have been issued
-        auto v_readers = [&](int u, int j) { return max(0, min(ns[u] - 2 * j, 2)); };
-        auto v_issued = [&](int u, int j) { return max(0, min(pv_s[u] - 2 * j, 2)); };
-        while (pv_s[0] < ns[0] || pv_s[1] < ns[1]) {
-          bool progress = false;
-#pragma unroll
+        mbar_wait(bar(KV_FULL + (fill & (kSlots - 1))), (fill / kSlots) & 1);  // K_0
+        tc05::fence_after_sync();
+        if (tc05::elect_one()) {
+          for (int t = 0; t < 2; ++t)
+            if (ns(t) > 0) {
+              issue_qk(t, fill & (kSlots - 1));
+              tc05::commit(bar(S_FULL + 2 * t));
+              tc05::commit(bar(S_FULL + 2 * t + 1));
+            }
+          tc05::commit(bar(KV_EMPTY + (fill & (kSlots - 1))));
+          if (n_kv == 1) tc05::commit(bar(Q_EMPTY));  // no further QK^T in this item
+        }
+        __syncwarp();
+        // The softmax warpgroups hand P over in a fixed order: (t0, lower half), (t0, upper half), (t1, lower),
+        // (t1, upper), next KV tile.  Behind the upper half of a tile goes its QK for KV tile j+1, i.e. one Q tile's
+        // PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t fv = fill + 2 * j + 1, fk1 = fill + 2 * j + 2;
+          const int vslot = fv & (kSlots - 1), k1slot = fk1 & (kSlots - 1);
+          const bool more_k = j + 1 < n_kv;
+          mbar_wait(bar((kConvertV ? V_CONV : KV_FULL) + vslot), (fv / kSlots) & 1);
+          if (kConvertV) tc05::fence_after_sync();
+          if (PAGED && !kConvertV && j == n_kv - 1) {
+            // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
+            // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
+            const int valid = it.kv_len - j * kKV;
+            if (valid < kKV) {
+              for (int e = lane; e < (kKV - valid) * 16; e += 32) {
+                const int r = valid + (e >> 4), c = e & 15;
+                const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+              }
+              fence_proxy_async();
+              __syncwarp();
+            }
+          }
+          if (more_k) mbar_wait(bar(KV_FULL + k1slot), (fk1 / kSlots) & 1);
           for (int t = 0; t < 2; ++t) {
-            // ---- O_t += P_t(s) V_j ----
-            if (pv_s[t] < ns[t]) {
-              const int s = pv_s[t], j = s >> 1, h = s & 1;
-              const uint32_t fv = fill + 2 * j + 1;
-              const int vslot = fv & (kSlots - 1);
-              const uint32_t np_th = h ? n_p[t][1] : n_p[t][0];  // (no run-time array index: keeps the counters in registers)
-              if (mbar_test_wait(bar(P_READY + 2 * t + h), np_th & 1) &&
-                  mbar_test_wait(bar((kConvertV ? V_CONV : KV_FULL) + vslot), (fv / kSlots) & 1)) {
-                TRACE(0, s, 3 * t + 1);
-                if (PAGED && !kConvertV && j == n_kv - 1 && !tail_zeroed) {
-                  // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
-                  // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-                  const int valid = it.kv_len - j * kKV;
-                  if (valid < kKV) {
-                    for (int e = lane; e < (kKV - valid) * 16; e += 32) {
-                      const int r = valid + (e >> 4), c = e & 15;
-                      const uint32_t a = skv + vslot * kTileBytes + (c >> 3) * kHalfBytes + r * 128 + ((c & 7) << 4);
-                      asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                  }
-                  tail_zeroed = true;
+            const int nst = ns(t);
+            if (2 * j >= nst) continue;
+            for (int h = 0; h < 2; ++h) {
+              const int s = 2 * j + h;
+              if (s >= nst) break;
+              mbar_wait(bar(P_READY + 2 * t + h), n_p[t][h] & 1);
+              ++n_p[t][h];
+              TRACE(0, s, 3 * t + 1);
+              tc05::fence_after_sync();
+              const bool last_of_tile = h == 1 || s == nst - 1;
+              if (tc05::elect_one()) {
+                issue_pv(t, vslot, h, s > 0);
+                tc05::commit(bar(PV_DONE + 2 * t + h));
+                if (last_of_tile && 2 * (j + 1) < nst) {
+                  issue_qk(t, k1slot);
+                  tc05::commit(bar(S_FULL + 2 * t));
+                  tc05::commit(bar(S_FULL + 2 * t + 1));
                 }
-                tc05::fence_after_sync();
-                if (h) ++n_p[t][1]; else ++n_p[t][0];
-                ++pv_s[t];
-                const bool release_v = v_issued(0, j) == v_readers(0, j) && v_issued(1, j) == v_readers(1, j);
-                if (tc05::elect_one()) {
-                  issue_pv(t, vslot, h, s > 0);
-                  tc05::commit(bar(PV_DONE + 2 * t + h));
-                  if (release_v) tc05::commit(bar(KV_EMPTY + vslot));
-                }
-                __syncwarp();
-                TRACE(0, s, 3 * t + 2);
-                progress = true;
               }
-            }
-            // ---- S = Q_t K_j^T ----
-            if (qk_j[t] < nk[t]) {
-              const int j = qk_j[t];
-              const uint32_t fk = fill + 2 * j;
-              const int kslot = fk & (kSlots - 1);
-              // just in time: the lower half of P_t(j-1) is out, warpgroup t is on the upper half
-              const bool due = j == 0 || pv_s[t] >= 2 * (j - 1) + 1;
-              if (due && (n_qk == 0 || mbar_test_wait(bar(S_FREE), (n_qk - 1) & 1)) &&
-                  mbar_test_wait(bar(KV_FULL + kslot), (fk / kSlots) & 1)) {
-                tc05::fence_after_sync();
-                ++n_qk;
-                ++qk_j[t];
-                const bool release_k = k_done(j);
-                const bool release_q = qk_j[0] == nk[0] && qk_j[1] == nk[1];
-                TRACE(0, 2 * j, 3 * t);
-                if (tc05::elect_one()) {
-                  issue_qk(t, kslot);
-                  tc05::commit(bar(S_FULL + t));
-                  if (release_k) tc05::commit(bar(KV_EMPTY + kslot));
-                  if (release_q) tc05::commit(bar(Q_EMPTY));  // the item's last QK^T is issued
-                }
-                __syncwarp();
-                progress = true;
-              }
+              __syncwarp();
+              TRACE(0, s, 3 * t + 2);
             }
           }
-          if (!progress && kPollNs > 0) {
-            // nothing was ready: park on the barrier that most likely fires next, for at most ~kPollNs
-            bool qk_blocked = false;
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-              qk_blocked |= qk_j[t] < nk[t] && (qk_j[t] == 0 || pv_s[t] >= 2 * (qk_j[t] - 1) + 1);
-            if (qk_blocked && n_qk > 0 && !mbar_test_wait(bar(S_FREE), (n_qk - 1) & 1)) {
-              tc05::mbar_try_wait_ns(bar(S_FREE), (n_qk - 1) & 1, kPollNs);
-            } else {
-              // (spelled out per tile / half: a run-time index would put the counters in local memory)
-              const bool t0 = pv_s[0] < ns[0] && (pv_s[1] >= ns[1] || pv_s[0] <= pv_s[1]);
-              const int h = (t0 ? pv_s[0] : pv_s[1]) & 1;
-              const uint32_t cnt = t0 ? (h ? n_p[0][1] : n_p[0][0]) : (h ? n_p[1][1] : n_p[1][0]);
-              tc05::mbar_try_wait_ns(bar(P_READY + (t0 ? 0 : 2) + h), cnt & 1, kPollNs);
-            }
+          if (tc05::elect_one()) {
+            tc05::commit(bar(KV_EMPTY + vslot));
+            if (more_k) tc05::commit(bar(KV_EMPTY + k1slot));
+            if (j + 2 == n_kv) tc05::commit(bar(Q_EMPTY));  // the item's last QK^T (of KV tile n_kv-1) is issued
           }
+          __syncwarp();
         }
         fill += 2 * n_kv;
       }
@@ -474,9 +434,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int wq = warp & 3;                // TMEM lane quarter of this warp
     const int r = wq * 32 + lane;           // row within the tile
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t t_s = tmem + lane_addr + kTmemS;            // the S region both tiles share
-    const uint32_t t_p = tmem + lane_addr + kTmemP + t * 64;   // this tile's P (two 32-column halves)
-    const uint32_t t_o = tmem + lane_addr + kTmemO + t * 128;
+    const uint32_t t_s = tmem + lane_addr + t * 128;
+    const uint32_t t_o = tmem + lane_addr + 256 + t * 128;
     const float sc = p.scale_log2;
     uint32_t n_s = 0;             // KV tiles (= QK^T results) of my Q tile consumed so far, all items
     uint32_t n_p[2] = {0, 0};     // my steps so far per S half = my arrivals on P_READY(t, half)
@@ -552,9 +511,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       auto do_half = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32], int hb, int si) {
         const float mneg = -m_used;
         const float2 sc2 = make_float2(sc, sc), mneg2 = make_float2(mneg, mneg);
-        const uint32_t t_pb = t_p + hb * 32;
-        // the PV that read this half's previous content must be done before it is overwritten (almost always is)
-        if (n_p[hb] > 0) mbar_wait(bar(PV_DONE + 2 * t + hb), (n_p[hb] - 1) & 1);
+        const uint32_t t_sb = t_s + hb * kStep;
         ++n_p[hb];
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
         // 2^(s*scale - m) of column pair `pi` of a 32-column chunk (pi is a compile-time index once unrolled)
@@ -583,7 +540,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const float2 a = exp_pair(x1[c], x1[c + 1], c >> 1);
           pk[16 + (c >> 1)] = pack_p<PT>(a.x, a.y);
         }
-        tc05::st32(t_pb, pk);
+        tc05::st32(t_sb, pk);
         sum_a = tc05::fadd2(sum_a, sum_b);
         l += sum_a.x + sum_a.y;
         if (wq == 0) TRACE(1 + t, si, 5);
@@ -599,7 +556,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int j = 0; j < my_tiles; ++j) {
         const bool has_b = 2 * j + 1 < my_ns;       // upper half visible to some row of the tile (CTA-uniform)
         if (wq == 0) TRACE(1 + t, 2 * j, 0);
-        mbar_wait(bar(S_FULL + t), n_s & 1);
+        mbar_wait(bar(S_FULL + 2 * t), n_s & 1);
+        if (has_b) mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);
         ++n_s;
         if (wq == 0) TRACE(1 + t, 2 * j, 1);
         tc05::fence_after_sync();
@@ -611,9 +569,6 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc05::ld32(t_s + 96, sb1);
         }
         tc05::wait_ld();
-        // S is in registers: hand the region to the other tile's (or this tile's next) QK^T
-        tc05::fence_before_sync();
-        mbar_arrive(bar(S_FREE));
         if (wq == 0) TRACE(1 + t, 2 * j, 2);
         const int rem_a = limit - 2 * j * kStep;
         mask_half(sa0, sa1, rem_a);

@@ -206,19 +206,6 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-// one bounded probe: the thread may be parked until the phase completes or ~`ns` nanoseconds have passed
-__device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
-
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   // try_wait already suspends the thread for a HW-defined time slice; spin on it
   while (!mbar_try_wait(bar, parity)) {
