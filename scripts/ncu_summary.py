@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise ncu outputs into profiles/: a launch list CSV (--metrics gpu__time_duration.sum) and/or a
-.ncu-rep full capture (read with `ncu -i ... --page raw --csv`)."""
+.ncu-rep full capture (read with `ncu -i ... --page raw --csv`).
+`--traffic KEY=file.ncu-rep[:kernel substring]` records dram__bytes_read.sum + dram__bytes_write.sum of the (first
+matching) kernel in profiles/ncu_traffic.json, which bench.py reports as `roofline.traffic`."""
 import collections
 import csv
 import io
@@ -45,7 +47,36 @@ def full(path):
                 print(f"| {k} | {r[i]} | {units[i]} |")
 
 
+def traffic(arg):
+    import json
+    import os
+
+    key, rest = arg.split("=", 1)
+    path, _, filt = rest.partition(":")
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if filt in name:
+            rd, wr = (int(float(r[hdr.index(k)])) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            dur = float(r[hdr.index("gpu__time_duration.sum")]) / 1e3
+            dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_traffic.json")
+            d = json.load(open(dst)) if os.path.exists(dst) else {}
+            d[key] = {"bytes": rd + wr, "read": rd, "write": wr, "kernel": name.split("(")[0][:80], "ncu_us": round(dur, 2),
+                      "source": f"ncu --set full, {os.path.basename(path)}: dram read+write of one launch"}
+            json.dump(d, open(dst, "w"), indent=1, sort_keys=True)
+            print(f"{key}: {rd + wr} B ({name[:60]}, {dur:.1f} us)")
+            return
+    print(f"{key}: no kernel matching {filt!r} in {path}")
+
+
 if __name__ == "__main__":
-    for a in sys.argv[1:]:
+    args = sys.argv[1:]
+    while args and args[0] == "--traffic":
+        traffic(args[1])
+        args = args[2:]
+    for a in args:
         (full if a.endswith(".ncu-rep") else launches)(a)
         print()
