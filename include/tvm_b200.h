@@ -180,7 +180,10 @@ TVMB200_API int tvmb200_split_rotary(const void* qkv, const int32_t* position_ma
  *  `num_qo_heads` heads into EVERY rank's gathered buffer `peer_outputs[i]` ([batch, world*num_qo_heads, D], heads
  *  [rank*num_qo_heads, (rank+1)*num_qo_heads)) through NVLink peer pointers, then writes `epoch` to
  *  `peer_flags[i][rank]` with release semantics at system scope.  `output` / `lse` still receive the local result.
- *  A consumer on rank i calls tvmb200_wait_peer_flags(peer_flags[i], world, epoch) before it reads its gathered buffer.
+ *  The same launch then waits until `peer_flags[rank][r]` has reached `epoch` for every r (16-byte peer stores, one
+ *  fence + ticket per block, raise-then-wait in the last block: no cycle), so when the call's stream work completes the
+ *  gathered buffer of THIS rank is complete and stream-ordered consumers may read it; tvmb200_wait_peer_flags remains for
+ *  consumers on other streams.
  *  Epochs must increase by one per call (wrap-around safe); pointers are peer-mapped device pointers of one process
  *  per GPU (e.g. torch.distributed._symmetric_memory buffer_ptrs).  world == 1 degenerates to a local copy.
  */

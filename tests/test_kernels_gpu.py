@@ -151,6 +151,51 @@ def test_split_rotary_append_fused(capi, dtype, apply_rope):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("apply_rope,rotary_dim", [(1, 0), (1, 64), (0, 0)])
+def test_split_rotary_large_batches_match_the_per_token_kernel(capi, dtype, apply_rope, rotary_dim):
+    """>= 1024 tokens take the warp-per-token kernel (page_kernels.cu split_rotary_warp_kernel); its q / k / v and the
+    appended pages must be bit-identical to the one-CTA-per-token kernel, reached by feeding the same tokens in chunks
+    of 512, with and without the fused append, skipped slots (-1) and a partial rotary_dim included."""
+    import torch
+
+    rng = np.random.default_rng(41)
+    n, hq, hkv, d = 2600, 32, 8, 128
+    npages = n // 16 + 8
+    qkv = to_dev(rand16(rng, (n, hq + 2 * hkv, d), dtype), dtype)
+    pos = _i32(rng.integers(0, 8192, n).astype(np.int32))
+    slots = rng.permutation(npages * 16)[:n].astype(np.int32)
+    slots[::37] = -1
+    dslots = _i32(slots)
+    pages0 = to_dev(rand16(rng, (npages, 2, hkv, 16, d), dtype), dtype)
+    tdt = qkv.dtype
+    res = []
+    for chunk in (n, 512):
+        q = torch.empty((n, hq, d), dtype=tdt, device="cuda")
+        k = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+        v = torch.empty((n, hkv, d), dtype=tdt, device="cuda")
+        q2, k2, v2 = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        pages = pages0.clone()
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            capi.split_rotary(qkv[a:b], pos[a:b], q[a:b], k[a:b], v[a:b], apply_rope, 1.0, 5e5, rotary_dim)
+            capi.split_rotary_append(qkv[a:b], pos[a:b], dslots[a:b], q2[a:b], k2[a:b], v2[a:b], pages, apply_rope, 1.0, 5e5,
+                                     rotary_dim)
+        torch.cuda.synchronize()
+        assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2)
+        res.append((q, k, v, pages))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    want = to_np(pages0).copy()
+    ok.transpose_append(want, to_np(res[0][1]), to_np(res[0][2]), slots)
+    assert np.array_equal(to_np(res[0][3]), want)
+    if rotary_dim == 0:
+        wq, wk, wv = ok.split_rotary(to_np(qkv), to_np(pos), hq, hkv, apply_rope, 5e5, 1.0, dtype)
+        assert np.array_equal(to_np(res[0][2]), wv)
+        assert_close("q", to_np(res[0][0]), wq, atol=3.2e-2 if dtype == "bfloat16" else 4e-3)
+        assert_close("k", to_np(res[0][1]), wk, atol=3.2e-2 if dtype == "bfloat16" else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_merge_state_inplace(capi, dtype):
     import torch
 

@@ -523,11 +523,11 @@ template <typename T, int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
                     const int32_t* __restrict__ chunk_off, T* __restrict__ output,
-                    float* __restrict__ lse, int num_qo_heads, const PeerGather pg) {
+                    float* __restrict__ lse, int num_qo_heads) {
   const int b = blockIdx.x, hq = blockIdx.y, dd = threadIdx.x;
   pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
   const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
-  if (pg.n == 0 && c1 - c0 <= 1) return;
+  if (c1 - c0 <= 1) return;
   // The kernel is pure latency (a few KiB per block): keep the loads independent -- the chunk LSEs go to shared
   // memory in one parallel sweep, the partial outputs are read four at a time -- instead of two serial chains.
   __shared__ float s_lse[D];
@@ -561,20 +561,91 @@ decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ 
   const T outv = DT<T>::from_f(acc / den);
   output[(static_cast<int64_t>(b) * num_qo_heads + hq) * D + dd] = outv;
   if (dd == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = mm + log2f(den);
-  if (pg.n > 0) {
-    const int64_t at = (static_cast<int64_t>(b) * pg.total_heads + pg.head_offset + hq) * D + dd;
-    for (int i = 0; i < pg.n; ++i) static_cast<T*>(pg.out[i])[at] = outv;
-    // completion: the block's peer stores are ordered (barrier, then ONE system-scope fence by thread 0 -- fences are
-    // cumulative over what the barrier made visible to it) before its ticket; the last block signals every peer
-    __syncthreads();
-    if (dd == 0) {
+}
+
+// Peer-gather flavour of the merge (pg.n > 0): a block owns whole sequences -- all local heads of sequence b are one
+// contiguous run of Hq_local * D elements in every rank's gathered [n, total_heads, D] buffer -- and every thread slot
+// produces 8 outputs, so each peer receives 16-byte vector stores (a warp writes 512 contiguous bytes per peer: full
+// NVLink write packets; the first version issued 2-byte stores from a (B, Hq) grid).  Completion is one system-scope
+// fence + one ticket per BLOCK (a few hundred per launch instead of B * Hq); the last block raises this rank's epoch in
+// every peer's flag array and then waits, in the same kernel, until every peer's epoch has arrived here: when the
+// launch completes, the gathered buffer of this step is complete on this rank and no separate wait launch is needed.
+// (No cycle: every rank raises its flags before it waits, and waits only for flags.)
+constexpr int kGatherStagedLse = 2048;
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+decode_merge_gather_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                           const int32_t* __restrict__ chunk_off, T* __restrict__ output, float* __restrict__ lse,
+                           int num_qo_heads, int batch, const PeerGather pg) {
+  constexpr int VPH = D / 8;  // 16-byte vectors per head
+  __shared__ float s_lse[kGatherStagedLse];
+  pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
+  const int nslots = num_qo_heads * VPH;
+  const int64_t cs = static_cast<int64_t>(num_qo_heads) * D;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
+    const int nc = c1 - c0;
+    const bool staged = nc * num_qo_heads <= kGatherStagedLse;
+    __syncthreads();  // the previous sequence's readers of s_lse are done
+    if (staged) {
+      for (int i = threadIdx.x; i < nc * num_qo_heads; i += blockDim.x) s_lse[i] = part_lse[static_cast<int64_t>(c0) * num_qo_heads + i];
+      __syncthreads();
+    }
+    for (int slot = threadIdx.x; slot < nslots; slot += blockDim.x) {
+      const int hq = slot / VPH, d0 = (slot - hq * VPH) * 8;
+      auto lse_of = [&](int c) {
+        return staged ? s_lse[c * num_qo_heads + hq] : part_lse[static_cast<int64_t>(c0 + c) * num_qo_heads + hq];
+      };
+      float mm = kNegInit;
+      for (int c = 0; c < nc; ++c) mm = fmaxf(mm, lse_of(c));
+      const float* po = part_o + (static_cast<int64_t>(c0) * num_qo_heads + hq) * D + d0;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float den = 0.f;
+      int c = 0;
+      for (; c + 2 <= nc; c += 2) {
+        const float4 a0 = *reinterpret_cast<const float4*>(po + c * cs), a1 = *reinterpret_cast<const float4*>(po + c * cs + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(po + (c + 1) * cs), b1 = *reinterpret_cast<const float4*>(po + (c + 1) * cs + 4);
+        const float w0 = exp2f(lse_of(c) - mm), w1 = exp2f(lse_of(c + 1) - mm);
+        // (same accumulation order as decode_merge_kernel: the gathered result is bit-identical to the plain path)
+        acc[0] += w0 * a0.x; acc[1] += w0 * a0.y; acc[2] += w0 * a0.z; acc[3] += w0 * a0.w;
+        acc[4] += w0 * a1.x; acc[5] += w0 * a1.y; acc[6] += w0 * a1.z; acc[7] += w0 * a1.w;
+        den += w0;
+        acc[0] += w1 * b0.x; acc[1] += w1 * b0.y; acc[2] += w1 * b0.z; acc[3] += w1 * b0.w;
+        acc[4] += w1 * b1.x; acc[5] += w1 * b1.y; acc[6] += w1 * b1.z; acc[7] += w1 * b1.w;
+        den += w1;
+      }
+      if (c < nc) {
+        const float4 a0 = *reinterpret_cast<const float4*>(po + c * cs), a1 = *reinterpret_cast<const float4*>(po + c * cs + 4);
+        const float w0 = exp2f(lse_of(c) - mm);
+        acc[0] += w0 * a0.x; acc[1] += w0 * a0.y; acc[2] += w0 * a0.z; acc[3] += w0 * a0.w;
+        acc[4] += w0 * a1.x; acc[5] += w0 * a1.y; acc[6] += w0 * a1.z; acc[7] += w0 * a1.w;
+        den += w0;
+      }
+      union { uint4 u; T h[8]; } pk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk.h[i] = DT<T>::from_f(den > 0.f ? acc[i] / den : 0.f);
+      *reinterpret_cast<uint4*>(output + (static_cast<int64_t>(b) * num_qo_heads + hq) * D + d0) = pk.u;
+      if (d0 == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = den > 0.f ? mm + log2f(den) : kNegInit;
+      const int64_t at = (static_cast<int64_t>(b) * pg.total_heads + pg.head_offset + hq) * D + d0;
+#pragma unroll 1
+      for (int i = 0; i < pg.n; ++i) *reinterpret_cast<uint4*>(static_cast<T*>(pg.out[i]) + at) = pk.u;
+    }
+  }
+  // completion: the block's peer stores are ordered (barrier, then ONE system-scope fence by thread 0 -- fences are
+  // cumulative over what the barrier made visible to it) before its ticket; the last block signals every peer
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(pg.done, 1) == static_cast<int>(gridDim.x) - 1) {
+      *pg.done = 0;
       __threadfence_system();
-      const int total = static_cast<int>(gridDim.x * gridDim.y);
-      if (atomicAdd(pg.done, 1) == total - 1) {
-        *pg.done = 0;
-        __threadfence_system();
-        for (int i = 0; i < pg.n; ++i)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pg.flags[i] + pg.rank), "r"(pg.epoch) : "memory");
+      for (int i = 0; i < pg.n; ++i)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pg.flags[i] + pg.rank), "r"(pg.epoch) : "memory");
+      for (int i = 0; i < pg.n; ++i) {
+        uint32_t v;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pg.flags[pg.rank] + i) : "memory");
+        } while (static_cast<int32_t>(v - pg.epoch) < 0);
       }
     }
   }
@@ -706,13 +777,23 @@ static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, in
   cfg.numAttrs = 1;
   TVMB200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, p));
   TVMB200_LAUNCH_OK();
-  if (need_merge) {
+  if (pg.n > 0) {
+    const int nslots = p.num_qo_heads * (D / 8);
+    const int max_blocks = 2 * num_sms();
+    cfg.gridDim = dim3(p.batch < max_blocks ? p.batch : max_blocks);
+    cfg.blockDim = dim3(nslots <= 64 ? 64 : nslots <= 128 ? 128 : 256);
+    cfg.dynamicSmemBytes = 0;
+    TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_gather_kernel<T, D>, static_cast<const float*>(p.part_o),
+                                    static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
+                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads, p.batch, pg));
+    TVMB200_LAUNCH_OK();
+  } else if (need_merge) {
     cfg.gridDim = dim3(p.batch, p.num_qo_heads);
     cfg.blockDim = dim3(D);
     cfg.dynamicSmemBytes = 0;
     TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_kernel<T, D>, static_cast<const float*>(p.part_o),
                                     static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
-                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads, pg));
+                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads));
     TVMB200_LAUNCH_OK();
   }
   return 0;

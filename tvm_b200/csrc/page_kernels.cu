@@ -178,6 +178,131 @@ split_rotary_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ p
   }
 }
 
+// Large token counts (prefill chunks): ONE WARP per token, tokens grid-strided over a grid sized to the machine.  The
+// per-CTA kernel above spends most of a CTA's life in its serial prologue (64 powf + sincosf on two warps, a barrier,
+// then three vectors per thread): 3.6 TB/s on 32768 tokens.  Here the frequency denominators are computed once per
+// CTA, a warp computes its token's (cos, sin) table into its own shared-memory slice (no CTA barrier in the loop), and
+// every lane rotates whole (lower, upper) vector pairs, so each input vector is loaded exactly once.  The arithmetic
+// per element is the very same sequence as above (pos / den -> sincosf -> rope_mix): outputs are bit-identical.
+template <typename T, bool APPEND>
+__global__ void __launch_bounds__(256, 4)
+split_rotary_warp_kernel(const uint4* __restrict__ qkv, const int32_t* __restrict__ position_map,
+                         uint4* __restrict__ q, uint4* __restrict__ k, uint4* __restrict__ v, int64_t ntoken,
+                         int num_qo_heads, int num_kv_heads, int head_dim, int rotary_dim,
+                         int apply_rope, float rope_scale, float rope_theta, uint4* __restrict__ pages,
+                         const int32_t* __restrict__ append_pos, int page_size, const RopeScaling rs) {
+  extern __shared__ float sm_rot[];  // den[rotary_dim/2] | per warp: float2 cs[rotary_dim/2]
+  const int nfreq = rotary_dim / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* den = sm_rot;
+  float2* cs = reinterpret_cast<float2*>(sm_rot + nfreq) + warp * nfreq;
+  pdl_launch_dependents();
+  if (apply_rope > 0)
+    for (int d = threadIdx.x; d < nfreq; d += blockDim.x) den[d] = rope_denominator(d, rotary_dim, rope_theta, rs);
+  __syncthreads();
+  const int row_vecs = head_dim / 8;
+  const int half_vecs = apply_rope > 0 ? rotary_dim / 16 : 0;  // vectors in one rotary half (0: plain split)
+  const int rot_heads = num_qo_heads + num_kv_heads;
+  const int fused_heads = rot_heads + num_kv_heads;
+  const int tail_vecs = row_vecs - 2 * half_vecs;              // unrotated vectors of a q / k head
+  const int warps_per_cta = blockDim.x >> 5;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp; t < ntoken;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_cta) {
+    if (apply_rope > 0) {
+      const float pos = static_cast<float>(position_map[t]) * rope_scale;
+      for (int d = lane; d < nfreq; d += 32) {
+        float sn, c;
+        sincosf(pos / den[d], &sn, &c);
+        cs[d] = make_float2(c, sn);
+      }
+      __syncwarp();
+    }
+    const uint4* src = qkv + t * fused_heads * row_vecs;
+    uint4* page_k = nullptr;  // row of (page, K, head 0, slot) -- head hh adds hh * page_size * row_vecs
+    int64_t v_off = 0;
+    if (APPEND) {
+      const int32_t slot = append_pos[t];
+      if (slot >= 0) {
+        const int64_t pg = slot / page_size, off = slot - pg * page_size;
+        page_k = pages + ((pg * 2 * num_kv_heads) * page_size + off) * row_vecs;
+        v_off = static_cast<int64_t>(num_kv_heads) * page_size * row_vecs;
+      }
+    }
+    const int64_t head_stride = static_cast<int64_t>(page_size) * row_vecs;
+    // rotated (lower, upper) vector pairs of the q and k heads
+#pragma unroll 2
+    for (int idx = lane; idx < rot_heads * half_vecs; idx += 32) {
+      const int h = idx / half_vecs, j = idx - h * half_vecs;
+      const uint4 lo = ldg_nc_v4(src + h * row_vecs + j);
+      const uint4 hi = ldg_nc_v4(src + h * row_vecs + j + half_vecs);
+      const T* le = reinterpret_cast<const T*>(&lo);
+      const T* he = reinterpret_cast<const T*>(&hi);
+      uint4 olo, ohi;
+      T* ol = reinterpret_cast<T*>(&olo);
+      T* oh = reinterpret_cast<T*>(&ohi);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = cs[j * 8 + e];
+        // reference: cos*x + sin*(d < rd/2 ? -x[d+rd/2] : x[d-rd/2]), negation done in dtype
+        ol[e] = DT<T>::from_f(rope_mix(f.x, DT<T>::to_f(le[e]), f.y, DT<T>::to_f(DT<T>::neg(he[e]))));
+        oh[e] = DT<T>::from_f(rope_mix(f.x, DT<T>::to_f(he[e]), f.y, DT<T>::to_f(le[e])));
+      }
+      if (h < num_qo_heads) {
+        uint4* dst = q + (t * num_qo_heads + h) * row_vecs + j;
+        dst[0] = olo;
+        dst[half_vecs] = ohi;
+      } else {
+        const int hh = h - num_qo_heads;
+        uint4* dst = k + (t * num_kv_heads + hh) * row_vecs + j;
+        dst[0] = olo;
+        dst[half_vecs] = ohi;
+        if (APPEND && page_k != nullptr) {
+          uint4* pd = page_k + hh * head_stride + j;
+          pd[0] = olo;
+          pd[half_vecs] = ohi;
+        }
+      }
+    }
+    // unrotated vectors of the q / k heads (rotary_dim < head_dim, or no rotation at all)
+    for (int idx = lane; idx < rot_heads * tail_vecs; idx += 32) {
+      const int h = idx / tail_vecs, j = 2 * half_vecs + idx - h * tail_vecs;
+      const uint4 x = ldg_nc_v4(src + h * row_vecs + j);
+      if (h < num_qo_heads) {
+        q[(t * num_qo_heads + h) * row_vecs + j] = x;
+      } else {
+        const int hh = h - num_qo_heads;
+        k[(t * num_kv_heads + hh) * row_vecs + j] = x;
+        if (APPEND && page_k != nullptr) page_k[hh * head_stride + j] = x;
+      }
+    }
+    // v heads: a copy
+#pragma unroll 2
+    for (int idx = lane; idx < num_kv_heads * row_vecs; idx += 32) {
+      const int hh = idx / row_vecs, j = idx - hh * row_vecs;
+      const uint4 x = ldg_nc_v4(src + (rot_heads + hh) * row_vecs + j);
+      v[(t * num_kv_heads + hh) * row_vecs + j] = x;
+      if (APPEND && page_k != nullptr) page_k[v_off + hh * head_stride + j] = x;
+    }
+    __syncwarp();  // the warp's (cos, sin) slice is rewritten for its next token
+  }
+}
+
+constexpr int64_t kWarpPerTokenMin = 1024;  // below this the one-CTA-per-token kernel has the shorter critical path
+
+template <typename T, bool APPEND>
+static void launch_split_rotary_warp(const void* qkv, const int32_t* position_map, void* q, void* k, void* v, int64_t ntoken,
+                                     int num_qo_heads, int num_kv_heads, int head_dim, int rotary_dim, int apply,
+                                     float rope_scale, float rope_theta, void* pages, const int32_t* append_pos,
+                                     int page_size, cudaStream_t st) {
+  const int warps = 8;
+  const size_t smem = static_cast<size_t>(rotary_dim / 2) * sizeof(float) * (1 + 2 * warps);
+  const int64_t want = (ntoken + warps - 1) / warps, cap = static_cast<int64_t>(num_sms()) * 4;  // one resident wave
+  split_rotary_warp_kernel<T, APPEND><<<static_cast<unsigned>(want < cap ? want : cap), warps * 32, smem, st>>>(
+      static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k), static_cast<uint4*>(v),
+      ntoken, num_qo_heads, num_kv_heads, head_dim, rotary_dim, apply, rope_scale, rope_theta, static_cast<uint4*>(pages),
+      append_pos, page_size, rope_scaling());
+}
+
 // f_split_rotary for the element-wise RoPE variants (gptj / llama4 / yarn, common.cuh RopeVariant): same CTA-per-token
 // layout, but the table holds one (cos, sin) per ELEMENT of the rotary range -- the two halves of a pair may rotate by
 // different angles (llama4, yarn) -- and gptj pairs neighbouring elements (2i, 2i+1) instead of the two halves.
@@ -402,6 +527,16 @@ extern "C" int tvmb200_split_rotary(const void* qkv, const int32_t* position_map
   if (apply && rope_variant().kind != 0)
     return launch_split_rotary_variant(qkv, position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim, rotary_dim,
                                        rope_scale, rope_theta, dtype, st);
+  if (ntoken >= kWarpPerTokenMin) {
+    if (dtype == TVMB200_F16)
+      launch_split_rotary_warp<__half, false>(qkv, position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim,
+                                              rotary_dim, apply, rope_scale, rope_theta, nullptr, nullptr, 16, st);
+    else
+      launch_split_rotary_warp<__nv_bfloat16, false>(qkv, position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim,
+                                                     rotary_dim, apply, rope_scale, rope_theta, nullptr, nullptr, 16, st);
+    TVMB200_LAUNCH_OK();
+    return 0;
+  }
   if (dtype == TVMB200_F16) {
     split_rotary_kernel<__half, false><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(
         static_cast<const uint4*>(qkv), position_map, static_cast<uint4*>(q), static_cast<uint4*>(k),
@@ -438,6 +573,17 @@ extern "C" int tvmb200_split_rotary_append(const void* qkv, const int32_t* q_rop
       return rc;
     return tvmb200_transpose_append(pages, k, v, append_position_map, ntoken, num_pages, num_kv_heads, page_size, head_dim,
                                     dtype, stream);
+  }
+  if (ntoken >= kWarpPerTokenMin) {
+    if (dtype == TVMB200_F16)
+      launch_split_rotary_warp<__half, true>(qkv, q_rope_position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads, head_dim,
+                                             rotary_dim, apply, rope_scale, rope_theta, pages, append_position_map, page_size, st);
+    else
+      launch_split_rotary_warp<__nv_bfloat16, true>(qkv, q_rope_position_map, q, k, v, ntoken, num_qo_heads, num_kv_heads,
+                                                    head_dim, rotary_dim, apply, rope_scale, rope_theta, pages,
+                                                    append_position_map, page_size, st);
+    TVMB200_LAUNCH_OK();
+    return 0;
   }
   if (dtype == TVMB200_F16) {
     split_rotary_kernel<__half, true><<<static_cast<unsigned>(ntoken), 256, smem, st>>>(

@@ -95,8 +95,7 @@ class PeerHeadGather:
         capi.attention_decode_gather(q, pages, page_indptr, page_values, length_info, k_rope_pos_offset,
                                      q_rope_position, output, lse, rotary_mode, rope_scale, rope_theta, sm_scale,
                                      self.buf_ptrs[par], self.flag_ptrs, self.rank, self.epoch)
-        capi.wait_peer_flags(self.flags, self.world, self.epoch)
-        return self.bufs[par]
+        return self.bufs[par]  # the launch itself waits for every peer's epoch (include/tvm_b200.h)
 
     def decode_fused_qkv(self, capi, qkv, q_rope_position, append_position, pages, page_indptr, page_values, length_info,
                          k_rope_pos_offset, output, lse, apply_rope, rope_scale, rope_theta, sm_scale):
@@ -107,5 +106,4 @@ class PeerHeadGather:
                                                length_info, k_rope_pos_offset, output, lse, apply_rope, rope_scale,
                                                rope_theta, sm_scale, self.buf_ptrs[par], self.flag_ptrs, self.rank,
                                                self.epoch)
-        capi.wait_peer_flags(self.flags, self.world, self.epoch)
         return self.bufs[par]
