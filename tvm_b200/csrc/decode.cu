@@ -5,9 +5,13 @@
 //            no split-KV).
 //
 // B200 design (HBM-bound; every KV byte is read from DRAM exactly once):
-//  * a work item is (sequence b, kv head h, chunk of `chunk_pages` pages).  Items are enumerated on
-//    the DEVICE from page_indptr (the callback only gets device arrays), by every CTA redundantly
-//    (block scan in shared memory); a persistent grid of CTAs strides over them (split-KV).
+//  * split-KV by a BALANCED CONTIGUOUS PARTITION: the (sequence, kv head, page) triples, in that order, form one
+//    line of nnz_pages * Hkv page-heads; CTA k of a persistent grid (2 CTAs per SM) owns the k-th `quota` of it, so
+//    every CTA streams the same number of bytes whatever the mix of sequence lengths, and a (sequence, head)
+//    segment is cut only where a CTA boundary falls inside it (2-4 work items per CTA instead of the 8-9 of the
+//    first version's fixed-size chunks: the per-item prologue / epilogue is what kept that one at 0.87-0.95 of the
+//    copy peak depending on the shape).  The walk is done on the DEVICE from page_indptr (the callback only gets
+//    device arrays): one binary search per CTA, then consecutive segments.
 //  * inside an item each WARP owns an independent TMA pipeline: lane 0 issues
 //    cp.async.bulk.tensor (128B-swizzled boxes of 16 slots x 64 elements; one page/head K block is
 //    4 KiB contiguous in HBM) into the warp's private ring of NSTAGE stages and waits on the warp's
@@ -18,9 +22,11 @@
 //    byte and the FMA/cvt pressure of a SIMT kernel (which would make this kernel issue-bound on
 //    B200) disappears.  For bf16, P is split into hi+lo bf16 parts so the PV product
 //    keeps ~16 bits of P (the reference keeps P in fp32).
-//  * the warps of an item merge (m, d, O) through shared memory; items that cover a whole sequence
-//    write O/LSE directly, the others write fp32 partials that decode_merge_kernel reduces
-//    (base-2 LSE merge, same arithmetic as f_merge_inplace).
+//  * the warps of an item merge (m, d, O) through shared memory; an item that covers its whole (sequence, head)
+//    segment writes O/LSE directly, the others write fp32 partials into the CTA's two slots, which
+//    decode_merge_kernel reduces (base-2 LSE merge, same arithmetic as f_merge_inplace).
+#include <cstdlib>
+
 #include "common.cuh"
 
 #include <mutex>
@@ -40,21 +46,25 @@ struct DecodeParams {
   const int32_t* q_rope_position;
   void* output;        // [B, Hq, D]
   float* lse;          // [B, Hq]
-  float* part_o;       // [n_chunks_total, Hq, D] fp32 (normalised partial outputs)
-  float* part_lse;     // [n_chunks_total, Hq]
-  int32_t* chunk_off;  // [B+1] exclusive scan of chunks per sequence (written by CTA 0)
+  float* part_o;       // [2 * grid, group, D] fp32 (normalised partial outputs), slot = 2 * cta + (continues ? 1 : 0)
+  float* part_lse;     // [2 * grid, group]
   int batch;
   int num_qo_heads;
   int num_kv_heads;
   int group;  // Hq / Hkv
-  int chunk_pages;
+  // Balanced split-KV plan: the (sequence, kv head, page) triples in that order form one line of `total` page-heads
+  // (sequence b, head h starts at page_indptr[b] * Hkv + h * np_b); CTA k owns [k * quota, (k + 1) * quota) -- every
+  // CTA streams the same number of bytes, and a (sequence, head) segment is cut only at CTA boundaries.  A piece that
+  // does not cover its whole segment writes an fp32 partial to one of the CTA's two slots: 2k when the segment began
+  // in an earlier CTA and ends here, 2k + 1 when it continues into the next CTA (a CTA has at most one of each).
+  int64_t total;       // nnz_pages * num_kv_heads
+  int quota;           // page-heads per CTA
   // fused split_rotary + transpose_append + decode (FUSED instantiation): q / new k / new v are read from the fused
   // qkv tensor, rotated in the kernel, and the new token is written to its page slot by the item that owns that page
   const void* qkv;              // [B, Hq + 2 Hkv, D]
   const int32_t* append_slot;   // [B] slot id (page * 16 + offset) of the new token = the sequence's last slot, or -1
   void* pages;                  // [P, 2, Hkv, 16, D]
   int fused_apply_rope;
-  int always_partial;  // every item writes fp32 partials, the merge kernel produces all outputs (peer-gather mode)
   int sliding;  // length_info is [3,B]
   int rotary_mode;
   float rope_scale;
@@ -65,7 +75,7 @@ struct DecodeParams {
 
 // shared-memory plan per CTA (dynamic):
 //   [0, NW*NSTAGE*STAGE_BYTES)   K/V stages, 1024-aligned, per warp
-//   then: mbarriers (NW*NSTAGE * 8 B), chunk_off scan (batch+1 ints), scan scratch (40 ints)
+//   then: mbarriers (NW*NSTAGE * 8 B), page_indptr copy (batch+1 ints), 40 spare ints
 template <int D>
 struct DecodeCfg {
   static constexpr int kPage = 16;
@@ -107,21 +117,25 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   // reads -- is touched above this line.  Without the attribute the wait returns at once.
   pdl_wait();
   const int B = p.batch;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const int np = p.page_indptr[b + 1] - p.page_indptr[b];
-    s_chunk_off[b] = max(1, (np + p.chunk_pages - 1) / p.chunk_pages);
-  }
-  __syncthreads();
-  block_exclusive_scan(s_chunk_off, B, s_scan_tmp);
-  if (ROPE || FUSED) {
+  int* s_indptr = s_chunk_off;  // page_indptr staged in shared memory (the item walk below reads it repeatedly)
+  for (int b = threadIdx.x; b <= B; b += blockDim.x) s_indptr[b] = p.page_indptr[b];
+  if (ROPE || FUSED)
     for (int d = threadIdx.x; d < D / 2; d += blockDim.x) s_denom[d] = rope_denominator(d, D, p.rope_theta, p.rs);
-    __syncthreads();
-  }
-  const int total_chunks = s_chunk_off[B];
+  __syncthreads();
   if (blockIdx.x == 0) {
-    for (int b = threadIdx.x; b <= B; b += blockDim.x) p.chunk_off[b] = s_chunk_off[b];
+    // sequences without pages belong to no CTA's range: the empty result (O = 0, lse = the -5e4 sentinel)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      if (s_indptr[b + 1] != s_indptr[b]) continue;
+      for (int i = 0; i < p.num_qo_heads * D; ++i)
+        static_cast<T*>(p.output)[static_cast<int64_t>(b) * p.num_qo_heads * D + i] = DT<T>::from_f(0.f);
+      for (int i = 0; i < p.num_qo_heads; ++i) p.lse[static_cast<int64_t>(b) * p.num_qo_heads + i] = kNegInit;
+    }
   }
-  const int n_items = total_chunks * p.num_kv_heads;
+  // (the line's true length comes from page_indptr; the host's nnz_pages only sized the grid)
+  const int64_t total = static_cast<int64_t>(s_indptr[B]) * p.num_kv_heads < p.total
+                            ? static_cast<int64_t>(s_indptr[B]) * p.num_kv_heads : p.total;
+  const int64_t lin_beg = static_cast<int64_t>(blockIdx.x) * p.quota;
+  const int64_t lin_end = lin_beg + p.quota < total ? lin_beg + p.quota : total;
 
   // per-warp pipeline bookkeeping: number of loads issued / consumed so far (monotonic across items,
   // so mbarrier phase parity is (count / NSTAGE) & 1)
@@ -131,22 +145,31 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
   const int qrow = lane >> 2;           // query head within the group held by this lane (B-frag n)
   const int qc0 = (lane & 3) * 2;       // S^T / O^T column pair (query heads qc0, qc0+1)
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int cg = item / p.num_kv_heads;
-    const int h = item - cg * p.num_kv_heads;
-    // binary search: largest b with chunk_off[b] <= cg
+  // first segment of this CTA's range: the last sequence b with page_indptr[b] * Hkv <= lin_beg (it has pages: a
+  // sequence without pages shares its start with its successor)
+  int b = 0;
+  {
     int lo = 0, hi = B;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (s_chunk_off[mid] <= cg) lo = mid; else hi = mid;
+      if (static_cast<int64_t>(s_indptr[mid]) * p.num_kv_heads <= lin_beg) lo = mid; else hi = mid;
     }
-    const int b = lo;
-    const int chunk = cg - s_chunk_off[b];
-    const int n_chunks_b = s_chunk_off[b + 1] - s_chunk_off[b];
-    const int pg_beg_seq = p.page_indptr[b];
-    const int n_pages_seq = p.page_indptr[b + 1] - pg_beg_seq;
-    const int pg0 = chunk * p.chunk_pages;
-    const int pg1 = min(n_pages_seq, pg0 + p.chunk_pages);
+    b = lo;
+  }
+  int h = 0, pg0 = 0;
+  if (lin_beg < lin_end) {
+    const int np = s_indptr[b + 1] - s_indptr[b];
+    const int off = static_cast<int>(lin_beg - static_cast<int64_t>(s_indptr[b]) * p.num_kv_heads);
+    h = off / np;
+    pg0 = off - h * np;
+  }
+  for (int64_t lin = lin_beg; lin < lin_end;) {
+    const int pg_beg_seq = s_indptr[b];
+    const int n_pages_seq = s_indptr[b + 1] - pg_beg_seq;
+    const int64_t room = lin_end - lin;
+    const int pg1 = n_pages_seq - pg0 <= room ? n_pages_seq : pg0 + static_cast<int>(room);
+    const bool whole = pg0 == 0 && pg1 == n_pages_seq;   // the segment lies inside this CTA's range: final result
+    const int slot = 2 * blockIdx.x + (pg1 < n_pages_seq ? 1 : 0);
 
     // sequence length bookkeeping (_kernel_common.py:155-170)
     int last_page_len, sw_off = 0, sink = 0;
@@ -488,17 +511,25 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
         const bool empty = den == 0.f;
         const float outv = empty ? 0.f : acc / den;
         const float lsev = empty ? kNegInit : mm + log2f(den);
-        if (n_chunks_b == 1 && !p.always_partial) {
+        if (whole) {
           static_cast<T*>(p.output)[(static_cast<int64_t>(b) * p.num_qo_heads + hq) * D + dd] = DT<T>::from_f(outv);
           if (dd == 0) p.lse[static_cast<int64_t>(b) * p.num_qo_heads + hq] = lsev;
         } else {
-          p.part_o[(static_cast<int64_t>(cg) * p.num_qo_heads + hq) * D + dd] = outv;
-          if (dd == 0) p.part_lse[static_cast<int64_t>(cg) * p.num_qo_heads + hq] = lsev;
+          p.part_o[(static_cast<int64_t>(slot) * g + qh) * D + dd] = outv;
+          if (dd == 0) p.part_lse[static_cast<int64_t>(slot) * g + qh] = lsev;
         }
       }
     }
     __syncthreads();  // scratch (= stage memory) is reused by the next item's TMA
+    // next segment of the line: the next head of this sequence, then the next sequence that has pages
+    lin += pg1 - pg0;
+    pg0 = 0;
+    if (++h == p.num_kv_heads) {
+      h = 0;
+      do { ++b; } while (b < B && s_indptr[b + 1] == s_indptr[b]);
+    }
   }
+  // (triggering at the top of the kernel instead, and again at the top of the merge kernel, was measured: no gain)
   pdl_launch_dependents();  // the merge kernel's blocks may be scheduled; they still wait for this grid's completion
 }
 
@@ -518,34 +549,59 @@ struct PeerGather {
   int32_t* done;       // block counter (zero between launches)
 };
 
-// reduce the partial (O, LSE) of sequences that were split into > 1 chunks.  grid = (B, Hq), D threads.
+// The pieces of segment (b, h): CTAs k0 .. k1 of the partition; piece c lives in slot 2 (k0 + c) + (c < nc - 1).
+struct SegPieces {
+  int k0, nc;
+  __device__ __forceinline__ int64_t slot(int c) const { return 2 * static_cast<int64_t>(k0 + c) + (c < nc - 1 ? 1 : 0); }
+};
+__device__ __forceinline__ SegPieces seg_pieces(const int32_t* __restrict__ page_indptr, int b, int h, int num_kv_heads,
+                                                int quota) {
+  const int p0 = page_indptr[b], np = page_indptr[b + 1] - p0;
+  SegPieces sp;
+  if (np == 0) {
+    sp.k0 = 0;
+    sp.nc = 0;
+    return sp;
+  }
+  const int64_t s0 = static_cast<int64_t>(p0) * num_kv_heads + static_cast<int64_t>(h) * np;
+  sp.k0 = static_cast<int>(s0 / quota);
+  sp.nc = static_cast<int>((s0 + np - 1) / quota) - sp.k0 + 1;
+  return sp;
+}
+
+// reduce the partial (O, LSE) of the (sequence, head) segments that were cut by a CTA boundary.  grid = (B, Hq), D threads.
 template <typename T, int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
-                    const int32_t* __restrict__ chunk_off, T* __restrict__ output,
-                    float* __restrict__ lse, int num_qo_heads) {
+                    const int32_t* __restrict__ page_indptr, T* __restrict__ output,
+                    float* __restrict__ lse, int num_qo_heads, int num_kv_heads, int quota) {
   const int b = blockIdx.x, hq = blockIdx.y, dd = threadIdx.x;
-  pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
-  const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
-  if (c1 - c0 <= 1) return;
-  // The kernel is pure latency (a few KiB per block): keep the loads independent -- the chunk LSEs go to shared
+  const int g = num_qo_heads / num_kv_heads, h = hq / g, qh = hq - h * g;
+  // page_indptr is an input of the step (not produced by decode_kernel): the piece list can be worked out before
+  // the programmatic dependency resolves
+  const SegPieces sp = seg_pieces(page_indptr, b, h, num_kv_heads, quota);
+  // launched as a programmatic dependent of decode_kernel: partials are complete past this point.  EVERY block waits,
+  // also the ones with nothing to merge: the completion of this grid must imply the completion of decode_kernel, or the
+  // next step's kernel (a programmatic dependent of THIS grid) could overtake it.
+  pdl_wait();
+  if (sp.nc <= 1) return;  // empty, or written directly by the CTA that held the whole segment
+  const int nc = sp.nc;
+  // The kernel is pure latency (a few KiB per block): keep the loads independent -- the piece LSEs go to shared
   // memory in one parallel sweep, the partial outputs are read four at a time -- instead of two serial chains.
   __shared__ float s_lse[D];
-  const int nc = c1 - c0;
   const bool staged = nc <= D;
   if (staged) {
-    if (dd < nc) s_lse[dd] = part_lse[static_cast<int64_t>(c0 + dd) * num_qo_heads + hq];
+    if (dd < nc) s_lse[dd] = part_lse[sp.slot(dd) * g + qh];
     __syncthreads();
   }
-  auto lse_of = [&](int c) { return staged ? s_lse[c] : part_lse[static_cast<int64_t>(c0 + c) * num_qo_heads + hq]; };
+  auto lse_of = [&](int c) { return staged ? s_lse[c] : part_lse[sp.slot(c) * g + qh]; };
+  auto po = [&](int c) { return part_o[(sp.slot(c) * g + qh) * D + dd]; };
   float mm = kNegInit;
   for (int c = 0; c < nc; ++c) mm = fmaxf(mm, lse_of(c));
-  const float* po = part_o + (static_cast<int64_t>(c0) * num_qo_heads + hq) * D + dd;
-  const int64_t cs = static_cast<int64_t>(num_qo_heads) * D;
   float acc = 0.f, den = 0.f;
   int c = 0;
   for (; c + 4 <= nc; c += 4) {
-    const float v0 = po[(c + 0) * cs], v1 = po[(c + 1) * cs], v2 = po[(c + 2) * cs], v3 = po[(c + 3) * cs];
+    const float v0 = po(c + 0), v1 = po(c + 1), v2 = po(c + 2), v3 = po(c + 3);
     const float w0 = exp2f(lse_of(c + 0) - mm), w1 = exp2f(lse_of(c + 1) - mm);
     const float w2 = exp2f(lse_of(c + 2) - mm), w3 = exp2f(lse_of(c + 3) - mm);
     acc += w0 * v0; den += w0;
@@ -555,7 +611,7 @@ decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ 
   }
   for (; c < nc; ++c) {
     const float w = exp2f(lse_of(c) - mm);
-    acc += w * po[c * cs];
+    acc += w * po(c);
     den += w;
   }
   const T outv = DT<T>::from_f(acc / den);
@@ -571,61 +627,46 @@ decode_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ 
 // every peer's flag array and then waits, in the same kernel, until every peer's epoch has arrived here: when the
 // launch completes, the gathered buffer of this step is complete on this rank and no separate wait launch is needed.
 // (No cycle: every rank raises its flags before it waits, and waits only for flags.)
-constexpr int kGatherStagedLse = 2048;
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 decode_merge_gather_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
-                           const int32_t* __restrict__ chunk_off, T* __restrict__ output, float* __restrict__ lse,
-                           int num_qo_heads, int batch, const PeerGather pg) {
+                           const int32_t* __restrict__ page_indptr, T* __restrict__ output, float* __restrict__ lse,
+                           int num_qo_heads, int num_kv_heads, int quota, int batch, const PeerGather pg) {
   constexpr int VPH = D / 8;  // 16-byte vectors per head
-  __shared__ float s_lse[kGatherStagedLse];
-  pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials are complete past this point
+  pdl_wait();  // launched as a programmatic dependent of decode_kernel: partials and direct outputs are complete
   const int nslots = num_qo_heads * VPH;
-  const int64_t cs = static_cast<int64_t>(num_qo_heads) * D;
+  const int g = num_qo_heads / num_kv_heads;
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-    const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
-    const int nc = c1 - c0;
-    const bool staged = nc * num_qo_heads <= kGatherStagedLse;
-    __syncthreads();  // the previous sequence's readers of s_lse are done
-    if (staged) {
-      for (int i = threadIdx.x; i < nc * num_qo_heads; i += blockDim.x) s_lse[i] = part_lse[static_cast<int64_t>(c0) * num_qo_heads + i];
-      __syncthreads();
-    }
     for (int slot = threadIdx.x; slot < nslots; slot += blockDim.x) {
       const int hq = slot / VPH, d0 = (slot - hq * VPH) * 8;
-      auto lse_of = [&](int c) {
-        return staged ? s_lse[c * num_qo_heads + hq] : part_lse[static_cast<int64_t>(c0 + c) * num_qo_heads + hq];
-      };
-      float mm = kNegInit;
-      for (int c = 0; c < nc; ++c) mm = fmaxf(mm, lse_of(c));
-      const float* po = part_o + (static_cast<int64_t>(c0) * num_qo_heads + hq) * D + d0;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float den = 0.f;
-      int c = 0;
-      for (; c + 2 <= nc; c += 2) {
-        const float4 a0 = *reinterpret_cast<const float4*>(po + c * cs), a1 = *reinterpret_cast<const float4*>(po + c * cs + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(po + (c + 1) * cs), b1 = *reinterpret_cast<const float4*>(po + (c + 1) * cs + 4);
-        const float w0 = exp2f(lse_of(c) - mm), w1 = exp2f(lse_of(c + 1) - mm);
-        // (same accumulation order as decode_merge_kernel: the gathered result is bit-identical to the plain path)
-        acc[0] += w0 * a0.x; acc[1] += w0 * a0.y; acc[2] += w0 * a0.z; acc[3] += w0 * a0.w;
-        acc[4] += w0 * a1.x; acc[5] += w0 * a1.y; acc[6] += w0 * a1.z; acc[7] += w0 * a1.w;
-        den += w0;
-        acc[0] += w1 * b0.x; acc[1] += w1 * b0.y; acc[2] += w1 * b0.z; acc[3] += w1 * b0.w;
-        acc[4] += w1 * b1.x; acc[5] += w1 * b1.y; acc[6] += w1 * b1.z; acc[7] += w1 * b1.w;
-        den += w1;
-      }
-      if (c < nc) {
-        const float4 a0 = *reinterpret_cast<const float4*>(po + c * cs), a1 = *reinterpret_cast<const float4*>(po + c * cs + 4);
-        const float w0 = exp2f(lse_of(c) - mm);
-        acc[0] += w0 * a0.x; acc[1] += w0 * a0.y; acc[2] += w0 * a0.z; acc[3] += w0 * a0.w;
-        acc[4] += w0 * a1.x; acc[5] += w0 * a1.y; acc[6] += w0 * a1.z; acc[7] += w0 * a1.w;
-        den += w0;
-      }
+      const int h = hq / g, qh = hq - h * g;
+      const SegPieces sp = seg_pieces(page_indptr, b, h, num_kv_heads, quota);
+      const int nc = sp.nc;
       union { uint4 u; T h[8]; } pk;
+      T* out_row = output + (static_cast<int64_t>(b) * num_qo_heads + hq) * D + d0;
+      if (nc <= 1) {
+        // final already (written by the CTA that held the whole segment, or the empty result): forward it
+        pk.u = *reinterpret_cast<const uint4*>(out_row);
+      } else {
+        auto lse_of = [&](int c) { return part_lse[sp.slot(c) * g + qh]; };
+        auto po = [&](int c) { return part_o + (sp.slot(c) * g + qh) * D + d0; };
+        float mm = kNegInit;
+        for (int c = 0; c < nc; ++c) mm = fmaxf(mm, lse_of(c));
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float den = 0.f;
+        // (same accumulation order as decode_merge_kernel: the gathered result is bit-identical to the plain path)
+        for (int c = 0; c < nc; ++c) {
+          const float4 a0 = *reinterpret_cast<const float4*>(po(c)), a1 = *reinterpret_cast<const float4*>(po(c) + 4);
+          const float w0 = exp2f(lse_of(c) - mm);
+          acc[0] += w0 * a0.x; acc[1] += w0 * a0.y; acc[2] += w0 * a0.z; acc[3] += w0 * a0.w;
+          acc[4] += w0 * a1.x; acc[5] += w0 * a1.y; acc[6] += w0 * a1.z; acc[7] += w0 * a1.w;
+          den += w0;
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pk.h[i] = DT<T>::from_f(den > 0.f ? acc[i] / den : 0.f);
-      *reinterpret_cast<uint4*>(output + (static_cast<int64_t>(b) * num_qo_heads + hq) * D + d0) = pk.u;
-      if (d0 == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = den > 0.f ? mm + log2f(den) : kNegInit;
+        for (int i = 0; i < 8; ++i) pk.h[i] = DT<T>::from_f(acc[i] / den);
+        *reinterpret_cast<uint4*>(out_row) = pk.u;
+        if (d0 == 0) lse[static_cast<int64_t>(b) * num_qo_heads + hq] = mm + log2f(den);
+      }
       const int64_t at = (static_cast<int64_t>(b) * pg.total_heads + pg.head_offset + hq) * D + d0;
 #pragma unroll 1
       for (int i = 0; i < pg.n; ++i) *reinterpret_cast<uint4*>(static_cast<T*>(pg.out[i]) + at) = pk.u;
@@ -784,16 +825,16 @@ static int launch_decode_impl(const CUtensorMap& tmap, const DecodeParams& p, in
     cfg.blockDim = dim3(nslots <= 64 ? 64 : nslots <= 128 ? 128 : 256);
     cfg.dynamicSmemBytes = 0;
     TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_gather_kernel<T, D>, static_cast<const float*>(p.part_o),
-                                    static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
-                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads, p.batch, pg));
+                                    static_cast<const float*>(p.part_lse), p.page_indptr, static_cast<T*>(p.output), p.lse,
+                                    p.num_qo_heads, p.num_kv_heads, p.quota, p.batch, pg));
     TVMB200_LAUNCH_OK();
   } else if (need_merge) {
     cfg.gridDim = dim3(p.batch, p.num_qo_heads);
     cfg.blockDim = dim3(D);
     cfg.dynamicSmemBytes = 0;
     TVMB200_CUDA(cudaLaunchKernelEx(&cfg, decode_merge_kernel<T, D>, static_cast<const float*>(p.part_o),
-                                    static_cast<const float*>(p.part_lse), static_cast<const int32_t*>(p.chunk_off),
-                                    static_cast<T*>(p.output), p.lse, p.num_qo_heads));
+                                    static_cast<const float*>(p.part_lse), p.page_indptr, static_cast<T*>(p.output), p.lse,
+                                    p.num_qo_heads, p.num_kv_heads, p.quota));
     TVMB200_LAUNCH_OK();
   }
   return 0;
@@ -839,22 +880,23 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   const int sms = num_sms();
   const int ctas_per_sm = 2;
   const int grid_max = sms * ctas_per_sm;
-  int64_t work = static_cast<int64_t>(nnz_pages) * num_kv_heads;  // (page, head) units
-  int chunk_pages = static_cast<int>((work + static_cast<int64_t>(grid_max) * 8 - 1) / (static_cast<int64_t>(grid_max) * 8));
-  chunk_pages = ((chunk_pages + NW - 1) / NW) * NW;
-  if (chunk_pages < 8) chunk_pages = 8;
-  // otherwise every sequence is a single chunk; the peer-gather mode always goes through the merge kernel
-  const bool need_merge = chunk_pages < nnz_pages || pg.n > 0;
-  const int64_t max_chunks = static_cast<int64_t>(nnz_pages) / chunk_pages + batch_size;
-  const int64_t n_items_max = max_chunks * num_kv_heads;
-  const int grid = static_cast<int>(n_items_max < grid_max ? n_items_max : grid_max);
+  // balanced contiguous partition of the nnz_pages * Hkv page-heads (see DecodeParams): one quota per resident CTA,
+  // never below 8 page-heads (tiny batches: fewer CTAs rather than one-page pieces), a multiple of NW so that a full
+  // piece splits evenly over the warps
+  const int64_t total = static_cast<int64_t>(nnz_pages) * num_kv_heads;
+  int64_t quota = (total + grid_max - 1) / grid_max;
+  if (quota < 8) quota = 8;
+  quota = (quota + NW - 1) / NW * NW;
+  TVMB200_CHECK(quota < (1ll << 30), "attention_decode: %lld page-heads are too many", static_cast<long long>(total));
+  int grid = static_cast<int>((total + quota - 1) / quota);
+  if (grid < 1) grid = 1;  // no pages at all: one CTA still writes the empty results
+  const bool need_merge = grid > 1 || pg.n > 0;
 
-  // workspace: chunk_off [B+1] | part_lse [max_chunks, Hq] | part_o [max_chunks, Hq, D]
-  const int64_t off_bytes = ((static_cast<int64_t>(batch_size) + 1) * 4 + 255) / 256 * 256;
-  const int64_t lse_bytes = (max_chunks * num_qo_heads * 4 + 255) / 256 * 256;
-  const int64_t o_bytes = max_chunks * num_qo_heads * head_dim * 4;
+  // workspace: part_lse [2 * grid, group] | part_o [2 * grid, group, D]  (two partial slots per CTA)
+  const int64_t lse_bytes = (static_cast<int64_t>(2) * grid * group * 4 + 255) / 256 * 256;
+  const int64_t o_bytes = static_cast<int64_t>(2) * grid * group * head_dim * 4;
   void* ws = nullptr;
-  if (int rc = get_workspace(off_bytes + lse_bytes + o_bytes, st, &ws)) return rc;
+  if (int rc = get_workspace(lse_bytes + o_bytes, st, &ws)) return rc;
 
   DecodeParams p;
   p.q = q;
@@ -865,15 +907,14 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   p.q_rope_position = q_rope_position;
   p.output = output;
   p.lse = lse;
-  p.chunk_off = static_cast<int32_t*>(ws);
-  p.part_lse = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + off_bytes);
-  p.part_o = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + off_bytes + lse_bytes);
+  p.part_lse = static_cast<float*>(ws);
+  p.part_o = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + lse_bytes);
   p.batch = batch_size;
   p.num_qo_heads = num_qo_heads;
   p.num_kv_heads = num_kv_heads;
   p.group = group;
-  p.chunk_pages = chunk_pages;
-  p.always_partial = pg.n > 0 ? 1 : 0;
+  p.total = total;
+  p.quota = static_cast<int>(quota);
   p.qkv = fused_qkv;
   p.append_slot = append_slot;
   p.pages = const_cast<void*>(pages);
