@@ -120,9 +120,21 @@ TVMB200_API int32_t tvmb200_get_rope_scaling_kind(void);
 /*!
  * \brief Prefill implementation selector (test / profiling hook): 0 = auto (tcgen05 path for eligible shapes
  *        with >= 2048 folded rows, generic mma.sync path otherwise), 1 = force generic, 2 = force tcgen05
- *        wherever it is eligible (head_dim 128, rotary_mode 0, mask none/causal, no sliding window).
+ *        wherever it is eligible (head_dim 128, GQA group 1 / 2 / 4 / 8 / 16; every mask; inline RoPE and sliding
+ *        windows through the pre-pass below).
  */
 TVMB200_API void tvmb200_set_prefill_impl(int impl);
+
+/*!
+ * \brief Prefill launches so far by path (test hook: "no silent fallback"): out[0] the mma.sync kernel, out[1] the tcgen05
+ *        kernel, out[2] the tcgen05 kernel behind the gather / rotate pre-pass.  The pre-pass serves rotary_mode = 1
+ *        (_kernel_common.py:115-127) and the `_sliding_window` flavours (_kernel_common.py:147-170): it writes rotated
+ *        q and position-ordered, rotated K / V into the context's scratch (tvmb200_reserve_workspace sizes it ahead of
+ *        time: 2 * nnz_pages * 16 * Hkv * D * 2 + n * Hq * D * 2 bytes), then the attention runs as a ragged tcgen05 launch.
+ */
+TVMB200_API void tvmb200_debug_prefill_path_counts(int64_t out[3]);
+/*! \brief Pre-pass scratch above this many bytes keeps such a call on the mma.sync kernel (default 2 GiB). */
+TVMB200_API void tvmb200_set_prefill_prepass_cap(int64_t bytes);
 
 /*!
  * \brief f_transpose_append  (ctor arg 13; _page_kernels.py:40-74; called paged_kv_cache.cc:1371,1399)

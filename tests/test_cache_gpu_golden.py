@@ -44,11 +44,17 @@ def run_scenario(name, impl):
             assert_close(f"{name} op {idx} layer {layer} merged lse", to_np(lse), z[f"lse_{idx}"][layer])
         n_checked[0] += 1
 
+    paths0 = capi.prefill_path_counts()
     try:
         replay(name, device=0, on_forward=on_forward, on_kv=on_kv, on_shared=on_shared, on_split=on_split)
     finally:
         capi.set_prefill_impl(0)
     assert n_checked[0] > 0
+    if impl == 2:
+        # every fixture is head_dim 128 / GQA group 4: forced, each prefill callback -- causal, tree-masked, sliding-window,
+        # inline-RoPE -- must have run on the tcgen05 kernel (directly or behind the pre-pass), none on the mma.sync one
+        d = [a - b for a, b in zip(capi.prefill_path_counts(), paths0)]
+        assert d[0] == 0 and d[1] + d[2] > 0, f"{name}: prefill paths (generic, tcgen05, pre-pass) = {d}"
 
 
 @pytest.mark.parametrize("impl", [0, 2])

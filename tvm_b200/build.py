@@ -27,6 +27,7 @@ SOURCES = [
     "decode.cu",
     "prefill_generic.cu",
     "prefill_tc05.cu",
+    "prefill_prepass.cu",
     "prefill_api.cu",
     "kv_cache_host.cc",
     "ffi_api.cc",

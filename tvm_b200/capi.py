@@ -58,6 +58,10 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_set_layer_sliding_window_size.restype = None
     L.tvmb200_set_prefill_impl.argtypes = [c_int]
     L.tvmb200_set_prefill_impl.restype = None
+    L.tvmb200_debug_prefill_path_counts.argtypes = [ctypes.POINTER(ctypes.c_int64)]
+    L.tvmb200_debug_prefill_path_counts.restype = None
+    L.tvmb200_set_prefill_prepass_cap.argtypes = [c_int64]
+    L.tvmb200_set_prefill_prepass_cap.restype = None
     P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
     L.tvmb200_transpose_append.argtypes = [P, P, P, P, I64, I64, I32, I32, I32, c_int, P]
     L.tvmb200_debug_get_kv.argtypes = [P, P, P, P, I64, I64, I64, I64, I32, I32, I32, c_int, P]
@@ -122,6 +126,17 @@ class Context:
 def set_prefill_impl(impl: int) -> None:
     """0 auto, 1 force the generic mma.sync kernel, 2 force the tcgen05 kernel where eligible."""
     lib().tvmb200_set_prefill_impl(impl)
+
+
+def prefill_path_counts() -> tuple[int, int, int]:
+    """prefill launches so far: (mma.sync kernel, tcgen05 kernel, tcgen05 kernel behind the gather / rotate pre-pass)"""
+    out = (ctypes.c_int64 * 3)()
+    lib().tvmb200_debug_prefill_path_counts(out)
+    return int(out[0]), int(out[1]), int(out[2])
+
+
+def set_prefill_prepass_cap(nbytes: int) -> None:
+    lib().tvmb200_set_prefill_prepass_cap(nbytes)
 
 
 def launch_count() -> int:

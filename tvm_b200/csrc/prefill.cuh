@@ -44,7 +44,36 @@ struct PrefillParams {
 int launch_prefill_generic(const PrefillParams& p, bool paged, int total_q_len, int head_dim, int dtype,
                            cudaStream_t st);
 
-// tcgen05 / TMEM path (prefill_tc05.cu): D = 128, rotary_mode 0, mask none / causal, no sliding window
+// gather / rotate pre-pass (prefill_prepass.cu): position-ordered, rotated ragged q / K / V for the tcgen05 kernel
+struct PrepassParams {
+  const void* q;                     // [n_q, hq, 128]  (rotated into q_out when rotary)
+  const int32_t* q_rope_position;    // [n_q]
+  const void* pages;                 // paged source
+  const int32_t* page_indptr;
+  const int32_t* page_values;
+  const int32_t* length_info;        // [B] or [3, B]
+  const void* k;                     // ragged source (rotary only; V is used in place)
+  const int32_t* kv_indptr;
+  const int32_t* k_rope_pos_offset;  // [B]
+  void* q_out;
+  void* k_out;                       // [kv_rows_bound, hkv, 128]
+  void* v_out;                       // paged sources only
+  int32_t* kv_indptr_out;            // paged sources only: [B + 1], written by the pass
+  int64_t n_q;
+  int64_t kv_rows_bound;             // rows k_out / v_out can hold (paged: nnz_pages * 16; ragged: total_kv_len)
+  int batch, hq, hkv;
+  int sliding;                       // length_info is [3, B]
+  int rotary;                        // rotate q and K
+  int tree_k_rope;                   // K row r is rotated at q_rope_position[r] (tree_attn.py:429)
+  float rope_scale, rope_theta;
+  RopeScaling rs;
+};
+int64_t prepass_scratch_bytes(bool paged, bool rotary, int64_t n_q, int hq, int hkv, int64_t kv_rows_bound, int batch,
+                              int64_t off[4]);
+int launch_prefill_prepass(const PrepassParams& a, bool paged, int dtype, cudaStream_t st);
+
+// tcgen05 / TMEM path (prefill_tc05.cu): D = 128, rotary_mode 0, no per-sequence slot remap; masks: none, causal, layer
+// sliding window, token tree
 bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim);
 int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int total_kv_len, int64_t num_pages,
                         int dtype, cudaStream_t st);

@@ -101,6 +101,7 @@ __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
 // one work item = 256 GQA-folded query rows of one sequence x one KV head
 struct Item {
   int h, q_beg, qo_len, row0, tok0, nqt, kv_len, kv_beg, pg_beg, n_pages, ns0, ns1, n_kv;
+  int tree_beg, tree_len;  // kMaskTree: the sequence's rows of tree_order; the mask covers the trailing tree_len columns
 };
 
 template <bool PAGED>
@@ -134,6 +135,12 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
     it.kv_beg = p.kv_indptr[b];
     it.kv_len = p.kv_indptr[b + 1] - it.kv_beg;
   }
+  it.tree_beg = 0;
+  it.tree_len = 0;
+  if (p.mask_mode == kMaskTree) {
+    it.tree_beg = p.tree_indptr[b];
+    it.tree_len = p.tree_indptr[b + 1] - it.tree_beg;
+  }
   const bool causal = p.mask_mode == kMaskCausal;
   // visible KV extent of each tile's last valid token bounds that tile's step count
   auto steps_of = [&](int t) {
@@ -154,7 +161,10 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
 // K / V tiles are in flight -- and its first QK^T issued -- while the softmax warpgroups still normalise and store the
 // previous item's O: TMEM allocation, barrier setup, the Q load from HBM and the O store no longer sit between two
 // tiles' tensor work (they cost ~12 % with one CTA per tile).
-template <typename T, typename PT, bool PAGED>
+// XMASK = true adds the two masks that are not a plain "columns [0, limit)": the per-layer sliding window (a LOWER bound
+// per row, _kernel_common.py:130-144) and the token-tree mask on the trailing tree_len columns (an ancestor test per
+// (row, column), tree_attn.py:48-65).  A separate instantiation: the causal / mask-free kernel keeps its registers.
+template <typename T, typename PT, bool PAGED, bool XMASK>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p, const uint32_t idesc_qk,
@@ -454,6 +464,18 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int tok = R / g;
       const bool valid = t < nqt && tok < qo_len;
       const int limit = causal ? max(0, min(kv_len, kv_len - qo_len + tok + 1)) : kv_len;  // visible columns [0, limit)
+      // XMASK: columns below `lower` are hidden (layer sliding window: the last max(sws - tok - 1, 0) columns are
+      // visible); tree: row = node `tok + tree_len - qo_len` of the tree, whose dfs order must fall into the
+      // [order, subtree end) interval of the column's node
+      int lower = 0, my_order = 0;
+      const int tree_start = kv_len - it.tree_len;
+      if (XMASK) {
+        if (p.mask_mode == kMaskLayerSliding) lower = max(kv_len - max(p.layer_sws - tok - 1, 0), 0);
+        if (p.mask_mode == kMaskTree) {
+          const int child = tok + it.tree_len - qo_len;
+          if (tok < qo_len && child >= 0) my_order = p.tree_order[2 * (it.tree_beg + child)];
+        }
+      }
       float m_used = kNegInit, l = 0.f;
       const int my_ns = t ? it.ns1 : it.ns0;
       if (t >= nqt) continue;
@@ -465,6 +487,32 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           for (int c = 0; c < 32; ++c) {
             if (c >= rem) x0[c] = ninf;
             if (c + 32 >= rem) x1[c] = ninf;
+          }
+        }
+      };
+      // XMASK: hide columns below `lower` and, inside the tree region, columns whose node is not an ancestor-or-self of
+      // the row's node; col0 = sequence column of x0[0]
+      auto mask_extra = [&](uint32_t (&x0)[32], uint32_t (&x1)[32], int col0) {
+        if (__any_sync(0xffffffffu, lower > col0)) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (col0 + c < lower) x0[c] = ninf;
+            if (col0 + 32 + c < lower) x1[c] = ninf;
+          }
+        }
+        if (p.mask_mode == kMaskTree && col0 + kStep > tree_start) {  // (uniform over the CTA)
+          const int2* ord = reinterpret_cast<const int2*>(p.tree_order) + it.tree_beg - tree_start;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int ca = col0 + c, cb = col0 + 32 + c;
+            if (ca >= tree_start && ca < kv_len) {
+              const int2 par = __ldg(ord + ca);
+              if (my_order < par.x || my_order >= par.y) x0[c] = ninf;
+            }
+            if (cb >= tree_start && cb < kv_len) {
+              const int2 par = __ldg(ord + cb);
+              if (my_order < par.x || my_order >= par.y) x1[c] = ninf;
+            }
           }
         }
       };
@@ -540,6 +588,13 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const float2 a = exp_pair(x1[c], x1[c + 1], c >> 1);
           pk[16 + (c >> 1)] = pack_p<PT>(a.x, a.y);
         }
+#ifdef TVMB200_SYNCCHECK
+        // compute-sanitizer's synccheck flags an mbarrier whose phase completes twice without a wait in between
+        // ("missing wait").  PV_DONE is committed for every PV but only waited for when O is rescaled or stored; the
+        // phase a waiter asks for is always its own latest P hand-off, so skipped phases are harmless.  This build
+        // observes every phase (the wait returns at once: S_FULL of this tile was committed behind that PV).
+        if (n_p[hb] > 1) mbar_wait(bar(PV_DONE + 2 * t + hb), (n_p[hb] - 2) & 1);
+#endif
         tc05::st32(t_sb, pk);
         sum_a = tc05::fadd2(sum_a, sum_b);
         l += sum_a.x + sum_a.y;
@@ -572,10 +627,12 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (wq == 0) TRACE(1 + t, 2 * j, 2);
         const int rem_a = limit - 2 * j * kStep;
         mask_half(sa0, sa1, rem_a);
+        if (XMASK) mask_extra(sa0, sa1, 2 * j * kStep);
         const float mx_a = half_max(sa0, sa1);
         float mx_b = -INFINITY;
         if (has_b) {
           mask_half(sb0, sb1, rem_a - kStep);
+          if (XMASK) mask_extra(sb0, sb1, (2 * j + 1) * kStep);
           mx_b = half_max(sb0, sb1);
         }
         if (wq == 0) TRACE(1 + t, 2 * j, 4);
@@ -640,8 +697,9 @@ static std::atomic<int> g_prefill_impl{0};   // 0 auto, 1 force generic, 2 force
 bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim) {
   const int impl = g_prefill_impl.load();
   if (impl == 1) return false;
+  // (inline RoPE and per-sequence sliding windows reach this kernel through the gather / rotate pre-pass of
+  // prefill_api.cu, which hands over position-ordered, rotated ragged K / V: rotary_mode 0, no slot remap)
   if (head_dim != kD || p.rotary_mode != 0 || p.sliding) return false;
-  if (p.mask_mode != kMaskNone && p.mask_mode != kMaskCausal) return false;
   const int g = p.group;
   if (!(g == 1 || g == 2 || g == 4 || g == 8 || g == 16)) return false;
   if (p.batch > 2048) return false;
@@ -657,7 +715,8 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   const int64_t max_items = max_pairs * p.num_kv_heads;
   const int grid = static_cast<int>(max_items < num_sms() ? max_items : num_sms());  // persistent: one CTA per SM
   const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
-  auto kern = prefill_tc05_kernel<T, PT, PAGED>;
+  const bool xmask = p.mask_mode == kMaskLayerSliding || p.mask_mode == kMaskTree;
+  auto kern = xmask ? prefill_tc05_kernel<T, PT, PAGED, true> : prefill_tc05_kernel<T, PT, PAGED, false>;
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
