@@ -127,12 +127,14 @@ TVMB200_API void tvmb200_set_prefill_impl(int impl);
 
 /*!
  * \brief Prefill launches so far by path (test hook: "no silent fallback"): out[0] the mma.sync kernel, out[1] the tcgen05
- *        kernel, out[2] the tcgen05 kernel behind the gather / rotate pre-pass.  The pre-pass serves rotary_mode = 1
+ *        kernel, out[2] the tcgen05 kernel behind the gather / rotate pre-pass, out[3] the launches of out[1] that cut every
+ *        item's KV range into parts merged by a second kernel (few long items, e.g. a token tree against a 32K context).
+ *        The pre-pass serves rotary_mode = 1
  *        (_kernel_common.py:115-127) and the `_sliding_window` flavours (_kernel_common.py:147-170): it writes rotated
  *        q and position-ordered, rotated K / V into the context's scratch (tvmb200_reserve_workspace sizes it ahead of
  *        time: 2 * nnz_pages * 16 * Hkv * D * 2 + n * Hq * D * 2 bytes), then the attention runs as a ragged tcgen05 launch.
  */
-TVMB200_API void tvmb200_debug_prefill_path_counts(int64_t out[3]);
+TVMB200_API void tvmb200_debug_prefill_path_counts(int64_t out[4]);
 /*! \brief Pre-pass scratch above this many bytes keeps such a call on the mma.sync kernel (default 2 GiB). */
 TVMB200_API void tvmb200_set_prefill_prepass_cap(int64_t bytes);
 
@@ -218,6 +220,30 @@ TVMB200_API int tvmb200_attention_decode_fused_qkv_gather(
     int32_t num_kv_heads, int32_t page_size, int32_t head_dim, int sliding_window, int64_t apply_rope, float rope_scale,
     float rope_theta, float sm_scale, int dtype, void* const* peer_outputs, uint32_t* const* peer_flags, int32_t world,
     int32_t rank, uint32_t epoch, tvmb200_stream_t stream);
+
+/*!
+ * \brief nvshmem.KVTransfer (src/runtime/extra/contrib/nvshmem/kv_transfer.cu:38-83, :139-257): push the k / v rows
+ *  [ntokens, local_num_kv_heads, head_dim] of freshly computed tokens into the page pool of the receiving cache(s),
+ *  slot remote_position_map[t] (-1 = skip), TP group starting at PE remote_tp_group_pe_offset[t].  The reference
+ *  addresses receivers through the NVSHMEM symmetric heap; here `remote_pages[pe]` is the peer-mapped device pointer of
+ *  PE pe's pool [*, 2, remote_num_kv_heads, page_size, head_dim] (NVLink stores, system-scope fence before the kernel
+ *  ends = nvshmem_quiet).  Head mapping between differently sharded sender / receiver: kv_transfer.cu:54-66.
+ */
+TVMB200_API int tvmb200_kv_transfer(void* const* remote_pages, const void* k, const void* v,
+                                    const int32_t* remote_position_map, const int32_t* remote_tp_group_pe_offset,
+                                    int64_t ntokens, int32_t local_num_kv_heads, int32_t remote_num_kv_heads,
+                                    int32_t page_size, int32_t head_dim, int32_t local_tp_rank, int32_t num_pe, int dtype,
+                                    tvmb200_stream_t stream);
+/*! \brief nvshmem.KVTransferPageToPage (kv_transfer.cu:84-130, :259-325): the same for rows already in the local pool
+ *  (slot local_position_map[t] of `local_pages`). */
+TVMB200_API int tvmb200_kv_transfer_page_to_page(void* const* remote_pages, const void* local_pages,
+                                                 const int32_t* remote_position_map, const int32_t* local_position_map,
+                                                 const int32_t* remote_tp_group_pe_offset, int64_t ntokens,
+                                                 int32_t local_num_kv_heads, int32_t remote_num_kv_heads,
+                                                 int32_t page_size, int32_t head_dim, int32_t local_tp_rank,
+                                                 int32_t num_pe, int dtype, tvmb200_stream_t stream);
+/*! \brief cudaDeviceEnablePeerAccess(device -> peer) for single-process multi-GPU hosts and tests. */
+TVMB200_API int tvmb200_enable_peer_access(int32_t device, int32_t peer);
 
 /*! \brief Block the stream until flags[r] has reached `epoch` for every r < world (see tvmb200_attention_decode_gather). */
 TVMB200_API int tvmb200_wait_peer_flags(const uint32_t* flags, int32_t world, uint32_t epoch, tvmb200_stream_t stream);

@@ -141,6 +141,29 @@ TVMB200_API int tvmb200_register_vm_builtins(int allow_override);
 
 /* ---- introspection (parity tests, integration glue) ---- */
 /*! \brief out6 = {num_qo_heads, num_kv_heads, head_dim, dtype, num_layers, layer_id_begin_offset}. */
+/*!
+ * \brief Disaggregated prefill -> decode (enable_kv_transfer of the reference's create call, paged_kv_cache.cc:376-405;
+ *  DisaggPrepareRecv / DisaggMarkSend :1220-1301; the transfers in AttentionWithFusedQKV :1374-1394).  The reference puts
+ *  the page pools on the NVSHMEM symmetric heap and addresses a receiver by its PE number; here a receiver is a
+ *  peer-mapped device pointer to its page pool of the layer (tvmb200_cache_pages on the receiving side, exported over
+ *  CUDA IPC / symmetric memory / peer access), registered per PE.  `local_tp_rank` and `remote_num_kv_heads` drive the
+ *  gather / scatter head mapping of kv_transfer.cu:54-66 when sender and receiver shard the KV heads differently.
+ *  Transfers run on a private stream behind the step's rotary / append and are joined back into the caller's stream at
+ *  the last layer of the step.
+ */
+TVMB200_API int tvmb200_cache_enable_kv_transfer(tvmb200_cache_t c, int32_t local_tp_rank, int32_t num_pe,
+                                                 int32_t remote_num_kv_heads);
+TVMB200_API int tvmb200_cache_set_remote_pages(tvmb200_cache_t c, int32_t pe, int64_t local_layer, void* peer_mapped_pages);
+/*! \brief vm.builtin.kv_cache_disagg_prepare_recv: reserves `append_length` slots for the sequence (a BeginForward) and
+ *  returns them run-length compressed, [n, begin_1, length_1, ..., begin_n, length_n]; *out_len = entries needed. */
+TVMB200_API int tvmb200_cache_disagg_prepare_recv(tvmb200_cache_t c, int64_t seq_id, int64_t append_length, int64_t* out,
+                                                  int64_t capacity, int64_t* out_len);
+/*! \brief vm.builtin.kv_cache_disagg_mark_send: tokens from `begin` on go to the slots of the (compressed) map on the
+ *  receiving TP group that starts at PE `recver_pe_offset`. */
+TVMB200_API int tvmb200_cache_disagg_mark_send(tvmb200_cache_t c, int64_t seq_id, int64_t begin,
+                                               const int64_t* compressed_remote_position_map, int64_t n,
+                                               int32_t recver_pe_offset);
+
 TVMB200_API int tvmb200_cache_shape(tvmb200_cache_t c, int64_t* out6);
 /*! \brief The cache's own kernel-set context (borrowed; valid while the cache lives).  It starts as a copy of the
  *  settings current at tvmb200_cache_create; tvmb200_context_enter(ctx) + tvmb200_set_rope_scaling(...) changes

@@ -413,3 +413,43 @@ def attention_prefill_ragged(q, q_indptr, k, v, kv_indptr, q_rope_position, k_ro
         o[qb0:qb1] = round_dtype(ob, dtype)
         lse[qb0:qb1] = lb.astype(np.float32)
     return o, lse
+
+
+def _kv_transfer_target(local_h: int, remote_h: int, local_tp_rank: int, pe_offset: int, h: int):
+    """(remote PE, remote kv head) of local kv head h -- src/runtime/extra/contrib/nvshmem/kv_transfer.cu:54-66."""
+    if local_h <= remote_h:  # gather
+        assert remote_h % local_h == 0
+        gather = remote_h // local_h
+        return pe_offset + local_tp_rank // gather, (local_tp_rank % gather) * local_h + h
+    assert local_h % remote_h == 0  # scatter
+    scatter = local_h // remote_h
+    return pe_offset + local_tp_rank * scatter + h // remote_h, h % remote_h
+
+
+def kv_transfer(remote_pages: list, k: np.ndarray, v: np.ndarray, remote_position_map: np.ndarray,
+                remote_tp_group_pe_offset: np.ndarray, local_tp_rank: int = 0) -> None:
+    """KVTransfer (kv_transfer.cu:38-83): remote_pages[pe] is PE pe's pool [P, 2, Hkv_remote, page, D], updated in place;
+    k / v [ntokens, Hkv_local, D]; position -1 skips the token."""
+    local_h = k.shape[1]
+    for t, pos in enumerate(np.asarray(remote_position_map)):
+        if pos == -1:
+            continue
+        for h in range(local_h):
+            pe, rh = _kv_transfer_target(local_h, remote_pages[0].shape[2], local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
+            page = remote_pages[pe].shape[3]
+            remote_pages[pe][pos // page, 0, rh, pos % page] = k[t, h]
+            remote_pages[pe][pos // page, 1, rh, pos % page] = v[t, h]
+
+
+def kv_transfer_page_to_page(remote_pages: list, local_pages: np.ndarray, remote_position_map: np.ndarray,
+                             local_position_map: np.ndarray, remote_tp_group_pe_offset: np.ndarray,
+                             local_tp_rank: int = 0) -> None:
+    """KVTransferPageToPage (kv_transfer.cu:84-130): rows already in the local pool [P, 2, Hkv_local, page, D]."""
+    local_h, page = local_pages.shape[2], local_pages.shape[3]
+    for t, (rpos, lpos) in enumerate(zip(np.asarray(remote_position_map), np.asarray(local_position_map))):
+        if rpos == -1 or lpos == -1:
+            continue
+        for h in range(local_h):
+            pe, rh = _kv_transfer_target(local_h, remote_pages[0].shape[2], local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
+            for kv in (0, 1):
+                remote_pages[pe][rpos // page, kv, rh, rpos % page] = local_pages[lpos // page, kv, h, lpos % page]

@@ -139,3 +139,26 @@ def test_tc05_prepass_cap_falls_back_loudly_countable(tc05):
         assert after[GENERIC] - before[GENERIC] == 1 and after[PREPASS] == before[PREPASS]
     finally:
         tc05.set_prefill_prepass_cap(2 << 30)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("causal", [0, 1])
+def test_tc05_kv_split_long_context_few_items(tc05, dtype, causal):
+    """few 256-row items against long contexts: every item's KV range is cut into parts (fp32 partials + merge kernel);
+    sequences shorter than the part count, a query longer than one tile pair, causal rows that see nothing in late parts"""
+    rng = np.random.default_rng(69)
+    before = tc05.prefill_path_counts()
+    with took(tc05, TC05):
+        _run_paged_prefill(tc05, rng, [64, 10, 70, 3], [4096 + 64, 3000, 5000, 40], 32, 8, 128, dtype, causal=causal)
+    assert tc05.prefill_path_counts()[3] == before[3] + 1, "the launch did not split its KV ranges"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tc05_kv_split_tree_paged(tc05, dtype):
+    """C5's shape in small: token trees against a long committed context, split KV + tree mask in the last part"""
+    rng = np.random.default_rng(70)
+    trees = [_random_tree(rng, 64), [(k - 1) // 2 if k else -1 for k in range(64)]]
+    before = tc05.prefill_path_counts()
+    with took(tc05, TC05):
+        _run_paged_prefill(tc05, rng, [64, 64], [64 + 4000, 64 + 2500], 32, 8, 128, dtype, tree=_tree_arrays(trees))
+    assert tc05.prefill_path_counts()[3] == before[3] + 1

@@ -29,6 +29,7 @@ SOURCES = [
     "prefill_tc05.cu",
     "prefill_prepass.cu",
     "prefill_api.cu",
+    "kv_transfer.cu",
     "kv_cache_host.cc",
     "ffi_api.cc",
 ]

@@ -56,6 +56,11 @@ def lib() -> ctypes.CDLL:
     L.tvmb200_context_enter.restype = c_void_p
     L.tvmb200_set_layer_sliding_window_size.argtypes = [c_int32]
     L.tvmb200_set_layer_sliding_window_size.restype = None
+    L.tvmb200_kv_transfer.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                      c_int32, c_int32, c_int32, c_int, c_void_p]
+    L.tvmb200_kv_transfer_page_to_page.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                                   c_int32, c_int32, c_int32, c_int32, c_int, c_void_p]
+    L.tvmb200_enable_peer_access.argtypes = [c_int32, c_int32]
     L.tvmb200_set_prefill_impl.argtypes = [c_int]
     L.tvmb200_set_prefill_impl.restype = None
     L.tvmb200_debug_prefill_path_counts.argtypes = [ctypes.POINTER(ctypes.c_int64)]
@@ -128,11 +133,12 @@ def set_prefill_impl(impl: int) -> None:
     lib().tvmb200_set_prefill_impl(impl)
 
 
-def prefill_path_counts() -> tuple[int, int, int]:
-    """prefill launches so far: (mma.sync kernel, tcgen05 kernel, tcgen05 kernel behind the gather / rotate pre-pass)"""
-    out = (ctypes.c_int64 * 3)()
+def prefill_path_counts() -> tuple[int, int, int, int]:
+    """prefill launches so far: (mma.sync kernel, tcgen05 kernel, tcgen05 kernel behind the gather / rotate pre-pass,
+    tcgen05 launches that split their items' KV range)"""
+    out = (ctypes.c_int64 * 4)()
     lib().tvmb200_debug_prefill_path_counts(out)
-    return int(out[0]), int(out[1]), int(out[2])
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
 
 def set_prefill_prepass_cap(nbytes: int) -> None:
@@ -301,6 +307,31 @@ def attention_decode_fused_qkv_gather(qkv, q_rope_position, append_position, pag
         _p(k_rope_pos_offset), _p(output), _p(lse), qkv.shape[0], page_values.shape[0], P, hq, Hkv, page, D,
         1 if length_info.dim() == 2 else 0, apply_rope, rope_scale, rope_theta, sm_scale, _dt(pages),
         ctypes.cast(outs, c_void_p), ctypes.cast(flags, c_void_p), world, rank, epoch & 0xFFFFFFFF, _stream(qkv)))
+
+
+def _ptr_table(ptrs):
+    return (c_void_p * len(ptrs))(*[c_void_p(int(x)) for x in ptrs])
+
+
+def kv_transfer(remote_pages_ptrs, k, v, remote_position_map, remote_tp_group_pe_offset, remote_num_kv_heads, page_size,
+                local_tp_rank=0):
+    """nvshmem.KVTransfer over peer-mapped pointers: remote_pages_ptrs[pe] = device address of PE pe's page pool"""
+    _check(lib().tvmb200_kv_transfer(_ptr_table(remote_pages_ptrs), _p(k), _p(v), _p(remote_position_map),
+                                     _p(remote_tp_group_pe_offset), k.shape[0], k.shape[1], remote_num_kv_heads, page_size,
+                                     k.shape[2], local_tp_rank, len(remote_pages_ptrs), _dt(k), _stream(k)))
+
+
+def kv_transfer_page_to_page(remote_pages_ptrs, local_pages, remote_position_map, local_position_map,
+                             remote_tp_group_pe_offset, remote_num_kv_heads, local_tp_rank=0):
+    _, _, hkv, page, d = local_pages.shape
+    _check(lib().tvmb200_kv_transfer_page_to_page(
+        _ptr_table(remote_pages_ptrs), _p(local_pages), _p(remote_position_map), _p(local_position_map),
+        _p(remote_tp_group_pe_offset), remote_position_map.shape[0], hkv, remote_num_kv_heads, page, d, local_tp_rank,
+        len(remote_pages_ptrs), _dt(local_pages), _stream(local_pages)))
+
+
+def enable_peer_access(device, peer):
+    _check(lib().tvmb200_enable_peer_access(device, peer))
 
 
 def wait_peer_flags(flags, world, epoch):

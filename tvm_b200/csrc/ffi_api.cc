@@ -650,7 +650,7 @@ int impl_launch_count(const TVMFFIAny*, int32_t, TVMFFIAny* result) {
 // kv_cache.py:124-351); register_vm_builtins() re-registers those names onto tvm_b200's cache (kv_cache_host.cc), so the
 // unmodified model runs on the sm_100a kernels.  The cache travels through the VM registers as a ref-counted ffi object
 // (destroyed with its last reference); the callback arguments of the constructor (13..27) are accepted and ignored.
-// Unsupported entries (MLA, disaggregation) are registered too and raise.
+// The MLA entries are registered too and raise.
 // =====================================================================================================
 // The cache travels through the VM registers as a tvm-ffi Function object whose resource handle is the cache and
 // whose deleter destroys it -- a ref-counted ffi Object, like the reference's PagedAttentionKVCacheObj, made with
@@ -733,8 +733,9 @@ int vm_create(void*, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   const int64_t d_qk = arg_int(args, 4, fn, "qk_head_dim"), d_v = arg_int(args, 5, fn, "v_head_dim");
   if (d_qk != d_v) throw Err{"ValueError", fmt("%s: qk_head_dim %ld != v_head_dim %ld (MLA is outside this hot path)", fn, (long)d_qk, (long)d_v)};
   const ShapeView kinds = arg_shape(args, 6, fn, "attn_kinds");
-  if (arg_int(args, 7, fn, "enable_kv_transfer") != 0)
-    throw Err{"ValueError", fmt("%s: enable_kv_transfer (NVSHMEM disaggregation) is not supported", fn)};
+  // enable_kv_transfer: the reference puts the pages on the NVSHMEM symmetric heap (paged_kv_cache.cc:376-405); here the
+  // receivers' pools are registered afterwards with the `kv_cache_set_remote_pages` packed function (peer-mapped pointers)
+  const bool enable_kv_transfer = arg_int(args, 7, fn, "enable_kv_transfer") != 0;
   if (args[11].type_index != kTVMFFINone)
     throw Err{"ValueError", fmt("%s: rope_ext_factors (longrope) is not supported", fn)};
   const Tensor init = arg_tensor(args, 12, fn, "init");
@@ -769,6 +770,10 @@ int vm_create(void*, const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   if (!create) throw Err{"RuntimeError", "libtvm_ffi.so (TVMFFIFunctionCreate) is not loaded"};
   tvmb200_cache_t cache = nullptr;
   cache_rc(tvmb200_cache_create(&c, &cache));
+  if (enable_kv_transfer && tvmb200_cache_enable_kv_transfer(cache, 0, 64, static_cast<int32_t>(hkv)) != 0) {
+    tvmb200_cache_destroy(cache);
+    throw Err{"RuntimeError", tvmb200_last_error()};
+  }
   TVMFFIObjectHandle h = nullptr;
   if (create(cache, cache_handle_call, cache_handle_delete, &h) != 0) {
     tvmb200_cache_destroy(cache);
@@ -1103,8 +1108,97 @@ int vm_merge_attn_output_inplace(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny
   if (rc != 0) return -1;
   TVMB200_VM_END();
 }
+// ffi.Shape(*ints) through tvm-ffi's own constructor (no object layout assumptions)
+int return_shape(const std::vector<int64_t>& v, TVMFFIAny* result) {
+  typedef int (*PFN_GetGlobal)(const TVMFFIByteArray*, TVMFFIObjectHandle*);
+  typedef int (*PFN_Call)(TVMFFIObjectHandle, TVMFFIAny*, int32_t, TVMFFIAny*);
+  typedef int (*PFN_DecRef)(TVMFFIObjectHandle);
+  static PFN_GetGlobal get_global = reinterpret_cast<PFN_GetGlobal>(ffi_sym("TVMFFIFunctionGetGlobal"));
+  static PFN_Call call = reinterpret_cast<PFN_Call>(ffi_sym("TVMFFIFunctionCall"));
+  static PFN_DecRef dec_ref = reinterpret_cast<PFN_DecRef>(ffi_sym("TVMFFIObjectDecRef"));
+  if (!get_global || !call || !dec_ref) throw Err{"RuntimeError", "libtvm_ffi.so is not loaded"};
+  static const char kShape[] = "ffi.Shape";
+  const TVMFFIByteArray name{kShape, sizeof(kShape) - 1};
+  TVMFFIObjectHandle ctor = nullptr;
+  if (get_global(&name, &ctor) != 0) return -1;
+  if (ctor == nullptr) throw Err{"RuntimeError", "tvm-ffi global function ffi.Shape is missing"};
+  std::vector<TVMFFIAny> args(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    args[i].type_index = kTVMFFIInt;
+    args[i].zero_padding = 0;
+    args[i].v_int64 = v[i];
+  }
+  const int rc = call(ctor, args.data(), static_cast<int32_t>(args.size()), result);
+  dec_ref(ctor);
+  return rc;
+}
+// kv_cache_disagg_prepare_recv(cache, seq_id, append_length) -> Shape  (kv_state.cc, paged_kv_cache.cc:1220-1248)
+int vm_disagg_prepare_recv(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_cache_disagg_prepare_recv";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 3, fn);
+  const int64_t len = arg_int(a, 2, fn, "append_length");
+  if (len <= 0) throw Err{"ValueError", fmt("%s: append_length %ld", fn, (long)len)};
+  std::vector<int64_t> out(static_cast<size_t>(2 * len + 1));
+  int64_t used = 0;
+  cache_rc(tvmb200_cache_disagg_prepare_recv(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id"), len, out.data(),
+                                             static_cast<int64_t>(out.size()), &used));
+  out.resize(static_cast<size_t>(used));
+  if (return_shape(out, result) != 0) return -1;
+  TVMB200_VM_END();
+}
+// kv_cache_disagg_mark_send(cache, seq_id, begin, compressed_remote_position_map, recver_pe_offset)  (:1250-1301)
+int vm_disagg_mark_send(void*, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "vm.builtin.kv_cache_disagg_mark_send";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 5, fn);
+  const ShapeView m = arg_shape(a, 3, fn, "compressed_remote_position_map");
+  cache_rc(tvmb200_cache_disagg_mark_send(arg_cache(a, 0, fn), arg_int(a, 1, fn, "seq_id"), arg_int(a, 2, fn, "begin"), m.data,
+                                          m.size, static_cast<int32_t>(arg_int(a, 4, fn, "recver_pe_offset"))));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+// kv_cache_enable_kv_transfer(cache, local_tp_rank, num_pe, remote_num_kv_heads): the geometry NVSHMEM / Disco would supply
+int impl_kv_cache_enable_kv_transfer(const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "kv_cache_enable_kv_transfer";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 4, fn);
+  cache_rc(tvmb200_cache_enable_kv_transfer(arg_cache(a, 0, fn), static_cast<int32_t>(arg_int(a, 1, fn, "local_tp_rank")),
+                                            static_cast<int32_t>(arg_int(a, 2, fn, "num_pe")),
+                                            static_cast<int32_t>(arg_int(a, 3, fn, "remote_num_kv_heads"))));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+// kv_cache_set_remote_pages(cache, pe, local_layer, pages): `pages` = the receiver's pool of that layer as a (peer-mapped)
+// CUDA tensor, an opaque pointer or an integer address
+int impl_kv_cache_set_remote_pages(const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "kv_cache_set_remote_pages";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 4, fn);
+  void* ptr = nullptr;
+  if (a[3].type_index == kTVMFFIInt) ptr = reinterpret_cast<void*>(static_cast<uintptr_t>(a[3].v_int64));
+  else if (a[3].type_index == kTVMFFIOpaquePtr) ptr = a[3].v_ptr;
+  else ptr = arg_tensor(a, 3, fn, "pages").data;
+  cache_rc(tvmb200_cache_set_remote_pages(arg_cache(a, 0, fn), static_cast<int32_t>(arg_int(a, 1, fn, "pe")),
+                                          arg_int(a, 2, fn, "local_layer"), ptr));
+  TVMB200_VM_NONE();
+  TVMB200_VM_END();
+}
+// kv_cache_pages(cache, local_layer) -> opaque pointer of this cache's pool of the layer (what a peer registers)
+int impl_kv_cache_pages(const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "kv_cache_pages";
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 2, fn);
+  void* ptr = nullptr;
+  int64_t np = 0;
+  cache_rc(tvmb200_cache_pages(arg_cache(a, 0, fn), arg_int(a, 1, fn, "local_layer"), &ptr, &np));
+  result->type_index = kTVMFFIOpaquePtr;
+  result->zero_padding = 0;
+  result->v_ptr = ptr;
+  TVMB200_VM_END();
+}
 int vm_unsupported(void*, const TVMFFIAny*, int32_t, TVMFFIAny*) {
-  return raise("RuntimeError", "tvm_b200: this vm.builtin KV-cache entry (MLA / disaggregation) is "
+  return raise("RuntimeError", "tvm_b200: this vm.builtin KV-cache entry (MLA) is "
                                "outside the PagedKVCache MHA hot path and is not implemented");
 }
 
@@ -1129,8 +1223,8 @@ const VmBuiltin kVmBuiltins[] = {
     {"vm.builtin.attention_kv_cache_get_query_positions", vm_query_positions},
     {"vm.builtin.attention_kv_cache_debug_get_kv", vm_debug_get_kv},
     {"vm.builtin.attention_kv_cache_attention_with_fused_qkv", vm_attention_with_fused_qkv},
-    {"vm.builtin.kv_cache_disagg_prepare_recv", vm_unsupported},
-    {"vm.builtin.kv_cache_disagg_mark_send", vm_unsupported},
+    {"vm.builtin.kv_cache_disagg_prepare_recv", vm_disagg_prepare_recv},
+    {"vm.builtin.kv_cache_disagg_mark_send", vm_disagg_mark_send},
     {"vm.builtin.attention_kv_cache_debug_get_kv_mla", vm_unsupported},
     {"vm.builtin.attention_kv_cache_self_attention", vm_self_attention},
     {"vm.builtin.attention_kv_cache_cross_attention", vm_cross_attention},
@@ -1211,6 +1305,9 @@ extern "C" int tvmb200_register_vm_builtins(int allow_override) {
   X(set_rope_scaling, impl_set_rope_scaling)                                  \
   X(set_rope_scaling_yarn, impl_set_rope_scaling_yarn)                        \
   X(launch_count, impl_launch_count)                                          \
+  X(kv_cache_enable_kv_transfer, impl_kv_cache_enable_kv_transfer)            \
+  X(kv_cache_set_remote_pages, impl_kv_cache_set_remote_pages)                \
+  X(kv_cache_pages, impl_kv_cache_pages)                                      \
   X(register_vm_builtins, impl_register_vm_builtins)
 
 namespace {

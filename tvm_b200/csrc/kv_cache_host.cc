@@ -20,6 +20,8 @@
 #include <functional>
 #include <memory>
 #include <numeric>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler injects itself
+#include <set>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -75,6 +77,11 @@ struct Sequence {
   std::vector<int32_t> tree_parent;
   std::vector<int32_t> tree_depth;
   bool committed = true;
+  // disaggregation (attn_utils.h:154-159 KVTransferMetadata): tokens from `kv_send_start` on are pushed to the receiver
+  int64_t kv_send_start = INT64_MAX;
+  std::vector<int32_t> kv_remote_pos;   // receiver slot of token kv_send_start + i
+  int32_t kv_recver_pe_offset = -1;
+  std::vector<int32_t> kv_local_pos;    // slots of the tokens already cached here that still have to be sent
 };
 
 using IVec = std::vector<int32_t>;
@@ -101,6 +108,12 @@ class Cache {
   void BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size);
   void BeginForwardImpl(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size);
   void EndForward() {}
+  // disaggregation (paged_kv_cache.cc:1220-1301)
+  void EnableKVTransfer(int32_t local_tp_rank, int32_t num_pe, int32_t remote_num_kv_heads);
+  void SetRemotePages(int32_t pe, int64_t local_layer, void* peer_ptr);
+  std::vector<int64_t> DisaggPrepareRecv(int64_t seq_id, int64_t append_length);
+  void DisaggMarkSend(int64_t seq_id, int64_t begin, const int64_t* compressed_remote_position_map, int64_t n,
+                      int32_t recver_pe_offset);
   void CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n);
   bool Empty() const {
     return seq_map_.empty() && free_blocks_.size() == blocks_.size() &&
@@ -311,6 +324,17 @@ class Cache {
   }
   void BuildAuxViews();
   void SyncAux(cudaStream_t compute);
+  void EnsureScratch(cudaStream_t compute);
+  std::set<cudaStream_t> scratch_streams_;
+  // ---- disaggregation ----
+  bool kv_transfer_enabled_ = false, transfer_kv_ = false, page_to_page_transfer_kv_ = false;
+  int32_t kv_local_tp_rank_ = 0, kv_num_pe_ = 0, kv_remote_num_kv_heads_ = 0;
+  std::vector<std::vector<void*>> remote_pages_;  // [local layer][pe] peer-mapped page pools of the receivers
+  IVec kv_tx_remote_pos_, kv_tx_recver_, kv_p2p_local_pos_, kv_p2p_remote_pos_, kv_p2p_recver_;
+  View v_kv_tx_remote_pos_, v_kv_tx_recver_, v_kv_p2p_local_pos_, v_kv_p2p_remote_pos_, v_kv_p2p_recver_;
+  cudaStream_t kv_transfer_stream_ = nullptr;
+  cudaEvent_t ev_kv_ready_ = nullptr, ev_kv_sent_ = nullptr;
+  bool kv_sent_pending_ = false, kv_aux_grown_ = false;
   int64_t CheckLayer(int64_t layer_id) const;
   void MarkAttentionDone(cudaStream_t st);
   void SelfAttnInternal(const void* q, const void* k, const void* v, void* o, float* lse, double sm_scale, cudaStream_t st);
@@ -462,6 +486,9 @@ Cache::~Cache() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (void* p : pages_) cudaFree(p);
+  if (kv_transfer_stream_) cudaStreamDestroy(kv_transfer_stream_);
+  if (ev_kv_ready_) cudaEventDestroy(ev_kv_ready_);
+  if (ev_kv_sent_) cudaEventDestroy(ev_kv_sent_);
   cudaFree(tmp_q_);
   cudaFree(tmp_k_);
   cudaFree(tmp_v_);
@@ -482,6 +509,13 @@ Cache::~Cache() {
   if (ev_compute_) cudaEventDestroy(ev_compute_);
   if (ev_attn_done_) cudaEventDestroy(ev_attn_done_);
 }
+
+// NVTX ranges named like the reference's (paged_kv_cache.cc:2374 "SyncAuxArrayToDevice"; the VM wraps every builtin in
+// "RelaxVM: <name>", vm.cc:551): a timeline of a reference-driven run and of this cache line up by name.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 void Cache::Clear() {
   seq_map_.clear();
@@ -804,6 +838,7 @@ void Cache::ConstructTokenTreeMask(const std::vector<Sequence*>& seqs, const int
 // cache stays usable; there is just no current batch (the attention / commit entries refuse to run until a
 // begin_forward completes).  The reference is not transactional (its errors are fatal ICHECKs).
 void Cache::BeginForward(const int64_t* seq_ids, const int64_t* lens, int n, const int64_t* tree, int tree_size) {
+  NvtxRange nvtx_range("vm.builtin.kv_state_begin_forward");
   batch_valid_ = false;
   HCHECK(n > 0, "begin_forward: the batch is empty");
   for (int i = 0; i < n; ++i) {
@@ -1023,6 +1058,12 @@ void Cache::BeginForwardImpl(const int64_t* seq_ids, const int64_t* lens, int n,
   // ---- token -> rope position, token -> KV slot (paged_kv_cache.cc:1150-1183) ----
   q_rope_pos_.clear();
   append_pos_.clear();
+  kv_tx_remote_pos_.clear();
+  kv_tx_recver_.clear();
+  kv_p2p_local_pos_.clear();
+  kv_p2p_remote_pos_.clear();
+  kv_p2p_recver_.clear();
+  transfer_kv_ = page_to_page_transfer_kv_ = false;
   for (int i = 0; i < n; ++i) {
     const int64_t len = lens[i];
     const Block& blk = blocks_[seqs[i]->last_block_idx];
@@ -1044,6 +1085,27 @@ void Cache::BeginForwardImpl(const int64_t* seq_ids, const int64_t* lens, int n,
         const int32_t o = pos_in_block - blk.sink_length + blk.sliding_window_offset;
         append_pos_.push_back(blk.page_ids[o / ps] * ps + o % ps);
       }
+      // paged_kv_cache.cc:1184-1196: where the token goes on the receiving side (if it is sent at all)
+      const int64_t pos_in_seq = seqs[i]->seq_length - len + pos;
+      if (pos_in_seq < seqs[i]->kv_send_start) {
+        kv_tx_remote_pos_.push_back(-1);
+        kv_tx_recver_.push_back(-1);
+      } else {
+        transfer_kv_ = true;
+        const size_t at = static_cast<size_t>(pos_in_seq - seqs[i]->kv_send_start);
+        HCHECK(at < seqs[i]->kv_remote_pos.size(), "sequence %ld sends more tokens than the receiver prepared", (long)seq_ids[i]);
+        kv_tx_remote_pos_.push_back(seqs[i]->kv_remote_pos[at]);
+        kv_tx_recver_.push_back(seqs[i]->kv_recver_pe_offset);
+      }
+    }
+    if (!seqs[i]->kv_local_pos.empty()) {  // :1197-1210 rows cached before mark_send: page-to-page, once
+      page_to_page_transfer_kv_ = true;
+      for (size_t k = 0; k < seqs[i]->kv_local_pos.size(); ++k) {
+        kv_p2p_local_pos_.push_back(seqs[i]->kv_local_pos[k]);
+        kv_p2p_remote_pos_.push_back(seqs[i]->kv_remote_pos[k]);
+        kv_p2p_recver_.push_back(seqs[i]->kv_recver_pe_offset);
+      }
+      seqs[i]->kv_local_pos.clear();
     }
   }
   BuildAuxViews();
@@ -1078,9 +1140,13 @@ void Cache::BuildAuxViews() {
   v_cur_len_indptr_ = Put(cur_len_indptr_);
   v_k_ragged_rope_off_ = Put(k_ragged_rope_off_);
   v_append_pos_ = Put(append_pos_);
-  // (five kv-transfer maps of total_append_ elements each live here in the reference; disaggregation is out of scope,
-  //  the offsets they would occupy are skipped so that later views keep the reference's byte offsets)
-  stage_off_ += 2 * ((total_append_ + 3) / 4 * 4);
+  // the five kv-transfer maps (SyncAuxArrayToDevice steps 10-14, paged_kv_cache.cc:2484-2505): two of total_append_
+  // elements (-1 = not sent), three page-to-page ones that are empty except right after a mark_send
+  v_kv_tx_remote_pos_ = Put(kv_tx_remote_pos_);
+  v_kv_tx_recver_ = Put(kv_tx_recver_);
+  v_kv_p2p_local_pos_ = Put(kv_p2p_local_pos_);
+  v_kv_p2p_remote_pos_ = Put(kv_p2p_remote_pos_);
+  v_kv_p2p_recver_ = Put(kv_p2p_recver_);
   for (int d = 0; d < num_depths_; ++d) {
     if (!is_chain_on_depths_[d]) {
       v_tree_mask_[d] = Put(tree_mask_[d]);
@@ -1092,7 +1158,27 @@ void Cache::BuildAuxViews() {
   dirty_ = true;
 }
 
+// Device scratch of this cache's kernel set on (device, compute stream): the split-KV partials of decode and -- for
+// caches that rotate inline or slide (rope mode "inline", sliding-window support, per-layer windows: the flavours the
+// tcgen05 prefill reaches through its gather / rotate pre-pass) -- rotated q of a full prefill chunk plus position-
+// ordered K / V of every page of one layer.  Reserved the FIRST time a stream is seen, so that no later callback
+// allocates (the stream is a per-call argument: it cannot be done in the constructor).
+void Cache::EnsureScratch(cudaStream_t compute) {
+  if (scratch_streams_.count(compute)) return;
+  int64_t bytes = int64_t(32) << 20;
+  if (rope_mode_ == TVMB200_ROPE_INLINE || support_sw_ || support_layer_sw_) {
+    const int64_t row = head_dim_ * 2;
+    const int64_t want = prefill_chunk_ * num_qo_heads_ * row + 2 * num_total_pages_ * page_size_ * num_kv_heads_ * row +
+                         (reserved_seqs_ + 64) * 4 + 4096;
+    if (want > bytes && want <= (int64_t(2) << 30)) bytes = want;
+  }
+  HCHECK(tvmb200_reserve_workspace_stream(device_, bytes, compute) == 0, "%s", tvmb200_last_error());
+  scratch_streams_.insert(compute);
+}
+
 void Cache::SyncAux(cudaStream_t compute) {
+  NvtxRange nvtx_range("SyncAuxArrayToDevice");
+  if (!planning_only()) EnsureScratch(compute);
   if (!dirty_ || planning_only()) {
     dirty_ = false;
     return;
@@ -1247,6 +1333,7 @@ void Cache::MarkAttentionDone(cudaStream_t st) {
 
 void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void* qkv, void* o, int64_t rows,
                                   cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_attention_with_fused_qkv");
   const int64_t local = CheckLayer(layer_id);
   const int64_t n = total_append_;
   HCHECK(n <= rows, "qkv has %ld rows but the batch appends %ld tokens", (long)rows, (long)n);
@@ -1272,8 +1359,13 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
   const bool fuse_step = !plan && append_before_attn_ && num_depths_ == 1 && use_decode_kernel_[0] &&
                          is_chain_on_depths_[0] && !page_indices_[0].empty() && rope_mode_ != TVMB200_ROPE_INLINE && d == 128 &&
                          attn_kinds_[layer_id] != TVMB200_ATTN_MHA_SLIDING && !support_sw_ &&
-                         static_cast<int64_t>(v_qo_indptr_[0].size - 1) == n &&
+                         static_cast<int64_t>(v_qo_indptr_[0].size - 1) == n && !transfer_kv_ &&
                          (apply_rope == 0 || tvmb200_get_rope_scaling_kind() <= TVMB200_ROPE_SCALING_LLAMA3);
+  // the previous layer's transfer still reads tmp_k_ / tmp_v_ (paged_kv_cache.cc:1356-1359)
+  if (!plan && kv_sent_pending_) {
+    HCUDA(cudaStreamWaitEvent(st, ev_kv_sent_, 0));
+    kv_sent_pending_ = false;
+  }
   if (append_before_attn_ && fuse_step) {
     trace_append();
   } else if (append_before_attn_) {
@@ -1288,15 +1380,129 @@ void Cache::AttentionWithFusedQKV(int64_t layer_id, double sm_scale, const void*
                             static_cast<float>(rotary_scale_), static_cast<float>(rotary_theta_), dtype_, st));
   }
 
+  // Part 4: KV transfer (paged_kv_cache.cc:1374-1394) on the transfer stream, overlapping the attention below: first
+  // the rows this cache already held when the sequence was marked (page to page), then this step's fresh k / v rows
+  if (page_to_page_transfer_kv_ || transfer_kv_) {
+    HCHECK(kv_transfer_enabled_, "a sequence is marked for KV transfer but the cache was not set up for it (tvmb200_cache_enable_kv_transfer)");
+    TRACE("kv_transfer", {SI(page_to_page_transfer_kv_ ? static_cast<int64_t>(kv_p2p_local_pos_.size()) : 0), SI(transfer_kv_ ? n : 0)});
+    if (!plan) {
+      void* const* table = remote_pages_[local].data();
+      HCUDA(cudaEventRecord(ev_kv_ready_, st));
+      HCUDA(cudaStreamWaitEvent(kv_transfer_stream_, ev_kv_ready_, 0));
+      if (page_to_page_transfer_kv_)
+        Rc(tvmb200_kv_transfer_page_to_page(table, pages, dev(v_kv_p2p_remote_pos_), dev(v_kv_p2p_local_pos_),
+                                            dev(v_kv_p2p_recver_), static_cast<int64_t>(kv_p2p_local_pos_.size()), hkv,
+                                            kv_remote_num_kv_heads_, ps, d, kv_local_tp_rank_, kv_num_pe_, dtype_,
+                                            kv_transfer_stream_));
+      if (transfer_kv_)
+        Rc(tvmb200_kv_transfer(table, tmp_k_, tmp_v_, dev(v_kv_tx_remote_pos_), dev(v_kv_tx_recver_), n, hkv,
+                               kv_remote_num_kv_heads_, ps, d, kv_local_tp_rank_, kv_num_pe_, dtype_, kv_transfer_stream_));
+      HCUDA(cudaEventRecord(ev_kv_sent_, kv_transfer_stream_));
+      kv_sent_pending_ = true;
+    }
+  }
+
   // Part 5: attention
   AttentionInternal(layer_id, tmp_q_, tmp_k_, tmp_v_, o, sm_scale, fuse_step ? qkv : nullptr, st);
   if (!append_before_attn_) append();
+  if (!plan && kv_sent_pending_ && local == num_layers_ - 1) {
+    // last layer of the step: the caller's stream owns the transfers from here on (EndForward has no stream argument)
+    HCUDA(cudaStreamWaitEvent(st, ev_kv_sent_, 0));
+    kv_sent_pending_ = false;
+  }
   MarkAttentionDone(st);
+}
+
+void Cache::EnableKVTransfer(int32_t local_tp_rank, int32_t num_pe, int32_t remote_num_kv_heads) {
+  HCHECK(num_pe >= 1 && num_pe <= 64 && local_tp_rank >= 0 && remote_num_kv_heads > 0, "bad KV-transfer geometry");
+  kv_transfer_enabled_ = true;
+  kv_local_tp_rank_ = local_tp_rank;
+  kv_num_pe_ = num_pe;
+  kv_remote_num_kv_heads_ = remote_num_kv_heads;
+  remote_pages_.assign(static_cast<size_t>(num_layers_), std::vector<void*>(static_cast<size_t>(num_pe), nullptr));
+  // room for the three page-to-page maps (up to every cached token of the batch's sequences): the merged aux buffers grow
+  const int64_t extra = 3 * ((num_total_pages_ * page_size_ + 3) / 4 * 4);
+  if (!kv_aux_grown_) {
+    aux_capacity_ += extra;
+    stage_.resize(static_cast<size_t>(aux_capacity_), 0);
+    if (!planning_only()) {
+      HCUDA(cudaSetDevice(device_));
+      HCUDA(cudaDeviceSynchronize());
+      for (int i = 0; i < 2; ++i) {
+        HCUDA(cudaFree(aux_dev_[i]));
+        HCUDA(cudaFreeHost(stage_pinned_[i]));
+        HCUDA(cudaMalloc(reinterpret_cast<void**>(&aux_dev_[i]), aux_capacity_ * 4));
+        HCUDA(cudaMallocHost(reinterpret_cast<void**>(&stage_pinned_[i]), aux_capacity_ * 4));
+        aux_used_[i] = false;
+      }
+      dirty_ = true;
+    }
+    kv_aux_grown_ = true;
+  }
+  if (!planning_only() && kv_transfer_stream_ == nullptr) {
+    HCUDA(cudaStreamCreateWithFlags(&kv_transfer_stream_, cudaStreamNonBlocking));
+    HCUDA(cudaEventCreateWithFlags(&ev_kv_ready_, cudaEventDisableTiming));
+    HCUDA(cudaEventCreateWithFlags(&ev_kv_sent_, cudaEventDisableTiming));
+  }
+}
+
+void Cache::SetRemotePages(int32_t pe, int64_t local_layer, void* peer_ptr) {
+  HCHECK(kv_transfer_enabled_, "tvmb200_cache_enable_kv_transfer first");
+  HCHECK(pe >= 0 && pe < kv_num_pe_ && local_layer >= 0 && local_layer < num_layers_, "remote pages: pe %d / layer %ld out of range", pe, (long)local_layer);
+  remote_pages_[static_cast<size_t>(local_layer)][static_cast<size_t>(pe)] = peer_ptr;
+}
+
+// DisaggPrepareRecv (paged_kv_cache.cc:1220-1248): reserve the slots through BeginForward and hand their ids back,
+// run-length compressed as [n, begin_1, length_1, ..., begin_n, length_n]
+std::vector<int64_t> Cache::DisaggPrepareRecv(int64_t seq_id, int64_t append_length) {
+  HCHECK(append_length > 0, "disagg_prepare_recv: append length %ld", (long)append_length);
+  const int64_t ids[1] = {seq_id}, lens[1] = {append_length};
+  BeginForward(ids, lens, 1, nullptr, 0);
+  HCHECK(static_cast<int64_t>(append_pos_.size()) == append_length, "append position map size mismatch");
+  std::vector<int64_t> out{1, append_pos_[0]};
+  for (int64_t i = 1; i < append_length; ++i) {
+    if (append_pos_[i] != append_pos_[i - 1] + 1) {
+      out.push_back(append_pos_[i - 1] - out.back() + 1);
+      ++out[0];
+      out.push_back(append_pos_[i]);
+    }
+  }
+  out.push_back(append_pos_.back() - out.back() + 1);
+  return out;
+}
+
+// DisaggMarkSend (paged_kv_cache.cc:1250-1301)
+void Cache::DisaggMarkSend(int64_t seq_id, int64_t begin, const int64_t* comp, int64_t n, int32_t recver_pe_offset) {
+  HCHECK(kv_transfer_enabled_, "disagg_mark_send: the cache was not set up for KV transfer (tvmb200_cache_enable_kv_transfer)");
+  auto it = seq_map_.find(seq_id);
+  HCHECK(it != seq_map_.end(), "The sequence \"%ld\" cannot be found in KV cache.", (long)seq_id);
+  HCHECK(n >= 1 && comp[0] >= 0 && n == 2 * comp[0] + 1, "disagg_mark_send: malformed compressed position map");
+  Sequence& seq = it->second;
+  seq.kv_send_start = begin;
+  seq.kv_remote_pos.clear();
+  for (int64_t i = 0; i < comp[0]; ++i)
+    for (int64_t j = 0; j < comp[2 * i + 2]; ++j) seq.kv_remote_pos.push_back(static_cast<int32_t>(comp[2 * i + 1] + j));
+  seq.kv_recver_pe_offset = recver_pe_offset;
+  seq.kv_local_pos.clear();
+  if (begin >= seq.seq_length) return;
+  // tokens [begin, seq_length) are cached already: their slots, oldest first
+  HCHECK(static_cast<int64_t>(seq.kv_remote_pos.size()) > seq.seq_length - begin, "Need at least one token to prefill");
+  const int64_t want = seq.seq_length - begin;
+  std::vector<int32_t> rev;
+  for (int32_t b = seq.last_block_idx; b != -1 && static_cast<int64_t>(rev.size()) < want; b = blocks_[b].parent_idx) {
+    const Block& blk = blocks_[b];
+    for (int32_t i = blk.seq_length - 1; i >= 0 && static_cast<int64_t>(rev.size()) < want; --i) {
+      const int32_t off = i < blk.sink_length ? i : i - blk.sink_length + blk.sliding_window_offset;
+      rev.push_back(blk.page_ids[off / page_size_] * static_cast<int32_t>(page_size_) + off % static_cast<int32_t>(page_size_));
+    }
+  }
+  seq.kv_local_pos.assign(rev.rbegin(), rev.rend());
 }
 
 // SelfAttention (paged_kv_cache.cc:1404-1445): q [n, Hq, D] against the step's own k / v [n, Hkv, D] (not the cache).
 void Cache::SelfAttention(int64_t layer_id, double sm_scale, const void* q, const void* k, const void* v, void* o,
                           float* lse, int64_t rows, cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_self_attention");
   CheckLayer(layer_id);
   HCHECK(attn_kinds_[layer_id] == TVMB200_ATTN_MHA, "self_attention: layer %ld is not an MHA layer (MLA is not built)",
          (long)layer_id);
@@ -1310,6 +1516,7 @@ void Cache::SelfAttention(int64_t layer_id, double sm_scale, const void* q, cons
 // CrossAttention (paged_kv_cache.cc:1447-1485): q against the cached KV of the layer, no causal mask.
 void Cache::CrossAttention(int64_t layer_id, double sm_scale, const void* q, void* o, float* lse, int64_t rows,
                            cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_cross_attention");
   CheckLayer(layer_id);
   HCHECK(attn_kinds_[layer_id] == TVMB200_ATTN_MHA, "cross_attention: layer %ld is not an MHA layer (MLA is not built)",
          (long)layer_id);
@@ -1324,6 +1531,7 @@ void Cache::CrossAttention(int64_t layer_id, double sm_scale, const void* q, voi
 // (pages already hold the step's tokens when the append ran before the source layer's attention).
 void Cache::AttentionWithSharedKV(int64_t source_layer_id, double sm_scale, const void* q, const void* cur_k,
                                   const void* cur_v, void* o, int64_t rows, cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_attention_with_shared_kv");
   CheckLayer(source_layer_id);
   HCHECK(rows == total_append_, "attention_with_shared_kv: the tensors have %ld rows but the batch appends %ld tokens",
          (long)rows, (long)total_append_);
@@ -1335,6 +1543,7 @@ void Cache::AttentionWithSharedKV(int64_t source_layer_id, double sm_scale, cons
 // MergeAttnOutputInplace (paged_kv_cache.cc:1553-1559): f_merge_inplace_[1] on caller tensors.
 void Cache::MergeAttnOutputInplace(void* o_self, float* lse_self, const void* o_cross, const float* lse_cross, int64_t n,
                                    int64_t num_heads, int64_t head_dim, cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_merge_attn_output_inplace");
   TRACE("merge", {TF({n, num_heads, head_dim}), TF({n, num_heads}, "float32"), TF({n, num_heads, head_dim}),
                   TF({n, num_heads}, "float32")});
   if (!planning_only())
@@ -1343,6 +1552,7 @@ void Cache::MergeAttnOutputInplace(void* o_self, float* lse_self, const void* o_
 }
 
 void Cache::CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* leaves, int n) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_commit_accepted_token_tree_nodes");
   // the reference indexes cur_append_lengths_ / cur_seq_ids_ / append_position_map_host_ of the last BeginForward with
   // the positions of seq_ids (paged_kv_cache.cc:1625-1650): the sequences must be that batch's, in its order
   HCHECK(batch_valid_, "commit_accepted_token_tree_nodes: the last begin_forward did not complete");
@@ -1401,6 +1611,7 @@ void Cache::CommitAcceptedTokenTreeNodes(const int64_t* seq_ids, const int64_t* 
 }
 
 void Cache::CompactKVCopy() {
+  NvtxRange nvtx_range("CompactKVCopy");
   const int total = commit_indptr_.back();
   if (total == 0) return;
   View vi, vsd;
@@ -1428,6 +1639,7 @@ void Cache::CompactKVCopy() {
 }
 
 void Cache::DebugGetKV(int64_t seq_id, int64_t start, int64_t end, void* k_out, void* v_out, cudaStream_t st) {
+  NvtxRange nvtx_range("vm.builtin.attention_kv_cache_debug_get_kv");
   const Sequence& s = Seq(seq_id);
   HCHECK(start >= 0, "DebugGetKV does not accept negative start_pos %ld", (long)start);
   HCHECK(end <= s.seq_length, "DebugGetKV does not accept out-of-range end_pos");
@@ -1519,6 +1731,25 @@ int tvmb200_cache_begin_forward(tvmb200_cache_t c, const int64_t* seq_ids, const
   CACHE_API_BEGIN_C(c); c->impl->BeginForward(seq_ids, lens, n, tree, tree_size); CACHE_API_END();
 }
 int tvmb200_cache_end_forward(tvmb200_cache_t c) { CACHE_API_BEGIN_C(c); c->impl->EndForward(); CACHE_API_END(); }
+int tvmb200_cache_enable_kv_transfer(tvmb200_cache_t c, int32_t local_tp_rank, int32_t num_pe, int32_t remote_num_kv_heads) {
+  CACHE_API_BEGIN_C(c); c->impl->EnableKVTransfer(local_tp_rank, num_pe, remote_num_kv_heads); CACHE_API_END();
+}
+int tvmb200_cache_set_remote_pages(tvmb200_cache_t c, int32_t pe, int64_t local_layer, void* peer_mapped_pages) {
+  CACHE_API_BEGIN_C(c); c->impl->SetRemotePages(pe, local_layer, peer_mapped_pages); CACHE_API_END();
+}
+int tvmb200_cache_disagg_prepare_recv(tvmb200_cache_t c, int64_t seq_id, int64_t append_length, int64_t* out, int64_t capacity,
+                                      int64_t* out_len) {
+  CACHE_API_BEGIN_C(c);
+  const std::vector<int64_t> v = c->impl->DisaggPrepareRecv(seq_id, append_length);
+  *out_len = static_cast<int64_t>(v.size());
+  if (static_cast<int64_t>(v.size()) > capacity) throw std::runtime_error("disagg_prepare_recv: the compressed position map needs " + std::to_string(v.size()) + " entries");
+  std::copy(v.begin(), v.end(), out);
+  CACHE_API_END();
+}
+int tvmb200_cache_disagg_mark_send(tvmb200_cache_t c, int64_t seq_id, int64_t begin, const int64_t* compressed_remote_position_map,
+                                   int64_t n, int32_t recver_pe_offset) {
+  CACHE_API_BEGIN_C(c); c->impl->DisaggMarkSend(seq_id, begin, compressed_remote_position_map, n, recver_pe_offset); CACHE_API_END();
+}
 int tvmb200_cache_enable_sliding_window_for_seq(tvmb200_cache_t c, int64_t s, int32_t w, int32_t sink) {
   CACHE_API_BEGIN_C(c); c->impl->EnableSlidingWindowForSeq(s, w, sink); CACHE_API_END();
 }

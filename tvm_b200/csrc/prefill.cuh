@@ -39,6 +39,13 @@ struct PrefillParams {
   float rope_theta;
   RopeScaling rs;
   float scale_log2;
+  // tcgen05 kernel only: the KV range of every work item is cut into kv_splits parts (launches with few, long items:
+  // a 64-node tree against a 32K context is one 256-row item per (sequence, kv head)); parts write normalised fp32
+  // partials [kv_splits, n, Hq, D] / [kv_splits, n, Hq] that prefill_merge_splits_kernel reduces
+  int kv_splits;
+  int total_q;
+  float* part_o;
+  float* part_lse;
 };
 
 int launch_prefill_generic(const PrefillParams& p, bool paged, int total_q_len, int head_dim, int dtype,
@@ -76,6 +83,6 @@ int launch_prefill_prepass(const PrepassParams& a, bool paged, int dtype, cudaSt
 // sliding window, token tree
 bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim);
 int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int total_kv_len, int64_t num_pages,
-                        int dtype, cudaStream_t st);
+                        int dtype, cudaStream_t st, int64_t avg_kv_len = 0);
 
 }  // namespace tvmb200

@@ -48,7 +48,9 @@ static int dispatch_prefill(PrefillParams& p, bool paged, int total_q_len, int t
   if (!needs_prepass) {
     if (tc05_eligible(p, paged, total_q_len, head_dim)) {
       g_path_counts[1]++;
-      return launch_prefill_tc05(p, paged, total_q_len, total_kv_len, num_pages, dtype, st);
+      const int64_t kv_total = paged ? static_cast<int64_t>(nnz_pages) * 16 : total_kv_len;
+      return launch_prefill_tc05(p, paged, total_q_len, total_kv_len, num_pages, dtype, st,
+                                 p.batch > 0 ? kv_total / p.batch : 0);
     }
     g_path_counts[0]++;
     return launch_prefill_generic(p, paged, total_q_len, head_dim, dtype, st);
@@ -103,10 +105,14 @@ static int dispatch_prefill(PrefillParams& p, bool paged, int total_q_len, int t
   return launch_prefill_tc05(t, false, total_q_len, static_cast<int>(kv_rows), 0, dtype, st);
 }
 
-// [0] mma.sync kernel, [1] tcgen05 kernel, [2] tcgen05 kernel behind the gather / rotate pre-pass (tests: no silent
-// fallback on the shapes the tensor-core path is meant to cover)
-extern "C" TVMB200_API void tvmb200_debug_prefill_path_counts(int64_t out[3]) {
+// [0] mma.sync kernel, [1] tcgen05 kernel, [2] tcgen05 kernel behind the gather / rotate pre-pass, [3] tcgen05 launches
+// (of [1]) that cut their items' KV range into parts (tests: no silent fallback on the shapes the tensor-core path covers)
+namespace tvmb200 {
+extern std::atomic<int64_t> g_kv_split_launches;
+}
+extern "C" TVMB200_API void tvmb200_debug_prefill_path_counts(int64_t out[4]) {
   for (int i = 0; i < 3; ++i) out[i] = g_path_counts[i].load();
+  out[3] = tvmb200::g_kv_split_launches.load();
 }
 // upper bound of the pre-pass scratch (bytes) above which inline-RoPE / sliding-window prefill stays on the mma.sync kernel
 extern "C" TVMB200_API void tvmb200_set_prefill_prepass_cap(int64_t bytes) { g_prepass_cap.store(bytes); }

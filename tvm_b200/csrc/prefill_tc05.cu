@@ -102,13 +102,18 @@ __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
 struct Item {
   int h, q_beg, qo_len, row0, tok0, nqt, kv_len, kv_beg, pg_beg, n_pages, ns0, ns1, n_kv;
   int tree_beg, tree_len;  // kMaskTree: the sequence's rows of tree_order; the mask covers the trailing tree_len columns
+  int j0;                  // first 128-row KV tile of this item (kv_splits > 1: the item covers tiles [j0, j0 + n_kv))
+  int split;               // which part (kv_splits > 1)
 };
 
 template <bool PAGED>
 __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s_tiles, int id, int n_items) {
   Item it;
   const int B = p.batch, g = p.group;
-  const int ritem = n_items - 1 - id;  // late (= long-KV under a causal mask) tiles first
+  const int ritem0 = n_items - 1 - id;  // late (= long-KV under a causal mask) tiles first
+  const int S = p.kv_splits;
+  const int ritem = ritem0 / S;
+  it.split = ritem0 - ritem * S;
   const int tg = ritem / p.num_kv_heads;
   it.h = ritem - tg * p.num_kv_heads;
   int lo = 0, hi = B;
@@ -151,6 +156,15 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
   it.ns0 = steps_of(0);
   it.ns1 = steps_of(1);
   it.n_kv = (max(it.ns0, it.ns1) + 1) >> 1;  // 128-row K / V tiles to load
+  it.j0 = 0;
+  if (S > 1) {
+    const int per = (it.n_kv + S - 1) / S;
+    it.j0 = min(it.split * per, it.n_kv);
+    const int j1 = min(it.n_kv, it.j0 + per);
+    it.ns0 = max(0, min(it.ns0 - 2 * it.j0, 2 * (j1 - it.j0)));
+    it.ns1 = max(0, min(it.ns1 - 2 * it.j0, 2 * (j1 - it.j0)));
+    it.n_kv = (max(it.ns0, it.ns1) + 1) >> 1;
+  }
   return it;
 }
 
@@ -190,7 +204,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
   __syncthreads();
   block_exclusive_scan(s_tiles, B, s_tmp);
-  const int n_items = s_tiles[B] * p.num_kv_heads;
+  const int n_items = s_tiles[B] * p.num_kv_heads * p.kv_splits;
   const bool causal = p.mask_mode == kMaskCausal;
   const int tok_per_tile = kRows / g;
 
@@ -257,7 +271,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         ++n_q;
         for (int fl = 0; fl < 2 * it.n_kv; ++fl, ++fill) {
-          const int j = fl >> 1, is_v = fl & 1, slot = fill & (kSlots - 1);
+          const int j = it.j0 + (fl >> 1), is_v = fl & 1, slot = fill & (kSlots - 1);  // j: absolute KV tile
           mbar_wait(bar(KV_EMPTY + slot), ((fill / kSlots) & 1) ^ 1);
           const uint32_t dst = skv + slot * kTileBytes;
           if (!PAGED) {
@@ -352,7 +366,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (PAGED && !kConvertV && j == n_kv - 1) {
             // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
             // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-            const int valid = it.kv_len - j * kKV;
+            const int valid = it.kv_len - (it.j0 + j) * kKV;
             if (valid < kKV) {
               for (int e = lane; e < (kKV - valid) * 16; e += 32) {
                 const int r = valid + (e >> 4), c = e & 15;
@@ -416,7 +430,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // conversion does not care about the 128B swizzle.  Rows past kv_len of a paged tile (whatever the page
           // holds, maybe NaN bit patterns) become zeros: P is exactly 0 there but 0 * NaN = NaN.
           uint4* half = reinterpret_cast<uint4*>(sgen + SmemLayout::kv + vslot * kTileBytes + (warp - 2) * kHalfBytes);
-          const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - j * kKV : kKV;
+          const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - (it.j0 + j) * kKV : kKV;
 #pragma unroll 4
           for (int e = lane; e < kHalfBytes / 16; e += 32) {
             uint4 v = half[e];
@@ -625,14 +639,15 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         tc05::wait_ld();
         if (wq == 0) TRACE(1 + t, 2 * j, 2);
-        const int rem_a = limit - 2 * j * kStep;
+        const int col_a = (it.j0 + j) * kKV;     // sequence column of the tile's first S column
+        const int rem_a = limit - col_a;
         mask_half(sa0, sa1, rem_a);
-        if (XMASK) mask_extra(sa0, sa1, 2 * j * kStep);
+        if (XMASK) mask_extra(sa0, sa1, col_a);
         const float mx_a = half_max(sa0, sa1);
         float mx_b = -INFINITY;
         if (has_b) {
           mask_half(sb0, sb1, rem_a - kStep);
-          if (XMASK) mask_extra(sb0, sb1, (2 * j + 1) * kStep);
+          if (XMASK) mask_extra(sb0, sb1, col_a + kStep);
           mx_b = half_max(sb0, sb1);
         }
         if (wq == 0) TRACE(1 + t, 2 * j, 4);
@@ -642,10 +657,19 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       // ---- epilogue: O / l -> global, LSE ----------------------------------------------------------------
       T* orow = nullptr;
+      float* prow = nullptr;   // kv_splits > 1: this part's fp32 partial row
       if (valid) {
         const int hq = h * g + (R - tok * g);
-        orow = static_cast<T*>(p.output) + (static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq) * kD;
-        p.lse[static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq] = l > 0.f ? m_used + log2f(l) : kNegInit;
+        const int64_t at = static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq;
+        const float lse_v = l > 0.f ? m_used + log2f(l) : kNegInit;
+        if (p.kv_splits > 1) {
+          const int64_t pat = static_cast<int64_t>(it.split) * p.total_q * p.num_qo_heads + at;
+          prow = p.part_o + pat * kD;
+          p.part_lse[pat] = lse_v;
+        } else {
+          orow = static_cast<T*>(p.output) + at * kD;
+          p.lse[at] = lse_v;
+        }
       }
       if (my_ns > 0) {
         const int hl = (my_ns - 1) & 1;
@@ -657,7 +681,13 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           uint32_t o[32];
           tc05::ld32(t_o + cc * 32, o);
           tc05::wait_ld();
-          if (valid) {
+          if (prow != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4)
+              *reinterpret_cast<float4*>(prow + cc * 32 + c) =
+                  make_float4(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv, __uint_as_float(o[c + 2]) * inv,
+                              __uint_as_float(o[c + 3]) * inv);
+          } else if (valid) {
 #pragma unroll
             for (int c = 0; c < 32; c += 8) {
               uint4 v;
@@ -672,6 +702,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // O_t is free for the next item's first PV: that PV waits for this warpgroup's next P_READY, which these
         // very threads only signal after the loads above
         tc05::fence_before_sync();
+      } else if (prow != nullptr) {
+#pragma unroll
+        for (int c = 0; c < kD; c += 4) *reinterpret_cast<float4*>(prow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       } else if (valid) {
         // no visible KV at all: O = 0, LSE = -5e4 (the reference's empty result)
 #pragma unroll
@@ -689,10 +722,41 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
+// kv_splits > 1: O = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse), LSE = max + log2(sum w) over the parts of a row
+// (the arithmetic of f_merge_inplace); a part that saw no visible column carries the -5e4 sentinel and weighs nothing.
+// One warp per (token, head) row, four dims per lane.
+template <typename T>
+__global__ void __launch_bounds__(256)
+prefill_merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse, T* __restrict__ output,
+                            float* __restrict__ lse, int64_t rows, int splits) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float mm = kNegInit;
+  for (int s = 0; s < splits; ++s) mm = fmaxf(mm, part_lse[s * rows + row]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float den = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float ls = part_lse[s * rows + row];
+    if (ls <= kNegInit) continue;
+    const float w = exp2f(ls - mm);
+    const float4 v = *reinterpret_cast<const float4*>(part_o + (s * rows + row) * kD + lane * 4);
+    acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    den += w;
+  }
+  const float inv = den > 0.f ? 1.f / den : 0.f;
+  uint2 pk;
+  pk.x = DT<T>::pack(acc.x * inv, acc.y * inv);
+  pk.y = DT<T>::pack(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(output + row * kD + lane * 4) = pk;
+  if (lane == 0) lse[row] = den > 0.f ? mm + log2f(den) : kNegInit;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static std::atomic<int> g_prefill_impl{0};   // 0 auto, 1 force generic, 2 force tcgen05 (where eligible)
+std::atomic<int64_t> g_kv_split_launches{0};  // tcgen05 launches that cut their items' KV range (prefill_api.cu reports it)
 
 bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head_dim) {
   const int impl = g_prefill_impl.load();
@@ -708,11 +772,49 @@ bool tc05_eligible(const PrefillParams& p, bool paged, int total_q_len, int head
   return static_cast<int64_t>(total_q_len) * g >= 2048;
 }
 
+// How many parts to cut every item's KV range into.  Known on the host: the number of 256-row items (bounds) and the
+// average KV length; wanted: the launch's makespan on `grid` CTAs, ceil(items * S / grid) rounds of ceil(tiles / S) KV
+// tiles, as short as possible without making parts shorter than 8 tiles.  S = 1 whenever the items already fill the
+// machine several times over (C3) or the contexts are short.
+static int choose_kv_splits(int64_t items, int64_t avg_kv_len, int grid) {
+  const int64_t tiles = (avg_kv_len + kKV - 1) / kKV;
+  if (items <= 0 || tiles < 16 || items >= 4 * static_cast<int64_t>(grid)) return 1;
+  int best = 1;
+  int64_t best_cost = ((items + grid - 1) / grid) * tiles;
+  for (int s = 2; s <= 8 && tiles / s >= 8; ++s) {
+    const int64_t cost = ((items * s + grid - 1) / grid) * ((tiles + s - 1) / s) + 2 * s;  // (+ a little per extra part)
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
 template <typename T, typename PT, bool PAGED>
-static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         int total_q_len, cudaStream_t st) {
+static int launch_tc05_t(const PrefillParams& p_in, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         int total_q_len, cudaStream_t st, int64_t avg_kv_len) {
+  PrefillParams p = p_in;
   const int64_t max_pairs = (static_cast<int64_t>(total_q_len) * p.group + 2 * kRows - 1) / (2 * kRows) + p.batch;
-  const int64_t max_items = max_pairs * p.num_kv_heads;
+  // (for the split decision: pairs without the per-sequence rounding slack)
+  const int64_t est_items = ((static_cast<int64_t>(total_q_len) * p.group + 2 * kRows - 1) / (2 * kRows)) * p.num_kv_heads;
+  p.kv_splits = avg_kv_len > 0 ? choose_kv_splits(est_items > p.batch * p.num_kv_heads ? est_items : p.batch * p.num_kv_heads,
+                                                  avg_kv_len, num_sms()) : 1;
+  p.total_q = total_q_len;
+  {  // partials are capped at 256 MiB of the context's scratch
+    const int64_t rows = static_cast<int64_t>(total_q_len) * p.num_qo_heads;
+    while (p.kv_splits > 1 && p.kv_splits * rows * (kD + 1) * 4 > (int64_t(256) << 20)) --p.kv_splits;
+  }
+  if (p.kv_splits > 1) {
+    g_kv_split_launches++;
+    const int64_t rows = static_cast<int64_t>(total_q_len) * p.num_qo_heads;
+    const int64_t lse_bytes = (p.kv_splits * rows * 4 + 255) / 256 * 256;
+    void* ws = nullptr;
+    if (int rc = get_workspace(lse_bytes + p.kv_splits * rows * kD * 4, st, &ws)) return rc;
+    p.part_lse = static_cast<float*>(ws);
+    p.part_o = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + lse_bytes);
+  }
+  const int64_t max_items = max_pairs * p.num_kv_heads * p.kv_splits;
   const int grid = static_cast<int>(max_items < num_sms() ? max_items : num_sms());  // persistent: one CTA per SM
   const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
   const bool xmask = p.mask_mode == kMaskLayerSliding || p.mask_mode == kMaskTree;
@@ -730,11 +832,18 @@ static int launch_tc05_t(const PrefillParams& p, const CUtensorMap& tq, const CU
   TVMB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   kern<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(tq, tk, tv, p, idesc_qk, idesc_pv, counter);
   TVMB200_LAUNCH_OK();
+  if (p.kv_splits > 1) {
+    const int64_t rows = static_cast<int64_t>(total_q_len) * p.num_qo_heads;
+    prefill_merge_splits_kernel<T><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
+        p.part_o, p.part_lse, static_cast<T*>(p.output), p.lse, rows, p.kv_splits);
+    TVMB200_LAUNCH_OK();
+  }
   return 0;
 }
 
+// avg_kv_len > 0 allows the KV split (the caller passes 0 when the context's scratch is already in use: pre-pass route)
 int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int total_kv_len, int64_t num_pages,
-                        int dtype, cudaStream_t st) {
+                        int dtype, cudaStream_t st, int64_t avg_kv_len) {
   CUtensorMap tq, tk, tv;
   const int g = p.group;
   const uint64_t row_q = static_cast<uint64_t>(p.num_qo_heads) * kD * 2;
@@ -749,10 +858,10 @@ int launch_prefill_tc05(const PrefillParams& p, bool paged, int total_q_len, int
     if (int rc = make_tmap_3d(&tv, p.v, dtype, kD, p.num_kv_heads, total_kv_len, kD * 2, row_kv, 1, kKV)) return rc;
   }
   if (dtype == TVMB200_F16)
-    return paged ? launch_tc05_t<__half, __half, true>(p, tq, tk, tv, total_q_len, st)
-                 : launch_tc05_t<__half, __half, false>(p, tq, tk, tv, total_q_len, st);
-  return paged ? launch_tc05_t<__nv_bfloat16, __half, true>(p, tq, tk, tv, total_q_len, st)
-               : launch_tc05_t<__nv_bfloat16, __half, false>(p, tq, tk, tv, total_q_len, st);
+    return paged ? launch_tc05_t<__half, __half, true>(p, tq, tk, tv, total_q_len, st, avg_kv_len)
+                 : launch_tc05_t<__half, __half, false>(p, tq, tk, tv, total_q_len, st, avg_kv_len);
+  return paged ? launch_tc05_t<__nv_bfloat16, __half, true>(p, tq, tk, tv, total_q_len, st, avg_kv_len)
+               : launch_tc05_t<__nv_bfloat16, __half, false>(p, tq, tk, tv, total_q_len, st, avg_kv_len);
 }
 
 }  // namespace tvmb200

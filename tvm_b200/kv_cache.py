@@ -68,6 +68,10 @@ def _lib():
         L.tvmb200_cache_merge_attn_output_inplace.argtypes = [P, P, P, P, P, I64, I64, I64, P]
         L.tvmb200_cache_debug_get_kv.argtypes = [P, I64, I64, I64, P, P, P]
         L.tvmb200_cache_pages.argtypes = [P, I64, POINTER(P), POINTER(I64)]
+        L.tvmb200_cache_enable_kv_transfer.argtypes = [P, I32, I32, I32]
+        L.tvmb200_cache_set_remote_pages.argtypes = [P, I32, I64, P]
+        L.tvmb200_cache_disagg_prepare_recv.argtypes = [P, I64, I64, P, I64, POINTER(I64)]
+        L.tvmb200_cache_disagg_mark_send.argtypes = [P, I64, I64, P, I64, I32]
         L.tvmb200_cache_shape.argtypes = [P, POINTER(I64)]
         L.tvmb200_cache_context.argtypes = [P, POINTER(P)]
         L.tvmb200_cache_set_trace.argtypes = [P, I32]
@@ -255,6 +259,27 @@ class PagedKVCache:
         ptr, n = c_void_p(), c_int64()
         capi._check(_lib().tvmb200_cache_pages(self._h, local_layer, byref(ptr), byref(n)))
         return ptr.value, n.value
+
+    # ---- disaggregated prefill -> decode (vm.builtin.kv_cache_disagg_*; include/tvm_b200_cache.h) ----
+    def enable_kv_transfer(self, local_tp_rank=0, num_pe=1, remote_num_kv_heads=None):
+        capi._check(_lib().tvmb200_cache_enable_kv_transfer(self._h, local_tp_rank, num_pe,
+                                                            remote_num_kv_heads or self.num_kv_heads))
+
+    def set_remote_pages(self, pe, local_layer, peer_mapped_ptr):
+        """peer_mapped_ptr: device pointer, valid on THIS cache's GPU, of PE `pe`'s page pool of the layer"""
+        capi._check(_lib().tvmb200_cache_set_remote_pages(self._h, pe, local_layer, c_void_p(peer_mapped_ptr)))
+
+    def disagg_prepare_recv(self, seq_id, append_length):
+        """-> the reserved slots, run-length compressed [n, begin_1, length_1, ...] (what mark_send takes)"""
+        cap = 2 * int(append_length) + 1
+        buf, n = (c_int64 * cap)(), c_int64()
+        capi._check(_lib().tvmb200_cache_disagg_prepare_recv(self._h, seq_id, append_length, buf, cap, byref(n)))
+        return [int(buf[i]) for i in range(n.value)]
+
+    def disagg_mark_send(self, seq_id, begin, compressed_remote_position_map, recver_pe_offset):
+        a = _i64(compressed_remote_position_map)
+        capi._check(_lib().tvmb200_cache_disagg_mark_send(self._h, seq_id, begin, a, len(compressed_remote_position_map),
+                                                          recver_pe_offset))
 
     def set_trace(self, on=True):
         capi._check(_lib().tvmb200_cache_set_trace(self._h, int(on)))
