@@ -66,6 +66,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     OBJDIR.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    # tuning knob: TVMB200_SWAP_SRC="prefill_tc05.cu=scripts/ab/prefill_tc05_r1.cu" builds a variant with one source swapped
+    # (A/B runs of a kernel against an earlier version on the same box)
+    for spec in os.environ.get("TVMB200_SWAP_SRC", "").split():
+        name, _, repl = spec.partition("=")
+        srcs = [(ROOT.parent / repl) if s.name == name else s for s in srcs]
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted((ROOT.parent / "include").glob("*.h"))
     flags = _flags(verbose) + ARCH + _ffi_includes()
     stamp = LIBDIR / f"build{SUFFIX}.stamp"

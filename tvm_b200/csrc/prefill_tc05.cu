@@ -106,14 +106,14 @@ struct Item {
   int split;               // which part (kv_splits > 1)
 };
 
-template <bool PAGED>
+template <bool PAGED, bool SPLIT>
 __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s_tiles, int id, int n_items) {
   Item it;
   const int B = p.batch, g = p.group;
   const int ritem0 = n_items - 1 - id;  // late (= long-KV under a causal mask) tiles first
-  const int S = p.kv_splits;
-  const int ritem = ritem0 / S;
-  it.split = ritem0 - ritem * S;
+  const int S = SPLIT ? p.kv_splits : 1;
+  const int ritem = SPLIT ? ritem0 / S : ritem0;
+  it.split = SPLIT ? ritem0 - ritem * S : 0;
   const int tg = ritem / p.num_kv_heads;
   it.h = ritem - tg * p.num_kv_heads;
   int lo = 0, hi = B;
@@ -157,7 +157,7 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
   it.ns1 = steps_of(1);
   it.n_kv = (max(it.ns0, it.ns1) + 1) >> 1;  // 128-row K / V tiles to load
   it.j0 = 0;
-  if (S > 1) {
+  if (SPLIT) {
     const int per = (it.n_kv + S - 1) / S;
     it.j0 = min(it.split * per, it.n_kv);
     const int j1 = min(it.n_kv, it.j0 + per);
@@ -177,8 +177,9 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
 // tiles' tensor work (they cost ~12 % with one CTA per tile).
 // XMASK = true adds the two masks that are not a plain "columns [0, limit)": the per-layer sliding window (a LOWER bound
 // per row, _kernel_common.py:130-144) and the token-tree mask on the trailing tree_len columns (an ancestor test per
-// (row, column), tree_attn.py:48-65).  A separate instantiation: the causal / mask-free kernel keeps its registers.
-template <typename T, typename PT, bool PAGED, bool XMASK>
+// (row, column), tree_attn.py:48-65).  SPLIT = true cuts every item's KV range into p.kv_splits parts that write fp32
+// partials.  Separate instantiations: the causal / mask-free kernel of the hot configuration keeps its registers.
+template <typename T, typename PT, bool PAGED, bool XMASK, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p, const uint32_t idesc_qk,
@@ -204,7 +205,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
   __syncthreads();
   block_exclusive_scan(s_tiles, B, s_tmp);
-  const int n_items = s_tiles[B] * p.num_kv_heads * p.kv_splits;
+  const int n_items = s_tiles[B] * p.num_kv_heads * (SPLIT ? p.kv_splits : 1);
   const bool causal = p.mask_mode == kMaskCausal;
   const int tok_per_tile = kRows / g;
 
@@ -259,7 +260,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         id = __shfl_sync(0xffffffffu, id, 0);
         if (id >= n_items) break;
-        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        const Item it = decode_item<PAGED, SPLIT>(p, s_tiles, id, n_items);
         if (it.n_kv == 0) continue;
         if (lane == 0) {
           mbar_wait(bar(Q_EMPTY), (n_q & 1) ^ 1);  // every QK^T of the previous item has read Q
@@ -271,7 +272,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         ++n_q;
         for (int fl = 0; fl < 2 * it.n_kv; ++fl, ++fill) {
-          const int j = it.j0 + (fl >> 1), is_v = fl & 1, slot = fill & (kSlots - 1);  // j: absolute KV tile
+          const int j = (SPLIT ? it.j0 : 0) + (fl >> 1), is_v = fl & 1, slot = fill & (kSlots - 1);  // j: absolute KV tile
           mbar_wait(bar(KV_EMPTY + slot), ((fill / kSlots) & 1) ^ 1);
           const uint32_t dst = skv + slot * kTileBytes;
           if (!PAGED) {
@@ -335,7 +336,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (id >= n_items) break;
         const int trace_item = id;
         (void)trace_item;
-        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        const Item it = decode_item<PAGED, SPLIT>(p, s_tiles, id, n_items);
         const int n_kv = it.n_kv;
         if (n_kv == 0) continue;
         auto ns = [&](int t) { return t ? it.ns1 : it.ns0; };
@@ -366,7 +367,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (PAGED && !kConvertV && j == n_kv - 1) {
             // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
             // P is exactly 0 there but 0 * NaN = NaN, so zero them before the tensor core reads them
-            const int valid = it.kv_len - (it.j0 + j) * kKV;
+            const int valid = it.kv_len - ((SPLIT ? it.j0 : 0) + j) * kKV;
             if (valid < kKV) {
               for (int e = lane; e < (kKV - valid) * 16; e += 32) {
                 const int r = valid + (e >> 4), c = e & 15;
@@ -421,7 +422,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(ITEM_EMPTY + islot));
         if (id >= n_items) break;
-        const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+        const Item it = decode_item<PAGED, SPLIT>(p, s_tiles, id, n_items);
         for (int j = 0; j < it.n_kv; ++j) {
           const uint32_t fv = fill + 2 * j + 1;
           const int vslot = fv & (kSlots - 1);
@@ -430,7 +431,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // conversion does not care about the 128B swizzle.  Rows past kv_len of a paged tile (whatever the page
           // holds, maybe NaN bit patterns) become zeros: P is exactly 0 there but 0 * NaN = NaN.
           uint4* half = reinterpret_cast<uint4*>(sgen + SmemLayout::kv + vslot * kTileBytes + (warp - 2) * kHalfBytes);
-          const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - (it.j0 + j) * kKV : kKV;
+          const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - ((SPLIT ? it.j0 : 0) + j) * kKV : kKV;
 #pragma unroll 4
           for (int e = lane; e < kHalfBytes / 16; e += 32) {
             uint4 v = half[e];
@@ -472,7 +473,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (id >= n_items) break;
       const int trace_item = id;
       (void)trace_item;
-      const Item it = decode_item<PAGED>(p, s_tiles, id, n_items);
+      const Item it = decode_item<PAGED, SPLIT>(p, s_tiles, id, n_items);
       const int h = it.h, q_beg = it.q_beg, qo_len = it.qo_len, kv_len = it.kv_len, nqt = it.nqt;
       const int R = it.row0 + t * kRows + r;     // folded row within the sequence
       const int tok = R / g;
@@ -626,7 +627,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const bool has_b = 2 * j + 1 < my_ns;       // upper half visible to some row of the tile (CTA-uniform)
         if (wq == 0) TRACE(1 + t, 2 * j, 0);
         mbar_wait(bar(S_FULL + 2 * t), n_s & 1);
-        if (has_b) mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);
+        mbar_wait(bar(S_FULL + 2 * t + 1), n_s & 1);  // (committed with the first one: every phase is observed)
         ++n_s;
         if (wq == 0) TRACE(1 + t, 2 * j, 1);
         tc05::fence_after_sync();
@@ -639,7 +640,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         tc05::wait_ld();
         if (wq == 0) TRACE(1 + t, 2 * j, 2);
-        const int col_a = (it.j0 + j) * kKV;     // sequence column of the tile's first S column
+        const int col_a = ((SPLIT ? it.j0 : 0) + j) * kKV;     // sequence column of the tile's first S column
         const int rem_a = limit - col_a;
         mask_half(sa0, sa1, rem_a);
         if (XMASK) mask_extra(sa0, sa1, col_a);
@@ -662,7 +663,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int hq = h * g + (R - tok * g);
         const int64_t at = static_cast<int64_t>(q_beg + tok) * p.num_qo_heads + hq;
         const float lse_v = l > 0.f ? m_used + log2f(l) : kNegInit;
-        if (p.kv_splits > 1) {
+        if (SPLIT) {
           const int64_t pat = static_cast<int64_t>(it.split) * p.total_q * p.num_qo_heads + at;
           prow = p.part_o + pat * kD;
           p.part_lse[pat] = lse_v;
@@ -681,7 +682,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           uint32_t o[32];
           tc05::ld32(t_o + cc * 32, o);
           tc05::wait_ld();
-          if (prow != nullptr) {
+          if (SPLIT && prow != nullptr) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4)
               *reinterpret_cast<float4*>(prow + cc * 32 + c) =
@@ -702,7 +703,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // O_t is free for the next item's first PV: that PV waits for this warpgroup's next P_READY, which these
         // very threads only signal after the loads above
         tc05::fence_before_sync();
-      } else if (prow != nullptr) {
+      } else if (SPLIT && prow != nullptr) {
 #pragma unroll
         for (int c = 0; c < kD; c += 4) *reinterpret_cast<float4*>(prow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       } else if (valid) {
@@ -818,7 +819,9 @@ static int launch_tc05_t(const PrefillParams& p_in, const CUtensorMap& tq, const
   const int grid = static_cast<int>(max_items < num_sms() ? max_items : num_sms());  // persistent: one CTA per SM
   const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
   const bool xmask = p.mask_mode == kMaskLayerSliding || p.mask_mode == kMaskTree;
-  auto kern = xmask ? prefill_tc05_kernel<T, PT, PAGED, true> : prefill_tc05_kernel<T, PT, PAGED, false>;
+  const bool split = p.kv_splits > 1;
+  auto kern = xmask ? (split ? prefill_tc05_kernel<T, PT, PAGED, true, true> : prefill_tc05_kernel<T, PT, PAGED, true, false>)
+                    : (split ? prefill_tc05_kernel<T, PT, PAGED, false, true> : prefill_tc05_kernel<T, PT, PAGED, false, false>);
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
