@@ -231,3 +231,60 @@ def test_failed_begin_forward_rolls_back(built_lib):
             m.end_forward()
         assert c.take_trace() == twin.take_trace()
         assert c.get_num_available_pages() == twin.get_num_available_pages()
+
+
+def test_disaggregation_bookkeeping_planning_only(built_lib):
+    """DisaggPrepareRecv / DisaggMarkSend (paged_kv_cache.cc:1220-1301) on planning-only caches: the compressed position map
+    is [n, begin_1, length_1, ...] over the receiver's append slots, the sender's next forward carries one transfer entry
+    with the fresh rows (and, when the sequence was marked after a partial prefill, the cached rows page to page), the
+    un-marked sequences send nothing, and the fused decode step is not taken while a transfer is due."""
+    from tvm_b200 import capi
+
+    recv = _plan_cache(reserved_num_seqs=4, total_token_capacity=256, prefill_chunk_size=128, num_layers=2)
+    recv.add_sequence(5)
+    recv.add_sequence(6)
+    recv.begin_forward([6], [3])                 # seq 6 takes the first page, so seq 5's slots do not start at 0
+    recv.attention_with_fused_qkv(0, 1.0, None, None)
+    recv.end_forward()
+    m = recv.disagg_prepare_recv(5, 40)
+    assert m[0] * 2 + 1 == len(m) and sum(m[2::2]) == 40
+    slots = [b + i for b, n in zip(m[1::2], m[2::2]) for i in range(n)]
+    assert len(set(slots)) == 40 and min(slots) >= 16
+    assert recv.get_total_sequence_length() == 43
+    recv.end_forward()
+
+    send = _plan_cache(reserved_num_seqs=4, total_token_capacity=256, prefill_chunk_size=128, num_layers=2)
+    send.add_sequence(5)
+    send.add_sequence(9)
+    with pytest.raises(capi.TvmB200Error, match="enable_kv_transfer|set up"):
+        send.disagg_mark_send(5, 0, m, 1)
+    send.enable_kv_transfer(local_tp_rank=0, num_pe=2)
+    with pytest.raises(capi.TvmB200Error, match="malformed"):
+        send.disagg_mark_send(5, 0, m[:-1], 1)
+    with pytest.raises(capi.TvmB200Error, match="cannot be found"):
+        send.disagg_mark_send(77, 0, m, 1)
+    send.disagg_mark_send(5, 0, m, 1)
+    send.set_trace(True)
+    send.begin_forward([5, 9], [25, 7])          # seq 9 is not marked: its rows stay here
+    for layer in range(2):
+        send.attention_with_fused_qkv(layer, 1.0, None, None)
+    send.end_forward()
+    tr = send.take_trace()
+    names = [c["fn"] if isinstance(c, dict) else c[0] for c in tr]
+    assert names.count("kv_transfer") == 2       # once per layer
+    send.begin_forward([5], [15])                # the rest of the prefill
+    send.attention_with_fused_qkv(0, 1.0, None, None)
+    send.attention_with_fused_qkv(1, 1.0, None, None)
+    send.end_forward()
+    with pytest.raises(capi.TvmB200Error, match="more tokens than the receiver prepared"):
+        send.begin_forward([5], [1])             # 41st token: the receiver reserved 40
+    # marking a sequence that already holds tokens: they go page to page with the next forward
+    send.disagg_mark_send(9, 2, [1, 100, 20], 1)
+    send.take_trace()
+    send.begin_forward([9], [4])
+    send.attention_with_fused_qkv(0, 1.0, None, None)
+    send.attention_with_fused_qkv(1, 1.0, None, None)
+    send.end_forward()
+    tr = send.take_trace()
+    kv = [c for c in tr if (c["fn"] if isinstance(c, dict) else c[0]) == "kv_transfer"]
+    assert len(kv) == 2

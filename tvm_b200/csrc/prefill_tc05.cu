@@ -56,13 +56,15 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P <= 2^8
 // inputs the V tile is converted to fp16 in shared memory by two otherwise idle warps (exact for |v| in [2^-14, 65504],
 // saturating above).  The first tcgen05 versions kept P in bf16 and added a second PV pass with the rounding residual
 // P_lo = P - bf16(P) for steps with dominant weights: slower (956 vs 976 TFLOP/s) and much more code.
-// of every 16 column pairs, how many take 2^x on the FMA pipe instead of the MUFU (swept on C3: 4)
+// of every 16 column pairs, how many take 2^x on the FMA pipe instead of the MUFU.  Swept on C3 in round 2 (fp16 P, burst /
+// sustained TFLOP/s): 0: 981 / 875, 1: 981 / 875, 2: 981-1001 / 874-876, 3: 977 / 873, 4: 974-995 / 865, 6: 982 / 855,
+// 8: 965 / 835 -- flat within 1 % up to 4, then worse: the MUFU is not what the softmax warps wait for
 #ifdef TVMB200_POLY_PAIRS
 template <typename PT>
 constexpr int kPolyPairsOf = TVMB200_POLY_PAIRS;
 #else
 template <typename PT>
-constexpr int kPolyPairsOf = 4;
+constexpr int kPolyPairsOf = 2;
 #endif
 
 struct SmemLayout {
