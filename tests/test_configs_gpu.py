@@ -157,6 +157,17 @@ def test_c3_ragged_prefill_16x2048_prefix_property(capi, dtype):
                                          np.array([0, L], np.int32), qpos[L - T:L], kofs[:1], 1, 0, 1.0, 5e5, sm, dtype)
     assert_close("tail O seq 9", go[s0 + L - T:s0 + L], wo)
     assert_close("tail LSE seq 9", gl[s0 + L - T:s0 + L], wl)
+    # ... and 96 rows picked at random over all sequences and positions (mid-sequence rows of interior work items, tile
+    # borders included): each restated by the oracle as a one-row causal query over its own prefix
+    picks = [(int(rng.integers(0, nseq)), int(t)) for t in
+             list(rng.integers(1, L, 80)) + [127, 128, 129, 255, 256, 1023, 1024, 1025, 2047, 63, 64, 65, 511, 512, 1535, 1536]]
+    one = np.array([0, 1], np.int32)
+    for b, t in picks:
+        s0 = b * L
+        wo, wl = ok.attention_prefill_ragged(q[s0 + t:s0 + t + 1], one, k[s0:s0 + t + 1], v[s0:s0 + t + 1],
+                                             np.array([0, t + 1], np.int32), qpos[t:t + 1], kofs[:1], 1, 0, 1.0, 5e5, sm, dtype)
+        assert_close(f"row O seq {b} pos {t}", go[s0 + t:s0 + t + 1], wo)
+        assert_close(f"row LSE seq {b} pos {t}", gl[s0 + t:s0 + t + 1], wl)
 
 
 def _random_tree(rng, n):

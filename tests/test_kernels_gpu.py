@@ -246,6 +246,41 @@ def test_decode_small(capi, dtype, hq, hkv, d):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hq,hkv", [(16, 1), (32, 2), (64, 2), (24, 1)])
+def test_decode_gqa_groups_above_eight(capi, dtype, hq, hkv):
+    """GQA groups of 16 / 32 / 24 query heads per kv head (Llama-3.1-405B: 128 / 8): cut into virtual heads of 8, each a
+    pass over the same pages; split-KV lengths included"""
+    rng = np.random.default_rng(16)
+    _run_decode(capi, rng, [11, 300, 1, 2049, 64], hq, hkv, 128, dtype)
+    _run_decode(capi, rng, [40, 7], hq, hkv, 128, dtype, rotary_mode=1)
+
+
+def test_unsupported_shapes_fail_loudly(capi):
+    """limits raise, nothing is computed by a fallback: a GQA group that is neither <= 8 nor a multiple of 8, head_dim 96,
+    8-slot pages, a float32 cache"""
+    import torch
+
+    from tvm_b200.capi import TvmB200Error
+
+    rng = np.random.default_rng(17)
+    with pytest.raises(TvmB200Error, match="group size 12"):
+        _run_decode(capi, rng, [11, 21], 12, 1, 128, "float16")
+    with pytest.raises(TvmB200Error, match="head_dim 96"):
+        _run_decode(capi, rng, [11, 21], 8, 2, 96, "float16")
+    i32 = lambda *a: torch.zeros(a, dtype=torch.int32, device="cuda")  # noqa: E731
+    q = torch.zeros((1, 8, 128), dtype=torch.float16, device="cuda")
+    lse = torch.zeros((1, 8), dtype=torch.float32, device="cuda")
+    pages8 = torch.zeros((4, 2, 2, 8, 128), dtype=torch.float16, device="cuda")
+    with pytest.raises(TvmB200Error, match="page_size 8"):
+        capi.attention_decode(q, pages8, i32(2), i32(1), i32(1), i32(1), i32(1), q.clone(), lse, 0, 1.0, 1e4, 1.0)
+    with pytest.raises(TvmB200Error, match="page_size 8"):
+        capi.attention_prefill_paged(q, i32(2), pages8, i32(2), i32(1), i32(1), i32(1), i32(1), q.clone(), lse, 0, 0, 1.0, 1e4, 1.0)
+    pages32 = torch.zeros((4, 2, 2, 16, 128), dtype=torch.float32, device="cuda")
+    with pytest.raises(TvmB200Error, match="dtype"):
+        capi.attention_decode(q.float(), pages32, i32(2), i32(1), i32(1), i32(1), i32(1), q.float(), lse, 0, 1.0, 1e4, 1.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_decode_ragged_lengths_and_empty(capi, dtype):
     rng = np.random.default_rng(11)
     # 0 = sequence with no pages at this depth (Appendix C.4): O = 0, lse = -5e4

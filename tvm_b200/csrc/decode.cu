@@ -50,7 +50,11 @@ struct DecodeParams {
   float* part_lse;     // [2 * grid, group]
   int batch;
   int num_qo_heads;
-  int num_kv_heads;
+  int num_kv_heads;    // VIRTUAL kv heads = kv_heads_real * vsplit: what the partition, the items and the merge see
+  int kv_heads_real;   // heads of the page pool / the fused qkv tensor
+  int vsplit;          // GQA groups above 8 query heads per kv head are cut into `vsplit` virtual heads of 8 (the MMA holds 8
+                       // query heads per KV pass); virtual head v reads the pages of kv head v / vsplit -- a second pass
+                       // over the same pages, normally out of L2 (its item sits next to the first on the line)
   int group;  // Hq / Hkv
   // Balanced split-KV plan: the (sequence, kv head, page) triples in that order form one line of `total` page-heads
   // (sequence b, head h starts at page_indptr[b] * Hkv + h * np_b); CTA k owns [k * quota, (k + 1) * quota) -- every
@@ -193,7 +197,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
       // when the cache's RoPE mode is "none"
       const float qpos = static_cast<float>(p.q_rope_position[b]) * p.rope_scale;
       const T* qg = FUSED ? static_cast<const T*>(p.qkv) +
-                                (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.num_kv_heads) + h * g) * D
+                                (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.kv_heads_real) + h * g) * D
                           : static_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.num_qo_heads + h * g) * D;
       const bool rotate = !FUSED || p.fused_apply_rope;
       for (int it = threadIdx.x; it < g * (D / 2); it += blockDim.x) {
@@ -256,8 +260,8 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
         const uint32_t bar = bar_addr(warp, st);
         const uint32_t dst = stages_base + st * Cfg::kStageBytes;
         mbar_expect_tx(bar, Cfg::kStageBytes);
-        const int row_k = ((pid * 2 + 0) * p.num_kv_heads + h) * Cfg::kPage;
-        const int row_v = ((pid * 2 + 1) * p.num_kv_heads + h) * Cfg::kPage;
+        const int row_k = ((pid * 2 + 0) * p.kv_heads_real + h / p.vsplit) * Cfg::kPage;
+        const int row_v = ((pid * 2 + 1) * p.kv_heads_real + h / p.vsplit) * Cfg::kPage;
 #pragma unroll
         for (int hf = 0; hf < Cfg::kHalves; ++hf) {
           tma_load_2d(dst + hf * Cfg::kHalfBytes, &tmap, hf * 64, row_k, bar, kEvictFirst);
@@ -287,8 +291,8 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
           // decode step).  Anything else would silently attend to a stale row: fail loudly instead.
           if (p.append_slot[b] != pid * Cfg::kPage + r) __trap();
           const T* kn = static_cast<const T*>(p.qkv) +
-                        (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.num_kv_heads) + p.num_qo_heads + h) * D;
-          const T* vn = kn + static_cast<int64_t>(p.num_kv_heads) * D;
+                        (static_cast<int64_t>(b) * (p.num_qo_heads + 2 * p.kv_heads_real) + p.num_qo_heads + h / p.vsplit) * D;
+          const T* vn = kn + static_cast<int64_t>(p.kv_heads_real) * D;
           const int e0 = lane * 4;
           const bool lower = e0 < D / 2;
           uint2 kx = *reinterpret_cast<const uint2*>(kn + e0);
@@ -311,8 +315,8 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeParams p) {
           asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(kb + off), "r"(kx.x), "r"(kx.y) : "memory");
           asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(vb + off), "r"(vx.x), "r"(vx.y) : "memory");
           T* pg = static_cast<T*>(p.pages);
-          const int64_t row_k = ((static_cast<int64_t>(pid) * 2 + 0) * p.num_kv_heads + h) * Cfg::kPage + r;
-          const int64_t row_v = ((static_cast<int64_t>(pid) * 2 + 1) * p.num_kv_heads + h) * Cfg::kPage + r;
+          const int64_t row_k = ((static_cast<int64_t>(pid) * 2 + 0) * p.kv_heads_real + h / p.vsplit) * Cfg::kPage + r;
+          const int64_t row_v = ((static_cast<int64_t>(pid) * 2 + 1) * p.kv_heads_real + h / p.vsplit) * Cfg::kPage + r;
           *reinterpret_cast<uint2*>(pg + row_k * D + e0) = kx;
           *reinterpret_cast<uint2*>(pg + row_v * D + e0) = vx;
           fence_proxy_async();  // generic-proxy writes before the next TMA refill of this stage
@@ -872,8 +876,12 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   TVMB200_CHECK(page_size == 16, "attention_decode: page_size %d unsupported (the B200 path is built for 16-slot pages)", page_size);
   TVMB200_CHECK(head_dim == 128 || head_dim == 64, "attention_decode: head_dim %d unsupported (64 or 128)", head_dim);
   TVMB200_CHECK(num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0, "attention_decode: num_qo_heads %d not a multiple of num_kv_heads %d", num_qo_heads, num_kv_heads);
-  const int group = num_qo_heads / num_kv_heads;
-  TVMB200_CHECK(group <= 8, "attention_decode: GQA group size %d > 8 unsupported", group);
+  const int group_real = num_qo_heads / num_kv_heads;
+  TVMB200_CHECK(group_real <= 8 || group_real % 8 == 0, "attention_decode: GQA group size %d unsupported (up to 8, or a multiple of 8)", group_real);
+  const int vsplit = group_real > 8 ? group_real / 8 : 1;
+  const int group = group_real / vsplit;
+  const int32_t kv_heads_real = num_kv_heads;
+  num_kv_heads *= vsplit;  // virtual heads from here on (the tensor map below keeps the real count)
   TVMB200_CHECK(batch_size <= kMaxBatchSmem, "attention_decode: batch %d exceeds %d", batch_size, kMaxBatchSmem);
   TVMB200_CHECK(rotary_mode == 0 || rotary_mode == 1, "attention_decode: rotary_mode %d (0 or 1)", rotary_mode);
   if (batch_size <= 0) return 0;
@@ -916,6 +924,8 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
   p.batch = batch_size;
   p.num_qo_heads = num_qo_heads;
   p.num_kv_heads = num_kv_heads;
+  p.kv_heads_real = kv_heads_real;
+  p.vsplit = vsplit;
   p.group = group;
   p.total = total;
   p.quota = static_cast<int>(quota);
@@ -933,7 +943,7 @@ static int decode_entry(const void* q, const void* pages, const int32_t* page_in
     if (int rc = check_no_rope_variant("attention_decode (in-kernel RoPE)")) return rc;
 
   CUtensorMap tmap;
-  const uint64_t rows = static_cast<uint64_t>(num_pages) * 2 * num_kv_heads * page_size;
+  const uint64_t rows = static_cast<uint64_t>(num_pages) * 2 * kv_heads_real * page_size;
   if (int rc = get_tmap_2d_cached(&tmap, pages, dtype, rows, head_dim, 16)) return rc;
 
   if (dtype == TVMB200_F16) {
