@@ -434,18 +434,27 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // holds, maybe NaN bit patterns) become zeros: P is exactly 0 there but 0 * NaN = NaN.
           uint4* half = reinterpret_cast<uint4*>(sgen + SmemLayout::kv + vslot * kTileBytes + (warp - 2) * kHalfBytes);
           const int valid = (PAGED && j == it.n_kv - 1) ? it.kv_len - ((SPLIT ? it.j0 : 0) + j) * kKV : kKV;
-#pragma unroll 4
-          for (int e = lane; e < kHalfBytes / 16; e += 32) {
-            uint4 v = half[e];
-            if ((e >> 3) < valid) {  // 8 x 16 B per 128-byte row of the half
-              v.x = tc05::bf16x2_to_f16x2_sat(v.x);
-              v.y = tc05::bf16x2_to_f16x2_sat(v.y);
-              v.z = tc05::bf16x2_to_f16x2_sat(v.z);
-              v.w = tc05::bf16x2_to_f16x2_sat(v.w);
-            } else {
-              v = make_uint4(0u, 0u, 0u, 0u);
+          // eight 16-byte vectors per lane in flight: all loads, then the conversions, then all stores (written as a plain
+          // load / convert / store loop the in-place update serialises on shared-memory latency -- ncu showed the two
+          // converter warps busy for the whole KV-tile period of the paged kernel, the MMA warp waiting on V_CONV)
+          constexpr int kBatch = 8;
+          for (int e0 = lane; e0 < kHalfBytes / 16; e0 += 32 * kBatch) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) v[i] = half[e0 + 32 * i];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+              if (((e0 + 32 * i) >> 3) < valid) {  // 8 x 16 B per 128-byte row of the half
+                v[i].x = tc05::bf16x2_to_f16x2_sat(v[i].x);
+                v[i].y = tc05::bf16x2_to_f16x2_sat(v[i].y);
+                v[i].z = tc05::bf16x2_to_f16x2_sat(v[i].z);
+                v[i].w = tc05::bf16x2_to_f16x2_sat(v[i].w);
+              } else {
+                v[i] = make_uint4(0u, 0u, 0u, 0u);
+              }
             }
-            half[e] = v;
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) half[e0 + 32 * i] = v[i];
           }
           fence_proxy_async();  // generic-proxy writes before the tensor core (async proxy) reads the tile
           __syncwarp();
