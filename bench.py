@@ -70,6 +70,25 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
+# algorithmic work: pure functions, checked against the table's numbers in tests/test_bench_contract.py
+# ---------------------------------------------------------------------------------------------------
+def decode_bytes_of(B, L, Hq, Hkv, D, page=16, e=2):
+    """f_attention_decode: every KV byte once, q in, O / LSE out, the index arrays"""
+    nnz = B * (-(-L // page))
+    return B * L * Hkv * D * 2 * e + 2 * B * Hq * D * e + 4 * B * Hq + 4 * (nnz + 4 * B + 1)
+
+
+def append_bytes_of(n, Hkv, D, e=2):
+    """f_transpose_append: k, v read and written into their slots, the slot ids"""
+    return n * Hkv * D * 2 * e * 2 + 4 * n
+
+
+def causal_prefill_flops_of(nseq, L, Hq, D):
+    """4 * D * Hq * (# unmasked (q, k) pairs), empty cache"""
+    return 4 * D * Hq * nseq * (L * (L + 1) // 2)
+
+
+# ---------------------------------------------------------------------------------------------------
 # workloads
 # ---------------------------------------------------------------------------------------------------
 class DecodeWorkload:
@@ -112,12 +131,10 @@ class DecodeWorkload:
 
     # algorithmic bytes
     def decode_bytes(self):
-        e = 2
-        return (self.B * self.L * self.Hkv * self.D * 2 * e + 2 * self.B * self.Hq * self.D * e + 4 * self.B * self.Hq
-                + 4 * (self.nnz + 4 * self.B + 1))
+        return decode_bytes_of(self.B, self.L, self.Hq, self.Hkv, self.D, self.page)
 
     def append_bytes(self):
-        return self.B * self.Hkv * self.D * 2 * 2 * 2 + 4 * self.B
+        return append_bytes_of(self.B, self.Hkv, self.D)
 
     def step_bytes(self):
         """the fused step: f_attention_decode's bytes (q in, O / LSE out, every KV byte once, the index arrays) + the
@@ -173,7 +190,7 @@ class PrefillWorkload:
         self.sm_scale = D ** -0.5
 
     def flops(self):
-        return 4 * self.D * self.Hq * self.nseq * (self.L * (self.L + 1) // 2)
+        return causal_prefill_flops_of(self.nseq, self.L, self.Hq, self.D)
 
     def bytes(self):
         return (2 * self.n * self.Hq + 2 * self.n * self.Hkv) * self.D * 2 + 4 * self.n * self.Hq
@@ -206,7 +223,7 @@ class AppendWorkload:
         self.pos = torch.from_numpy(np.tile(np.arange(L, dtype=np.int32), nseq)).to(device)
 
     def append_bytes(self):
-        return self.n * self.Hkv * self.D * 2 * 2 * 2 + 4 * self.n
+        return append_bytes_of(self.n, self.Hkv, self.D)
 
     def rotary_append_bytes(self):
         # qkv read once; q, k, v written; k, v written into the pages; the two position arrays
@@ -502,7 +519,7 @@ def sub_prefill_c3(args, capi, dev, peaks, peak_src, dtype="bf16", seed=0):
 
 
 def w_flops_c3():
-    return 4 * 128 * 32 * 16 * (2048 * 2049 // 2)
+    return causal_prefill_flops_of(16, 2048, 32, 128)
 
 
 def sub_append_c3(args, capi, dev, peaks, peak_src):
