@@ -275,6 +275,13 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         ++n_q;
         for (int fl = 0; fl < 2 * it.n_kv; ++fl, ++fill) {
           const int j = (SPLIT ? it.j0 : 0) + (fl >> 1), is_v = fl & 1, slot = fill & (kSlots - 1);  // j: absolute KV tile
+          int pid = 0;
+          if (PAGED && lane < 16) {
+            // the page id does not depend on the ring slot: its load runs under the wait for the slot (the paged kernel's
+            // tile period is set by the loop slot free -> page id -> TMA from HBM -> [bf16: convert] -> PV -> slot free)
+            const int pi = min(j * 8 + (lane >> 1), it.n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
+            pid = __ldg(p.page_values + it.pg_beg + pi);
+          }
           mbar_wait(bar(KV_EMPTY + slot), ((fill / kSlots) & 1) ^ 1);
           const uint32_t dst = skv + slot * kTileBytes;
           if (!PAGED) {
@@ -290,8 +297,6 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             __syncwarp();
             if (lane < 16) {
               const int i = lane >> 1, hf = lane & 1;
-              const int pi = min(j * 8 + i, it.n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
-              const int pid = __ldg(p.page_values + it.pg_beg + pi);
               const int row = ((pid * 2 + is_v) * p.num_kv_heads + it.h) * 16;
               tma_load_2d(dst + hf * kHalfBytes + i * 16 * 128, &tm_k, hf * 64, row, bar(KV_FULL + slot), kEvictLast);
             }
