@@ -36,6 +36,7 @@
 #include "prefill.cuh"
 #include "tc05.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -67,20 +68,33 @@ template <typename PT>
 constexpr int kPolyPairsOf = 2;
 #endif
 
-struct SmemLayout {
+// NS = K / V tile slots: 4 = one ring K_j, V_j, K_j+1, V_j+1; 5 (VR3 instantiations) = a K ring of 2 + a V ring of 3
+template <int NS>
+struct SmemLayoutT {
   static constexpr int q = 0;
   static constexpr int kv = q + 2 * kTileBytes;
-  static constexpr int bars = kv + kSlots * kTileBytes;   // 30 mbarriers
-  static constexpr int tmem_ptr = bars + 256;
-  static constexpr int item = bars + 280;     // int[2]: work-item ring filled by the producer warp
-  static constexpr int scan = bars + 288;
+  static constexpr int bars = kv + NS * kTileBytes;   // 33 mbarriers
+  static constexpr int tmem_ptr = bars + 288;
+  static constexpr int item = bars + 304;     // int[2]: work-item ring filled by the producer warp
+  static constexpr int scan = bars + 320;
 };
 // S_FULL / P_READY / PV_DONE: one barrier per (tile, S half) = index 2 t + h.  The kernel is persistent, so every
 // barrier is used across work items: each role keeps running use counts and waits for parity (count & 1).
 enum Bar {
-  Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 5, S_FULL = 9, P_READY = 13, PV_DONE = 17, Q_EMPTY = 21, ITEM_FULL = 22,
-  ITEM_EMPTY = 24, V_CONV = 26, NUM_BARS = 30
+  Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 6, S_FULL = 11, P_READY = 15, PV_DONE = 19, Q_EMPTY = 23, ITEM_FULL = 24,
+  ITEM_EMPTY = 26, V_CONV = 28, NUM_BARS = 33   // KV_FULL / KV_EMPTY / V_CONV: one per tile slot (up to 5)
 };
+// The f-th K / V tile load of a CTA (K tiles even f, V tiles odd f) -> its slot and the parity of its use of that slot.
+// VR3: V tiles go round three slots of their own, so a V tile is requested two KV tiles ahead of its PV instead of one:
+// the paged bf16 kernel's tile period was set by the loop slot free -> TMA from HBM -> convert -> PV -> slot free.
+template <bool VR3>
+__device__ __forceinline__ int slot_of(uint32_t f) {
+  return VR3 ? ((f & 1) ? 2 + static_cast<int>((f >> 1) % 3u) : static_cast<int>((f >> 1) & 1u)) : static_cast<int>(f & 3u);
+}
+template <bool VR3>
+__device__ __forceinline__ uint32_t phase_of(uint32_t f) {
+  return VR3 ? ((f & 1) ? ((f >> 1) / 3u) & 1u : (f >> 2) & 1u) : (f >> 2) & 1u;
+}
 
 #ifdef TVMB200_TRACE
 // tuning aid: clock64 stamps of one CTA (role 0 = MMA warp, 1 / 2 = softmax warpgroup 0 / 1), [role][step][slot];
@@ -181,12 +195,14 @@ __device__ __forceinline__ Item decode_item(const PrefillParams& p, const int* s
 // per row, _kernel_common.py:130-144) and the token-tree mask on the trailing tree_len columns (an ancestor test per
 // (row, column), tree_attn.py:48-65).  SPLIT = true cuts every item's KV range into p.kv_splits parts that write fp32
 // partials.  Separate instantiations: the causal / mask-free kernel of the hot configuration keeps its registers.
-template <typename T, typename PT, bool PAGED, bool XMASK, bool SPLIT>
+template <typename T, typename PT, bool PAGED, bool XMASK, bool SPLIT, bool VR3 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p, const uint32_t idesc_qk,
                     const uint32_t idesc_pv, int* __restrict__ work_counter) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  using SmemLayout = SmemLayoutT<VR3 ? 5 : 4>;
+  constexpr int kNumSlots = VR3 ? 5 : 4;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -218,7 +234,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (!PAGED) tma_prefetch_desc(&tm_v);
     mbar_init(bar(Q_FULL), 1);
     mbar_init(bar(Q_EMPTY), 1);
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(bar(KV_FULL + i), 1);
       mbar_init(bar(KV_EMPTY + i), 1);
       mbar_init(bar(V_CONV + i), 2);
@@ -274,7 +290,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         ++n_q;
         for (int fl = 0; fl < 2 * it.n_kv; ++fl, ++fill) {
-          const int j = (SPLIT ? it.j0 : 0) + (fl >> 1), is_v = fl & 1, slot = fill & (kSlots - 1);  // j: absolute KV tile
+          const int j = (SPLIT ? it.j0 : 0) + (fl >> 1), is_v = fl & 1, slot = slot_of<VR3>(fill);  // j: absolute KV tile
           int pid = 0;
           if (PAGED && lane < 16) {
             // the page id does not depend on the ring slot: its load runs under the wait for the slot (the paged kernel's
@@ -282,7 +298,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const int pi = min(j * 8 + (lane >> 1), it.n_pages - 1);  // tail boxes re-read the last page (rows masked / zeroed)
             pid = __ldg(p.page_values + it.pg_beg + pi);
           }
-          mbar_wait(bar(KV_EMPTY + slot), ((fill / kSlots) & 1) ^ 1);
+          mbar_wait(bar(KV_EMPTY + slot), phase_of<VR3>(fill) ^ 1);
           const uint32_t dst = skv + slot * kTileBytes;
           if (!PAGED) {
             if (lane == 0) {
@@ -349,16 +365,16 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         auto ns = [&](int t) { return t ? it.ns1 : it.ns0; };
         mbar_wait(bar(Q_FULL), n_q & 1);
         ++n_q;
-        mbar_wait(bar(KV_FULL + (fill & (kSlots - 1))), (fill / kSlots) & 1);  // K_0
+        mbar_wait(bar(KV_FULL + slot_of<VR3>(fill)), phase_of<VR3>(fill));  // K_0
         tc05::fence_after_sync();
         if (tc05::elect_one()) {
           for (int t = 0; t < 2; ++t)
             if (ns(t) > 0) {
-              issue_qk(t, fill & (kSlots - 1));
+              issue_qk(t, slot_of<VR3>(fill));
               tc05::commit(bar(S_FULL + 2 * t));
               tc05::commit(bar(S_FULL + 2 * t + 1));
             }
-          tc05::commit(bar(KV_EMPTY + (fill & (kSlots - 1))));
+          tc05::commit(bar(KV_EMPTY + slot_of<VR3>(fill)));
           if (n_kv == 1) tc05::commit(bar(Q_EMPTY));  // no further QK^T in this item
         }
         __syncwarp();
@@ -367,9 +383,9 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // PV + QK occupy the tensor pipe while the other tile's warpgroup runs its softmax.
         for (int j = 0; j < n_kv; ++j) {
           const uint32_t fv = fill + 2 * j + 1, fk1 = fill + 2 * j + 2;
-          const int vslot = fv & (kSlots - 1), k1slot = fk1 & (kSlots - 1);
+          const int vslot = slot_of<VR3>(fv), k1slot = slot_of<VR3>(fk1);
           const bool more_k = j + 1 < n_kv;
-          mbar_wait(bar((kConvertV ? V_CONV : KV_FULL) + vslot), (fv / kSlots) & 1);
+          mbar_wait(bar((kConvertV ? V_CONV : KV_FULL) + vslot), phase_of<VR3>(fv));
           if (kConvertV) tc05::fence_after_sync();
           if (PAGED && !kConvertV && j == n_kv - 1) {
             // last tile: rows past kv_len of the V tile hold whatever is in the page (maybe NaN bit patterns);
@@ -385,7 +401,7 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               __syncwarp();
             }
           }
-          if (more_k) mbar_wait(bar(KV_FULL + k1slot), (fk1 / kSlots) & 1);
+          if (more_k) mbar_wait(bar(KV_FULL + k1slot), phase_of<VR3>(fk1));
           for (int t = 0; t < 2; ++t) {
             const int nst = ns(t);
             if (2 * j >= nst) continue;
@@ -432,8 +448,8 @@ prefill_tc05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const Item it = decode_item<PAGED, SPLIT>(p, s_tiles, id, n_items);
         for (int j = 0; j < it.n_kv; ++j) {
           const uint32_t fv = fill + 2 * j + 1;
-          const int vslot = fv & (kSlots - 1);
-          mbar_wait(bar(KV_FULL + vslot), (fv / kSlots) & 1);
+          const int vslot = slot_of<VR3>(fv);
+          mbar_wait(bar(KV_FULL + vslot), phase_of<VR3>(fv));
           // warp 2 owns the first 64-column half of the tile (16 KiB), warp 3 the second; the element-wise
           // conversion does not care about the 128B swizzle.  Rows past kv_len of a paged tile (whatever the page
           // holds, maybe NaN bit patterns) become zeros: P is exactly 0 there but 0 * NaN = NaN.
@@ -833,11 +849,25 @@ static int launch_tc05_t(const PrefillParams& p_in, const CUtensorMap& tq, const
   }
   const int64_t max_items = max_pairs * p.num_kv_heads * p.kv_splits;
   const int grid = static_cast<int>(max_items < num_sms() ? max_items : num_sms());  // persistent: one CTA per SM
-  const size_t smem = 1024 + SmemLayout::scan + (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
+  const size_t tail = (static_cast<size_t>(p.batch) + 1 + 40) * sizeof(int);
   const bool xmask = p.mask_mode == kMaskLayerSliding || p.mask_mode == kMaskTree;
   const bool split = p.kv_splits > 1;
+  // paged bf16 (pages come from HBM once, V passes through the converter warps): a V ring of three slots, when the fifth
+  // tile still fits next to the batch's scan array (227 KiB of shared memory per CTA).  TVMB200_PREFILL_VR3=0: A/B knob
+  constexpr bool kCanVr3 = PAGED && !std::is_same<T, PT>::value;
+  static const bool vr3_on = [] {
+    const char* e = getenv("TVMB200_PREFILL_VR3");
+    return !(e && atoi(e) == 0);
+  }();
+  const bool vr3 = kCanVr3 && vr3_on && 1024 + SmemLayoutT<5>::scan + tail <= 227 * 1024;
+  const size_t smem = 1024 + (vr3 ? SmemLayoutT<5>::scan : SmemLayoutT<4>::scan) + tail;
   auto kern = xmask ? (split ? prefill_tc05_kernel<T, PT, PAGED, true, true> : prefill_tc05_kernel<T, PT, PAGED, true, false>)
                     : (split ? prefill_tc05_kernel<T, PT, PAGED, false, true> : prefill_tc05_kernel<T, PT, PAGED, false, false>);
+  if constexpr (kCanVr3) {
+    if (vr3)
+      kern = xmask ? (split ? prefill_tc05_kernel<T, PT, PAGED, true, true, true> : prefill_tc05_kernel<T, PT, PAGED, true, false, true>)
+                   : (split ? prefill_tc05_kernel<T, PT, PAGED, false, true, true> : prefill_tc05_kernel<T, PT, PAGED, false, false, true>);
+  }
   TVMB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr uint32_t fa = std::is_same<T, __half>::value ? 0u : 1u;
   constexpr uint32_t fp = std::is_same<PT, __half>::value ? 0u : 1u;
