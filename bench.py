@@ -264,9 +264,10 @@ class TreeWorkload:
     MHACrossAttnInternal): tree-masked ragged self-attention over the new nodes, mask-free paged prefill over the
     committed context, f_merge_inplace."""
 
-    def __init__(self, B=32, L=32768, nodes=64, Hq=32, Hkv=8, D=128, page=16, seed=0, device="cuda"):
+    def __init__(self, B=32, L=32768, nodes=64, Hq=32, Hkv=8, D=128, page=16, seed=0, device="cuda", dtype="bf16"):
         import torch
 
+        tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
         self.B, self.L, self.nodes, self.Hq, self.Hkv, self.D = B, L, nodes, Hq, Hkv, D
         rng = np.random.default_rng(seed)
         n = B * nodes
@@ -276,7 +277,7 @@ class TreeWorkload:
         P = self.nnz + 1
         g = torch.Generator(device=device)
         g.manual_seed(seed)
-        self.pages = torch.randn((P, 2, Hkv, page, D), generator=g, device=device, dtype=torch.bfloat16)
+        self.pages = torch.randn((P, 2, Hkv, page, D), generator=g, device=device, dtype=tdt)
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(device)  # noqa: E731
         self.page_values = i32(rng.permutation(P)[: self.nnz])
         self.page_indptr = i32(np.arange(B + 1) * ppseq)
@@ -296,10 +297,10 @@ class TreeWorkload:
         self.mask = i32(np.concatenate([dfs_tree_mask(t) for t in trees]))
         self.indptr = i32(np.arange(B + 1) * nodes)
         self.qpos = i32(np.concatenate([L + np.array(d) for d in depth]))
-        self.q = torch.randn((n, Hq, D), generator=g, device=device, dtype=torch.bfloat16)
-        self.k = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
-        self.v = torch.randn((n, Hkv, D), generator=g, device=device, dtype=torch.bfloat16)
-        self.o = torch.empty((n, Hq, D), device=device, dtype=torch.bfloat16)
+        self.q = torch.randn((n, Hq, D), generator=g, device=device, dtype=tdt)
+        self.k = torch.randn((n, Hkv, D), generator=g, device=device, dtype=tdt)
+        self.v = torch.randn((n, Hkv, D), generator=g, device=device, dtype=tdt)
+        self.o = torch.empty((n, Hq, D), device=device, dtype=tdt)
         self.lse = torch.empty((n, Hq), device=device, dtype=torch.float32)
         self.o2, self.lse2 = torch.empty_like(self.o), torch.empty_like(self.lse)
         self.sm_scale = D ** -0.5
@@ -553,10 +554,10 @@ def sub_append_c3(args, capi, dev, peaks, peak_src):
     return out
 
 
-def sub_c5_tree_prefill(args, capi, dev, peaks, peak_src):
+def sub_c5_tree_prefill(args, capi, dev, peaks, peak_src, dtype="bf16"):
     import torch
 
-    w = TreeWorkload(device=dev)
+    w = TreeWorkload(device=dev, dtype=dtype)
     for _ in range(3):
         w.run(capi)
     torch.cuda.synchronize()
@@ -571,7 +572,7 @@ def sub_c5_tree_prefill(args, capi, dev, peaks, peak_src):
     sus = peaks.get("bf16_tflops_sustained")
     traffic, tsrc = ncu_traffic("c5_tree_prefill")
     out = {"metric": "prefill_tflops", "value": round(tf, 2), "unit": "TFLOP/s", "ms_per_step": round(ms, 4), "steps": K,
-           "windows": R, "windows_ms": windows, "dtype": "bf16",
+           "windows": R, "windows_ms": windows, "dtype": dtype,
            "config": {"workload": "C5 tree prefill: batch 32 x 64-node token trees (complete binary / random parents) over "
                                   "32768 cached tokens each, 32q/8kv, D128, page16; step = tree-masked ragged self part + "
                                   "mask-free paged part over the cache + merge (first tree round of the cache)",
@@ -789,7 +790,7 @@ def run_own(args):
 
     single = {"prefill": lambda: sub_prefill_c3(args, capi, dev, peaks, peak_src, dtype=args.dtype, seed=rank),
               "append": lambda: sub_append_c3(args, capi, dev, peaks, peak_src),
-              "c5": lambda: sub_c5_tree_prefill(args, capi, dev, peaks, peak_src),
+              "c5": lambda: sub_c5_tree_prefill(args, capi, dev, peaks, peak_src, dtype=args.dtype),
               "c5decode": lambda: sub_c5_decode(args, capi, dev, peaks, peak_src),
               "c4": lambda: sub_c4(args, capi, rank, world, dev, peaks, peak_src, dist)}
     if args.workload in single:
