@@ -435,7 +435,8 @@ def kv_transfer(remote_pages: list, k: np.ndarray, v: np.ndarray, remote_positio
         if pos == -1:
             continue
         for h in range(local_h):
-            pe, rh = _kv_transfer_target(local_h, remote_pages[0].shape[2], local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
+            remote_h = next(x for x in remote_pages if x is not None).shape[2]
+            pe, rh = _kv_transfer_target(local_h, remote_h, local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
             page = remote_pages[pe].shape[3]
             remote_pages[pe][pos // page, 0, rh, pos % page] = k[t, h]
             remote_pages[pe][pos // page, 1, rh, pos % page] = v[t, h]
@@ -450,6 +451,7 @@ def kv_transfer_page_to_page(remote_pages: list, local_pages: np.ndarray, remote
         if rpos == -1 or lpos == -1:
             continue
         for h in range(local_h):
-            pe, rh = _kv_transfer_target(local_h, remote_pages[0].shape[2], local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
+            remote_h = next(x for x in remote_pages if x is not None).shape[2]
+            pe, rh = _kv_transfer_target(local_h, remote_h, local_tp_rank, int(remote_tp_group_pe_offset[t]), h)
             for kv in (0, 1):
                 remote_pages[pe][rpos // page, kv, rh, rpos % page] = local_pages[lpos // page, kv, h, lpos % page]

@@ -261,3 +261,42 @@ def test_mark_send_of_a_partly_prefilled_sequence_goes_page_to_page(built_lib):
     gk, gv = _dump(recv, 7, first + second, 0)
     wk, wv = _dump(local, 7, first + second, 0)
     assert np.array_equal(gk[:, begin:], wk[:, begin:]) and np.array_equal(gv[:, begin:], wv[:, begin:])
+
+
+@pytest.mark.parametrize("page_to_page", [0, 1])
+def test_bound_packed_functions_have_the_nvshmem_signatures(built_lib, page_to_page):
+    """bind_kv_transfer(pool base pointers per PE, own PE, tp rank, page_to_page) -> a packed function with the reference's
+    nvshmem.KVTransfer / KVTransferPageToPage signature (kv_transfer.cu:139-257, :259-325): `remote_pages` is the caller's
+    own pool view of the LAYER (as in the reference test: a view at a byte offset into a [layers, ...] pool), whose offset
+    inside the pool selects the layer on every PE."""
+    import torch
+    import tvm_ffi
+    from tvm_ffi import Shape
+
+    from tvm_b200.build import LIB
+
+    rng = np.random.default_rng(83)
+    mod = tvm_ffi.load_module(str(LIB))
+    layers, layer_id, num_pages, hkv, page, d, n = 4, 1, 100, 4, 4, 128, len(POSITIONS)
+    pool0 = rand16(rng, (layers, num_pages, 2, hkv, page, d), "float16")
+    local = to_dev(pool0, "float16")          # PE 0: the sender's own pool
+    remote = to_dev(pool0, "float16")         # PE 1: the receiver's
+    f = mod["bind_kv_transfer"](Shape([local.data_ptr(), remote.data_ptr()]), 0, 0, page_to_page)
+    pos = np.array(POSITIONS, np.int32)
+    pe = np.ones(n, np.int32)
+    want = pool0.copy()
+    layer_view = tvm_ffi.from_dlpack(local[layer_id])
+    if not page_to_page:
+        k, v = rand16(rng, (n, hkv, d), "float16"), rand16(rng, (n, hkv, d), "float16")
+        f(layer_view, tvm_ffi.from_dlpack(to_dev(k, "float16")), tvm_ffi.from_dlpack(to_dev(v, "float16")),
+          tvm_ffi.from_dlpack(_i32(pos)), tvm_ffi.from_dlpack(_i32(pe)), None)
+        w = [None, want[layer_id]]
+        ok.kv_transfer(w, k, v, pos, pe)
+    else:
+        lpos = np.array(list(reversed(POSITIONS)), np.int32)
+        f(layer_view, layer_view, tvm_ffi.from_dlpack(_i32(pos)), tvm_ffi.from_dlpack(_i32(lpos)), tvm_ffi.from_dlpack(_i32(pe)), None)
+        w = [None, want[layer_id]]
+        ok.kv_transfer_page_to_page(w, pool0[layer_id], pos, lpos, pe)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(remote), want), "the receiver's pool differs (wrong layer offset or rows)"
+    assert np.array_equal(to_np(local), pool0), "the sender's own pool was touched"

@@ -1388,6 +1388,84 @@ int impl_bind_context(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
   TVMB200_VM_END();
 }
 
+// ---- nvshmem.KVTransfer / nvshmem.KVTransferPageToPage without NVSHMEM ---------------------------------------------------
+//   f = bind_kv_transfer(Shape(pe_0_ptr, pe_1_ptr, ...), local_tp_rank, page_to_page)
+// returns a Function with the REFERENCE's signature (src/runtime/extra/contrib/nvshmem/kv_transfer.cu:139-257, :259-325):
+//   f(remote_pages, k, v, remote_position_map, remote_tp_group_pe_offset, transfer_stream)                     (page_to_page 0)
+//   f(remote_pages, local_pages, remote_position_map, local_position_map, remote_tp_group_pe_offset, stream)   (page_to_page 1)
+// `remote_pages` is, as in the reference, the caller's OWN pool of the layer: only its geometry is read (shape[2] = the
+// receivers' kv heads per rank, shape[3] = page size), and its data pointer locates the layer inside the pool, so that one
+// table of pool BASE pointers per PE serves every layer (NVSHMEM's symmetric addressing: same offset on every PE).  A
+// maintainer registers the two results under `nvshmem.KVTransfer` / `nvshmem.KVTransferPageToPage`.
+struct BoundTransfer {
+  std::vector<void*> pe_base;   // base address of every PE's page pool (peer-mapped)
+  void* local_base;             // base address of this rank's own pool (pe_base[own pe]); layer offset = pages.data - local_base
+  int32_t local_tp_rank;
+  bool page_to_page;
+};
+int bound_transfer_call(void* self, const TVMFFIAny* a, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "nvshmem.KVTransfer";
+  BoundTransfer* b = static_cast<BoundTransfer*>(self);
+  TVMB200_FFI_BEGIN();
+  expect_nargs(n, 6, fn);
+  const Tensor pages = arg_tensor(a, 0, fn, "remote_pages");
+  if (pages.ndim() != 5) throw Err{"ValueError", fmt("%s: remote_pages must be [num_pages, 2, kv_heads, page_size, head_dim]", fn)};
+  const int dtype = kv_dtype(pages, fn, "remote_pages");
+  const int64_t layer_off = static_cast<char*>(pages.data) - static_cast<char*>(b->local_base);
+  std::vector<void*> table(b->pe_base.size());
+  for (size_t i = 0; i < table.size(); ++i) table[i] = b->pe_base[i] ? static_cast<char*>(b->pe_base[i]) + layer_off : nullptr;
+  void* stream = nullptr;
+  if (a[5].type_index == kTVMFFIOpaquePtr) stream = a[5].v_ptr;
+  else if (a[5].type_index == kTVMFFINone) stream = env_stream(pages.t->device.device_id);
+  else stream = reinterpret_cast<void*>(static_cast<uintptr_t>(arg_int(a, 5, fn, "transfer_stream")));
+  const int32_t remote_h = static_cast<int32_t>(pages.shape(2)), page = static_cast<int32_t>(pages.shape(3)),
+                d = static_cast<int32_t>(pages.shape(4));
+  if (!b->page_to_page) {
+    const Tensor k = arg_tensor(a, 1, fn, "k"), v = arg_tensor(a, 2, fn, "v"), pos = arg_tensor(a, 3, fn, "remote_position_map"),
+                 pe = arg_tensor(a, 4, fn, "remote_tp_group_pe_offset");
+    if (k.ndim() != 3 || v.ndim() != 3 || k.shape(2) != d) throw Err{"ValueError", fmt("%s: k / v must be [ntokens, kv_heads, head_dim]", fn)};
+    check_rc(tvmb200_kv_transfer(table.data(), k.data, v.data, static_cast<const int32_t*>(pos.data),
+                                 static_cast<const int32_t*>(pe.data), pos.shape(0), static_cast<int32_t>(k.shape(1)), remote_h, page,
+                                 d, b->local_tp_rank, static_cast<int32_t>(table.size()), dtype, stream));
+  } else {
+    const Tensor lp = arg_tensor(a, 1, fn, "local_pages"), rpos = arg_tensor(a, 2, fn, "remote_position_map"),
+                 lpos = arg_tensor(a, 3, fn, "local_position_map"), pe = arg_tensor(a, 4, fn, "remote_tp_group_pe_offset");
+    if (lp.ndim() != 5 || lp.shape(4) != d) throw Err{"ValueError", fmt("%s: local_pages must be a 5-d page pool of the same head_dim", fn)};
+    check_rc(tvmb200_kv_transfer_page_to_page(table.data(), lp.data, static_cast<const int32_t*>(rpos.data),
+                                              static_cast<const int32_t*>(lpos.data), static_cast<const int32_t*>(pe.data),
+                                              rpos.shape(0), static_cast<int32_t>(lp.shape(2)), remote_h, page, d, b->local_tp_rank,
+                                              static_cast<int32_t>(table.size()), dtype, stream));
+  }
+  TVMB200_FFI_END();
+}
+void bound_transfer_delete(void* self) { delete static_cast<BoundTransfer*>(self); }
+int impl_bind_kv_transfer(const TVMFFIAny* args, int32_t n, TVMFFIAny* result) {
+  static const char* fn = "bind_kv_transfer";
+  typedef int (*PFN_Create)(void*, TVMFFISafeCallType, void (*)(void*), TVMFFIObjectHandle*);
+  static PFN_Create create = reinterpret_cast<PFN_Create>(ffi_sym("TVMFFIFunctionCreate"));
+  TVMB200_VM_BEGIN();
+  expect_nargs(n, 4, fn);
+  if (!create) throw Err{"RuntimeError", "libtvm_ffi.so (TVMFFIFunctionCreate) is not loaded"};
+  const ShapeView ptrs = arg_shape(args, 0, fn, "pe_pool_base_pointers");
+  if (ptrs.size < 1 || ptrs.size > 64) throw Err{"ValueError", fmt("%s: 1..64 processing elements", fn)};
+  const int64_t own = arg_int(args, 1, fn, "own_pe");
+  if (own < 0 || own >= ptrs.size) throw Err{"ValueError", fmt("%s: own_pe %ld out of range", fn, (long)own)};
+  BoundTransfer* b = new BoundTransfer;
+  for (int64_t i = 0; i < ptrs.size; ++i) b->pe_base.push_back(reinterpret_cast<void*>(static_cast<uintptr_t>(ptrs[i])));
+  b->local_base = b->pe_base[static_cast<size_t>(own)];
+  b->local_tp_rank = static_cast<int32_t>(arg_int(args, 2, fn, "local_tp_rank"));
+  b->page_to_page = arg_int(args, 3, fn, "page_to_page") != 0;
+  TVMFFIObjectHandle h = nullptr;
+  if (create(b, bound_transfer_call, bound_transfer_delete, &h) != 0) {
+    delete b;
+    return -1;
+  }
+  result->type_index = kTVMFFIFunction;
+  result->zero_padding = 0;
+  result->v_obj = static_cast<TVMFFIObject*>(h);
+  TVMB200_VM_END();
+}
+
 }  // namespace
 
 #define TVMB200_EXPORT(name, impl)                                                                      \
@@ -1401,3 +1479,4 @@ TVMB200_CALLBACKS(TVMB200_EXPORT)
 TVMB200_EXPORT(context_create, impl_context_create)
 TVMB200_EXPORT(context_release, impl_context_release)
 TVMB200_EXPORT(bind_context, impl_bind_context)
+TVMB200_EXPORT(bind_kv_transfer, impl_bind_kv_transfer)
