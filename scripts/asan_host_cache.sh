@@ -3,7 +3,8 @@
 # (tvm_b200/lib/libtvm_b200_asan.so, selected by TVMB200_LIB_SUFFIX), replays every fixture + the error / limits tests on
 # planning-only caches and then runs 240 random programs (scripts/asan_fuzz_host_cache.py).  libstdc++ is preloaded next
 # to libasan so that ASan's __cxa_throw interceptor finds the real function inside a Python process.
-# Round 1 result: 43 tests + 240 programs + 14 boundary tests, no report.  Remove tvm_b200/lib/*_asan* afterwards.
+# Round 1 result: 43 tests + 240 programs + 14 boundary tests, no report; round 2 (with the disaggregation bookkeeping and the
+# scratch reservation): 46 tests + 240 programs + 16 boundary tests, no report.  Remove tvm_b200/lib/*_asan* afterwards.
 # The same recipe with TVMB200_LIB_SUFFIX=_ubsan, -fsanitize=undefined -fno-sanitize-recover=undefined and libubsan preloaded
 # (UndefinedBehaviorSanitizer) was run as well: no report either.
 set -e
